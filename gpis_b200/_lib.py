@@ -1,0 +1,97 @@
+"""ctypes binding of include/gpis_b200.h.  No CPU fallback: if the shared library is
+missing this raises, and gpis_create fails with GPIS_ERR_NO_DEVICE without a GPU."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpis_b200.so")
+
+GPIS_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_NOT_PD, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
+BETA_FIXED, BETA_GOTOVOS, BETA_SELECTCHOL = 0, 1, 2
+VAR_LATENT, VAR_PREDICTIVE = 0, 1
+PREC_FP64, PREC_TF32 = 0, 1
+
+# every symbol include/gpis_b200.h declares
+SYMBOLS = [
+    "gpis_version", "gpis_status_string", "gpis_last_error", "gpis_create", "gpis_destroy",
+    "gpis_set_candidates", "gpis_select", "gpis_select_begin", "gpis_step_append", "gpis_step_update",
+    "gpis_select_end", "gpis_exchange_buffers", "gpis_get_active", "gpis_get_factor", "gpis_fit",
+    "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
+]
+
+
+class GpisConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("dim", C.c_int32),
+        ("num_candidates", C.c_int64), ("total_candidates", C.c_int64), ("id_base", C.c_int64),
+        ("max_active", C.c_int32), ("use_gradients", C.c_int32), ("precision", C.c_int32),
+        ("beta_mode", C.c_int32), ("variance_mode", C.c_int32),
+        ("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32),
+        ("ell", C.c_double), ("sf2", C.c_double),
+        ("mean_w", C.c_double * 3), ("mean_c", C.c_double),
+        ("noise", C.c_double), ("level", C.c_double), ("eps", C.c_double), ("beta", C.c_double),
+        ("beta_delta", C.c_double),
+    ]
+
+
+class GpisError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"gpis_b200 status {status}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library (building nothing: run __graft_entry__.build() or
+    python -m gpis_b200.build first)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m gpis_b200.build` "
+                          "(there is no CPU fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64p, i32p, dp, u8p = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p
+    lib.gpis_version.restype = C.c_char_p
+    lib.gpis_status_string.restype = C.c_char_p
+    lib.gpis_status_string.argtypes = [C.c_int32]
+    lib.gpis_last_error.restype = C.c_char_p
+    lib.gpis_last_error.argtypes = [vp]
+    sig = {
+        "gpis_create": [C.POINTER(vp), C.POINTER(GpisConfig)],
+        "gpis_destroy": [vp],
+        "gpis_set_candidates": [vp, dp, dp, dp, dp, vp, vp],
+        "gpis_select": [vp, C.c_int64, C.c_int32, vp],
+        "gpis_select_begin": [vp, C.c_int64, vp],
+        "gpis_step_append": [vp, vp],
+        "gpis_step_update": [vp, vp],
+        "gpis_select_end": [vp, vp],
+        "gpis_exchange_buffers": [vp, C.POINTER(vp), C.POINTER(vp), i64p],
+        "gpis_get_active": [vp, vp, i32p, i32p, vp],
+        "gpis_get_factor": [vp, dp, C.c_int64, dp, i32p, vp],
+        "gpis_fit": [vp, dp, dp, dp, dp, C.c_int32, vp],
+        "gpis_predict": [vp, dp, C.c_int64, dp, dp, dp, vp],
+        "gpis_get_levelset": [vp, dp, u8p, u8p, u8p, vp],
+        "gpis_get_candidate_posterior": [vp, dp, dp, vp],
+        "gpis_get_stats": [vp, i64p, i64p, i64p, i64p],
+        "gpis_get_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int32
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, status):
+    if status != GPIS_OK:
+        msg = lib.gpis_status_string(status).decode()
+        if handle:
+            detail = lib.gpis_last_error(handle).decode()
+            if detail:
+                msg += ": " + detail
+        raise GpisError(status, msg)

@@ -1,0 +1,614 @@
+// C ABI of the GPIS engine (include/gpis_b200.h): host-side orchestration only.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/gpis_b200.h"
+#include "gpis_common.cuh"
+#include "gpis_predict.cuh"
+#include "gpis_select.cuh"
+
+using namespace gpis;
+
+struct gpis_engine {
+  gpis_config cfg;
+  int NB, D;
+  int device;
+  int num_sms;
+  EngineParams P;
+  std::vector<void*> allocs;
+  // device buffers
+  double* d_pts = nullptr;      // [D][N]
+  double* d_tsdf = nullptr;
+  double* d_nrm = nullptr;      // [D][N]
+  double* d_noise = nullptr;
+  long long* d_ids = nullptr;
+  double* d_Wt = nullptr;
+  double* d_alpha = nullptr;
+  long long ldw = 0, rk_pad = 0;
+  bool have_candidates = false, have_noise = false, have_ids = false;
+  bool selecting = false;
+  int inverse_rows = -1;        // rows Wt/alpha are valid for
+  int upd_grid = 0;
+  size_t upd_smem = 0;
+  cudaGraphExec_t step_graph = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double select_ms = 0.0, predict_ms = 0.0;
+  long long launches = 0;
+  std::string err;
+  DevState host_state;
+};
+
+namespace {
+
+const char* kVersion = "gpis_b200 0.1 (sm_100a)";
+
+gpis_status fail(gpis_engine* e, gpis_status s, const std::string& msg) {
+  if (e) e->err = msg;
+  return s;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(e, _e == cudaErrorMemoryAllocation ? GPIS_ERR_NOMEM : GPIS_ERR_CUDA,   \
+                  std::string(#call) + ": " + cudaGetErrorString(_e));                   \
+  } while (0)
+
+template <class T>
+cudaError_t dalloc(gpis_engine* e, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t r = cudaMalloc(&q, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+  if (r == cudaSuccess) { e->allocs.push_back(q); *p = static_cast<T*>(q); }
+  return r;
+}
+
+struct Dispatch {
+  void (*append)(EngineParams, int, int);
+  void (*update)(EngineParams);
+  void (*predict)(PredictParams);
+};
+
+template <int NB, int D>
+Dispatch make_dispatch() {
+  return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>};
+}
+
+Dispatch get_dispatch(int D, bool grad) {
+  switch (D * 2 + (grad ? 1 : 0)) {
+    case 2: return make_dispatch<1, 1>();
+    case 3: return make_dispatch<2, 1>();
+    case 4: return make_dispatch<1, 2>();
+    case 5: return make_dispatch<3, 2>();
+    case 6: return make_dispatch<1, 3>();
+    default: return make_dispatch<4, 3>();
+  }
+}
+
+constexpr size_t PRED_SMEM = (2 * PKC * PSB + 2 * PKC * PQ + 32 * PQ) * sizeof(double);
+
+gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int finalize_only) {
+  Dispatch d = get_dispatch(e->D, e->NB > 1);
+  d.append<<<1, APP_THREADS, 0, s>>>(e->P, external, finalize_only);
+  e->launches++;
+  CU(cudaGetLastError());
+  return GPIS_OK;
+}
+
+gpis_status launch_update(gpis_engine* e, cudaStream_t s) {
+  Dispatch d = get_dispatch(e->D, e->NB > 1);
+  d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
+  e->launches++;
+  CU(cudaGetLastError());
+  return GPIS_OK;
+}
+
+gpis_status read_state(gpis_engine* e, cudaStream_t s) {
+  CU(cudaMemcpyAsync(&e->host_state, e->P.st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (e->host_state.err == GPIS_ERR_NOT_PD)
+    return fail(e, GPIS_ERR_NOT_PD, "covariance block lost positive definiteness while appending a point");
+  return GPIS_OK;
+}
+
+// W = L^-1 (transposed) and alpha for the current model; cached per row count.
+gpis_status ensure_inverse(gpis_engine* e, cudaStream_t s) {
+  gpis_status rc = read_state(e, s);
+  if (rc != GPIS_OK) return rc;
+  const int R = e->host_state.r;
+  if (e->inverse_rows == R) return GPIS_OK;
+  CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
+  if (R > 0) {
+    const int blocks = (R * 32 + 255) / 256;
+    k_invert_factor<<<blocks, 256, 0, s>>>(e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
+    CU(cudaGetLastError());
+    k_alpha<<<blocks, 256, 0, s>>>(e->d_Wt, e->ldw, e->P.g, R, e->d_alpha);
+    CU(cudaGetLastError());
+    e->launches += 2;
+  }
+  e->inverse_rows = R;
+  return GPIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gpis_version(void) { return kVersion; }
+
+const char* gpis_status_string(gpis_status s) {
+  switch (s) {
+    case GPIS_OK: return "ok";
+    case GPIS_ERR_INVALID: return "invalid argument";
+    case GPIS_ERR_CUDA: return "CUDA error";
+    case GPIS_ERR_NOMEM: return "out of device memory";
+    case GPIS_ERR_STATE: return "call out of order";
+    case GPIS_ERR_NOT_PD: return "matrix not positive definite";
+    case GPIS_ERR_NO_DEVICE: return "no CUDA device (there is no CPU path)";
+    default: return "unknown status";
+  }
+}
+
+const char* gpis_last_error(gpis_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
+  if (!out || !cfg) return GPIS_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(gpis_config)) return GPIS_ERR_INVALID;
+  if (cfg->dim < 1 || cfg->dim > MAXD || cfg->num_candidates < 0 || cfg->max_active < 1) return GPIS_ERR_INVALID;
+  if (!(cfg->ell > 0.0) || !(cfg->sf2 > 0.0) || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return GPIS_ERR_INVALID;
+  if (cfg->precision != GPIS_PREC_FP64) return GPIS_ERR_INVALID;   // TF32 storage mode: not built yet
+  if (cfg->num_candidates > 0x7fffffffLL * TW / 2) return GPIS_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GPIS_ERR_NO_DEVICE; }
+  gpis_engine* e = new (std::nothrow) gpis_engine();
+  if (!e) return GPIS_ERR_NOMEM;
+  e->cfg = *cfg;
+  e->D = cfg->dim;
+  e->NB = cfg->use_gradients ? cfg->dim + 1 : 1;
+  gpis_status rc = GPIS_OK;
+  auto body = [&]() -> gpis_status {
+    if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
+    CU(cudaGetDevice(&e->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major < 10) return fail(e, GPIS_ERR_NO_DEVICE, "device is not sm_100 class");
+    e->num_sms = prop.multiProcessorCount;
+    EngineParams& P = e->P;
+    memset(&P, 0, sizeof(P));
+    const long long N = cfg->num_candidates;
+    const int D = e->D, NB = e->NB;
+    P.N = N;
+    P.N_total = cfg->total_candidates > 0 ? cfg->total_candidates : N;
+    P.id_base = cfg->id_base;
+    P.n_tiles = (int)((N + TW - 1) / TW);
+    P.M_cap = cfg->max_active;
+    P.R_cap = cfg->max_active * NB;
+    P.tile_stride = (long long)P.R_cap * TW;
+    P.rank = cfg->rank;
+    P.world = cfg->world_size;
+    P.inv_ell2 = 1.0 / (cfg->ell * cfg->ell);
+    P.sf2 = cfg->sf2;
+    P.level = cfg->level;
+    P.eps = cfg->eps;
+    P.beta = cfg->beta;
+    P.beta_delta = cfg->beta_delta;
+    P.noise_scalar = cfg->noise;
+    for (int d = 0; d < MAXD; ++d) P.mean_w[d] = d < D ? cfg->mean_w[d] : 0.0;
+    P.mean_c = cfg->mean_c;
+    P.beta_mode = cfg->beta_mode;
+    P.variance_mode = cfg->variance_mode;
+    P.pay_stride = PAY_HDR + P.R_cap;
+
+    const size_t Nn = (size_t)(N > 0 ? N : 1);
+    CU(dalloc(e, &e->d_pts, Nn * D));
+    CU(dalloc(e, &e->d_tsdf, Nn));
+    CU(dalloc(e, &e->d_nrm, Nn * D));
+    CU(dalloc(e, &e->d_noise, Nn));
+    CU(dalloc(e, &e->d_ids, Nn));
+    CU(dalloc(e, &P.mu, Nn));
+    CU(dalloc(e, &P.var, Nn));
+    CU(dalloc(e, &P.amb, Nn));
+    CU(dalloc(e, &P.flags, Nn));
+    CU(dalloc(e, &P.live[0], (size_t)P.n_tiles + 1));
+    CU(dalloc(e, &P.live[1], (size_t)P.n_tiles + 1));
+    CU(dalloc(e, &P.V, (size_t)P.n_tiles * (size_t)P.tile_stride));
+    CU(dalloc(e, &P.L, (size_t)P.R_cap * P.R_cap));
+    CU(dalloc(e, &P.g, (size_t)P.R_cap));
+    for (int d = 0; d < D; ++d) CU(dalloc(e, &P.AX[d], (size_t)P.M_cap));
+    CU(dalloc(e, &P.sel_ids, (size_t)P.M_cap + 1));
+    CU(dalloc(e, &P.st, 1));
+    CU(cudaMemset(P.st, 0, sizeof(DevState)));
+    CU(cudaMemset(P.L, 0, sizeof(double) * (size_t)P.R_cap * P.R_cap));
+    CU(dalloc(e, &P.pay_send, (size_t)P.pay_stride));
+    if (P.world > 1) CU(dalloc(e, &P.pay_recv, (size_t)P.pay_stride * P.world));
+    else P.pay_recv = P.pay_send;
+    CU(cudaMemset(P.pay_send, 0, sizeof(double) * P.pay_stride));
+    e->ldw = ((long long)P.R_cap + PSB - 1) / PSB * PSB;
+    e->rk_pad = ((long long)P.R_cap + PKC - 1) / PKC * PKC;
+    CU(dalloc(e, &e->d_Wt, (size_t)e->ldw * e->rk_pad));
+    CU(dalloc(e, &e->d_alpha, (size_t)P.R_cap));
+    for (int d = 0; d < D; ++d) { P.cx[d] = e->d_pts + (size_t)d * Nn; }
+    P.tsdf = e->d_tsdf;
+
+    // update kernel launch shape: persistent, a whole number of CTAs per SM
+    Dispatch disp = get_dispatch(D, NB > 1);
+    size_t max_ell = (size_t)96 * 1024 / (sizeof(double) * NB);
+    P.ell_chunk = (int)std::min<size_t>((size_t)P.R_cap, max_ell);
+    if (P.ell_chunk < 1) P.ell_chunk = 1;
+    e->upd_smem = sizeof(double) * NB * (size_t)P.ell_chunk;
+    CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
+    CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)disp.update, UPD_THREADS, e->upd_smem));
+    if (occ < 1) return fail(e, GPIS_ERR_CUDA, "update kernel does not fit on an SM");
+    e->upd_grid = e->num_sms * occ;
+    CU(dalloc(e, &P.partials, (size_t)e->upd_grid));
+    CU(cudaEventCreate(&e->ev0));
+    CU(cudaEventCreate(&e->ev1));
+    return GPIS_OK;
+  };
+  rc = body();
+  if (rc != GPIS_OK) {
+    // keep the message reachable through a static for the failed-create case
+    static thread_local std::string last;
+    last = e->err;
+    gpis_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return GPIS_OK;
+}
+
+gpis_status gpis_destroy(gpis_handle e) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+  return GPIS_OK;
+}
+
+gpis_status gpis_set_candidates(gpis_handle e, const double* pts, const double* tsdf, const double* normals,
+                                const double* noise, const int64_t* ids, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  if (N && (!pts || !tsdf)) return fail(e, GPIS_ERR_INVALID, "pts and tsdf are required");
+  if (e->NB > 1 && N && !normals) return fail(e, GPIS_ERR_INVALID, "use_gradients needs normals");
+  if (N) {
+    CU(cudaMemcpyAsync(e->d_pts, pts, sizeof(double) * N * e->D, cudaMemcpyDefault, s));
+    CU(cudaMemcpyAsync(e->d_tsdf, tsdf, sizeof(double) * N, cudaMemcpyDefault, s));
+    if (normals) CU(cudaMemcpyAsync(e->d_nrm, normals, sizeof(double) * N * e->D, cudaMemcpyDefault, s));
+    if (noise) CU(cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * N, cudaMemcpyDefault, s));
+    if (ids) CU(cudaMemcpyAsync(e->d_ids, ids, sizeof(long long) * N, cudaMemcpyDefault, s));
+  }
+  for (int d = 0; d < e->D; ++d) e->P.nrm[d] = normals ? e->d_nrm + (size_t)d * (N ? N : 1) : nullptr;
+  e->P.noise = noise ? e->d_noise : nullptr;
+  e->P.ids = ids ? e->d_ids : nullptr;
+  e->have_candidates = true;
+  e->selecting = false;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return GPIS_OK;
+}
+
+gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (!e->have_candidates) return fail(e, GPIS_ERR_STATE, "gpis_set_candidates has not been called");
+  if (first_local >= e->P.N) return fail(e, GPIS_ERR_INVALID, "first index out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = std::max<long long>(e->P.N, e->P.n_tiles);
+  if (n > 0) {
+    k_init_candidates<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->P);
+    CU(cudaGetLastError());
+    e->launches++;
+  }
+  k_begin<<<1, 32, 0, s>>>(e->P, first_local < 0 ? -1 : first_local);
+  CU(cudaGetLastError());
+  e->launches++;
+  e->selecting = true;
+  e->inverse_rows = -1;
+  return GPIS_OK;
+}
+
+gpis_status gpis_step_append(gpis_handle e, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
+  e->inverse_rows = -1;
+  return launch_append(e, (cudaStream_t)stream, 0, 0);
+}
+
+gpis_status gpis_step_update(gpis_handle e, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
+  return launch_update(e, (cudaStream_t)stream);
+}
+
+gpis_status gpis_select_end(gpis_handle e, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
+  return launch_append(e, (cudaStream_t)stream, 0, 1);
+}
+
+gpis_status gpis_exchange_buffers(gpis_handle e, void** send, void** recv, int64_t* bytes_per_rank) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (send) *send = e->P.pay_send;
+  if (recv) *recv = e->P.pay_recv;
+  if (bytes_per_rank) *bytes_per_rank = (int64_t)(e->P.pay_stride * sizeof(double));
+  return GPIS_OK;
+}
+
+gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (e->P.world != 1) return fail(e, GPIS_ERR_STATE, "gpis_select needs world_size == 1; drive the step calls");
+  if (K < 1 || K > e->P.M_cap) return fail(e, GPIS_ERR_INVALID, "K must be in 1..max_active");
+  if (first_local < 0) return fail(e, GPIS_ERR_INVALID, "first index out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaEventRecord(e->ev0, s));
+  gpis_status rc = gpis_select_begin(e, first_local, stream);
+  if (rc != GPIS_OK) return rc;
+  const int iters = K - 1;
+  if (iters > 0 && !e->step_graph) {
+    // capture one (append, update) pair; every argument is constant, all state is on the device
+    cudaStream_t cs = nullptr;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const long long l0 = e->launches;
+      ok = launch_append(e, cs, 0, 0) == GPIS_OK && launch_update(e, cs) == GPIS_OK;
+      e->launches = l0;
+      ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && ok && g;
+      if (ok) ok = cudaGraphInstantiate(&e->step_graph, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaStreamDestroy(cs);
+    if (!ok) { cudaGetLastError(); e->step_graph = nullptr; }
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (e->step_graph) {
+      CU(cudaGraphLaunch(e->step_graph, s));
+      e->launches += 2;
+    } else {
+      rc = launch_append(e, s, 0, 0);
+      if (rc != GPIS_OK) return rc;
+      rc = launch_update(e, s);
+      if (rc != GPIS_OK) return rc;
+    }
+  }
+  rc = gpis_select_end(e, stream);
+  if (rc != GPIS_OK) return rc;
+  CU(cudaEventRecord(e->ev1, s));
+  CU(cudaEventSynchronize(e->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+  e->select_ms = ms;
+  return read_state(e, s);
+}
+
+gpis_status gpis_get_active(gpis_handle e, int64_t* ids, int32_t* n_selected, int32_t* n_in_model, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  gpis_status rc = read_state(e, s);
+  if (rc != GPIS_OK) return rc;
+  if (n_selected) *n_selected = e->host_state.n_sel;
+  if (n_in_model) *n_in_model = e->host_state.m;
+  if (ids && e->host_state.n_sel > 0) {
+    CU(cudaMemcpyAsync(ids, e->P.sel_ids, sizeof(long long) * e->host_state.n_sel, cudaMemcpyDefault, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_factor(gpis_handle e, double* L, int64_t ldl, double* alpha, int32_t* rows, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  gpis_status rc = ensure_inverse(e, s);
+  if (rc != GPIS_OK) return rc;
+  const int R = e->host_state.r;
+  if (rows) *rows = R;
+  if (L && R > 0) {
+    if (ldl < R) return fail(e, GPIS_ERR_INVALID, "ldl smaller than the row count");
+    CU(cudaMemcpy2DAsync(L, sizeof(double) * ldl, e->P.L, sizeof(double) * e->P.R_cap, sizeof(double) * R, R,
+                         cudaMemcpyDefault, s));
+  }
+  if (alpha && R > 0) CU(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(double) * R, cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const double* normals,
+                     const double* noise, int32_t m, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (m < 0 || m > e->P.M_cap) return fail(e, GPIS_ERR_INVALID, "m must be in 0..max_active");
+  if (m && (!pts || !tsdf)) return fail(e, GPIS_ERR_INVALID, "pts and tsdf are required");
+  if (e->NB > 1 && m && !normals) return fail(e, GPIS_ERR_INVALID, "use_gradients needs normals");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = e->D;
+  // stage the training set on the host side as exchange records, one point per append
+  std::vector<double> hp((size_t)m * D), ht(m), hn((size_t)m * D, 0.0), hz(m, e->cfg.noise);
+  CU(cudaMemcpyAsync(hp.data(), pts, sizeof(double) * m * D, cudaMemcpyDefault, s));
+  CU(cudaMemcpyAsync(ht.data(), tsdf, sizeof(double) * m, cudaMemcpyDefault, s));
+  if (normals) CU(cudaMemcpyAsync(hn.data(), normals, sizeof(double) * m * D, cudaMemcpyDefault, s));
+  if (noise) CU(cudaMemcpyAsync(hz.data(), noise, sizeof(double) * m, cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  k_begin<<<1, 32, 0, s>>>(e->P, -1);
+  CU(cudaGetLastError());
+  e->launches++;
+  e->selecting = false;
+  e->inverse_rows = -1;
+  // records live in a staging array on the device; each append reads record 0 of pay_recv,
+  // so copy them in one by one (stream-ordered)
+  double* d_recs = nullptr;
+  CU(cudaMalloc(&d_recs, sizeof(double) * PAY_HDR * (size_t)(m > 0 ? m : 1)));
+  std::vector<double> recs((size_t)PAY_HDR * m, 0.0);
+  for (int i = 0; i < m; ++i) {
+    double* r = &recs[(size_t)i * PAY_HDR];
+    r[PAY_SCORE] = 0.0;
+    long long idv = i, loc = 0;
+    memcpy(&r[PAY_ID], &idv, 8);
+    memcpy(&r[PAY_LOCAL], &loc, 8);
+    r[PAY_TSDF] = ht[i];
+    r[PAY_NOISE] = hz[i];
+    for (int d = 0; d < D; ++d) { r[PAY_X + d] = hp[(size_t)d * m + i]; r[PAY_NRM + d] = hn[(size_t)d * m + i]; }
+  }
+  gpis_status rc = GPIS_OK;
+  cudaError_t ce = cudaMemcpyAsync(d_recs, recs.data(), sizeof(double) * recs.size(), cudaMemcpyHostToDevice, s);
+  EngineParams saved = e->P;
+  for (int i = 0; i < m && ce == cudaSuccess && rc == GPIS_OK; ++i) {
+    e->P.pay_recv = d_recs + (size_t)i * PAY_HDR;
+    e->P.world = 1;
+    e->P.rank = 0;
+    rc = launch_append(e, s, 1, 0);
+  }
+  e->P = saved;
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  cudaFree(d_recs);
+  if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
+  if (rc != GPIS_OK) return rc;
+  return read_state(e, s);
+}
+
+gpis_status gpis_predict(gpis_handle e, const double* query, int64_t nq, double* mean, double* var,
+                         double* normals, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (nq < 0 || (nq && (!query || !mean || !var))) return fail(e, GPIS_ERR_INVALID, "query, mean and var are required");
+  if (nq == 0) return GPIS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  gpis_status rc = ensure_inverse(e, s);
+  if (rc != GPIS_OK) return rc;
+  const int D = e->D;
+  // query / outputs may be host memory: stage through device buffers
+  cudaPointerAttributes at;
+  auto on_device = [&](const void* p) {
+    if (!p) return true;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+  };
+  const bool qd = on_device(query), od = on_device(mean) && on_device(var) && on_device(normals);
+  double *dq = nullptr, *dout = nullptr;
+  const size_t n = (size_t)nq;
+  auto cleanup = [&]() { if (dq) cudaFree(dq); if (dout) cudaFree(dout); };
+  if (!qd) {
+    cudaError_t ce = cudaMalloc(&dq, sizeof(double) * n * D);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(dq, query, sizeof(double) * n * D, cudaMemcpyHostToDevice, s);
+    if (ce != cudaSuccess) { cleanup(); return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce)); }
+  }
+  if (!od) {
+    cudaError_t ce = cudaMalloc(&dout, sizeof(double) * n * (2 + D));
+    if (ce != cudaSuccess) { cleanup(); return fail(e, GPIS_ERR_NOMEM, cudaGetErrorString(ce)); }
+  }
+  PredictParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.Wt = e->d_Wt;
+  Q.ldw = e->ldw;
+  Q.alpha = e->d_alpha;
+  const double* qsrc = qd ? query : dq;
+  for (int d = 0; d < D; ++d) { Q.AX[d] = e->P.AX[d]; Q.q[d] = qsrc + (size_t)d * n; }
+  Q.nq = nq;
+  Q.mean = od ? mean : dout;
+  Q.var = od ? var : dout + n;
+  for (int d = 0; d < D; ++d) Q.nrm[d] = normals ? (od ? normals + (size_t)d * n : dout + (2 + d) * n) : nullptr;
+  Q.R = e->host_state.r;
+  Q.inv_ell2 = e->P.inv_ell2;
+  Q.sf2 = e->P.sf2;
+  for (int d = 0; d < MAXD; ++d) Q.mean_w[d] = e->P.mean_w[d];
+  Q.mean_c = e->P.mean_c;
+  Dispatch disp = get_dispatch(D, e->NB > 1);
+  cudaEventRecord(e->ev0, s);
+  disp.predict<<<(unsigned)((nq + PQ - 1) / PQ), PRED_THREADS, PRED_SMEM, s>>>(Q);
+  cudaError_t ce = cudaGetLastError();
+  e->launches++;
+  cudaEventRecord(e->ev1, s);
+  if (ce == cudaSuccess && !od) {
+    ce = cudaMemcpyAsync(mean, dout, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(var, dout + n, sizeof(double) * n, cudaMemcpyDeviceToHost, s);
+    if (ce == cudaSuccess && normals)
+      ce = cudaMemcpyAsync(normals, dout + 2 * n, sizeof(double) * n * D, cudaMemcpyDeviceToHost, s);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  cleanup();
+  if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->predict_ms = ms;
+  return GPIS_OK;
+}
+
+namespace {
+__global__ void k_split_flags(const unsigned char* f, long long n, unsigned char* hi, unsigned char* lo,
+                              unsigned char* ac) {
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j < n) {
+    const unsigned char v = f[j];
+    if (hi) hi[j] = (v & F_HIGH) ? 1 : 0;
+    if (lo) lo[j] = (v & F_LOW) ? 1 : 0;
+    if (ac) ac[j] = (v & F_ACTIVE) ? 1 : 0;
+  }
+}
+}  // namespace
+
+gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, uint8_t* low, uint8_t* active,
+                              void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  if (!N) return GPIS_OK;
+  if (ambiguity) CU(cudaMemcpyAsync(ambiguity, e->P.amb, sizeof(double) * N, cudaMemcpyDefault, s));
+  if (high || low || active) {
+    unsigned char* tmp = nullptr;
+    CU(cudaMalloc(&tmp, 3 * N));
+    k_split_flags<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P.flags, (long long)N, tmp, tmp + N, tmp + 2 * N);
+    e->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess && high) ce = cudaMemcpyAsync(high, tmp, N, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && low) ce = cudaMemcpyAsync(low, tmp + N, N, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess && active) ce = cudaMemcpyAsync(active, tmp + 2 * N, N, cudaMemcpyDefault, s);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_candidate_posterior(gpis_handle e, double* mean, double* var, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  if (mean && N) CU(cudaMemcpyAsync(mean, e->P.mu, sizeof(double) * N, cudaMemcpyDefault, s));
+  if (var && N) CU(cudaMemcpyAsync(var, e->P.var, sizeof(double) * N, cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_stats(gpis_handle e, int64_t* kernel_launches, int64_t* live_tiles, int64_t* iterations,
+                           int64_t* panel_bytes) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (kernel_launches) *kernel_launches = e->launches;
+  if (live_tiles || iterations) {
+    gpis_status rc = read_state(e, 0);
+    if (rc != GPIS_OK && rc != GPIS_ERR_NOT_PD) return rc;
+    if (live_tiles) *live_tiles = e->host_state.n_live[e->host_state.iter & 1];
+    if (iterations) *iterations = e->host_state.iter;
+  }
+  if (panel_bytes) *panel_bytes = (int64_t)((size_t)e->P.n_tiles * (size_t)e->P.tile_stride * sizeof(double));
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (select_ms) *select_ms = e->select_ms;
+  if (predict_ms) *predict_ms = e->predict_ms;
+  return GPIS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Shared device/host definitions of the GPIS engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpis {
+
+constexpr int TW = 64;            // candidates per tile (one 512-byte fp64 row segment)
+constexpr int UPD_THREADS = 256;  // update kernel: 8 warps, each owns every 8th factor row
+constexpr int UPD_WARPS = UPD_THREADS / 32;
+constexpr int APP_THREADS = 512;  // append kernel (single CTA)
+constexpr int PAY_HDR = 16;       // exchange record header, in 8-byte slots
+constexpr int MAXD = 3;
+constexpr int MAXNB = MAXD + 1;
+
+constexpr unsigned char F_ACTIVE = 1, F_HIGH = 2, F_LOW = 4;
+
+// exchange record header slots
+enum { PAY_SCORE = 0, PAY_ID = 1, PAY_LOCAL = 2, PAY_TSDF = 3, PAY_NOISE = 4, PAY_X = 5, PAY_NRM = 8 };
+
+struct DevState {
+  int r;        // rows in the factor
+  int r0;       // rows before the block appended last (what the update kernel reads)
+  int m;        // points in the model
+  int n_sel;    // points selected (m, or m + 1 while the last pick is pending)
+  int done;     // selection stopped (nothing unclassified / capacity)
+  int iter;     // update iterations executed
+  int err;      // sticky device-side error (GPIS_ERR_*)
+  int n_live[2];
+  unsigned int blocks_done;
+  long long pending_id;
+  double nx[MAXD];          // point appended last
+  double Lnn[MAXNB * MAXNB];  // its diagonal block of L
+  double gnew[MAXNB];       // its entries of g = L^-1 (y - m)
+  double nnoise;
+};
+
+struct BlockBest {
+  double score;
+  long long id;
+  long long local;
+};
+
+struct EngineParams {
+  // candidates (this rank's shard)
+  const double* cx[MAXD];
+  const double* tsdf;
+  const double* nrm[MAXD];
+  const double* noise;     // per-point or null
+  const long long* ids;    // or null
+  long long id_base;
+  long long N;
+  long long N_total;
+  int n_tiles;
+  // panels of V = L^-1 K(rows, candidates): [tile][row][TW]
+  double* V;
+  long long tile_stride;   // R_cap * TW
+  double* mu;
+  double* var;
+  double* amb;
+  unsigned char* flags;
+  int* live[2];
+  // factor
+  double* L;               // [R_cap][R_cap] lower, row-major
+  double* g;               // L^-1 (y - m)
+  double* AX[MAXD];        // active points, SoA [M_cap]
+  long long* sel_ids;      // [M_cap + 1]
+  int R_cap, M_cap;
+  DevState* st;
+  BlockBest* partials;
+  double* pay_send;
+  double* pay_recv;
+  long long pay_stride;    // slots per record
+  int rank, world;
+  int ell_chunk;           // factor rows staged in shared memory per pass
+  // model
+  double inv_ell2, sf2, level, eps, beta, beta_delta, noise_scalar;
+  double mean_w[MAXD], mean_c;
+  int beta_mode, variance_mode;
+};
+
+__host__ __device__ inline long long cand_id(const EngineParams& P, long long j) {
+  return P.ids ? P.ids[j] : P.id_base + j;
+}
+
+}  // namespace gpis

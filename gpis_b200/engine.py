@@ -1,0 +1,200 @@
+"""Host-side handle over the C-ABI engine (include/gpis_b200.h).
+
+Arrays may be NumPy (host) or torch CUDA tensors (device); the C ABI takes either
+kind of pointer.  Points are given row-major (N, D) as in the reference's MATLAB
+structs and converted to the reference's SoA layout pts[i + d*N]
+(src/gpu_active_set_selector.cpp:96-101) here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+try:  # torch is plumbing only: device memory + streams
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _soa(x, n_cols=None):
+    """(N, D) -> contiguous (D, N) float64, NumPy or torch (kept on its device)."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        x = x.to(torch.float64)
+        if x.dim() == 1:
+            x = x[:, None]
+        return x.t().contiguous()
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[:, None]
+    return np.ascontiguousarray(x.T)
+
+
+def _vec(x, dtype=np.float64):
+    if x is None:
+        return None
+    if _is_torch(x):
+        tdt = {np.float64: torch.float64, np.int64: torch.int64}[dtype]
+        return x.to(tdt).contiguous().reshape(-1)
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype).reshape(-1))
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return C.c_void_p(x.ctypes.data)
+
+
+def _stream():
+    if torch is not None and torch.cuda.is_available():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(0)
+
+
+class GpisEngine:
+    """One engine = one candidate shard + one (replicated) active-set factor."""
+
+    def __init__(self, dim, num_candidates, max_active, *, ell, sf2=1.0, mean_w=None, mean_c=0.0,
+                 noise=0.01, level=0.0, eps=1e-2, beta=10.0, use_gradients=False,
+                 beta_mode=_lib.BETA_FIXED, beta_delta=0.01, variance_mode=_lib.VAR_LATENT,
+                 precision=_lib.PREC_FP64, rank=0, world_size=1, total_candidates=0, id_base=0, device=-1):
+        self.lib = _lib.load()
+        self.dim, self.N, self.max_active = int(dim), int(num_candidates), int(max_active)
+        self.use_gradients = bool(use_gradients)
+        self.nb = self.dim + 1 if self.use_gradients else 1
+        cfg = _lib.GpisConfig()
+        cfg.struct_size = C.sizeof(_lib.GpisConfig)
+        cfg.dim, cfg.num_candidates, cfg.max_active = self.dim, self.N, self.max_active
+        cfg.total_candidates, cfg.id_base = int(total_candidates), int(id_base)
+        cfg.use_gradients, cfg.precision = int(self.use_gradients), int(precision)
+        cfg.beta_mode, cfg.variance_mode = int(beta_mode), int(variance_mode)
+        cfg.rank, cfg.world_size, cfg.device = int(rank), int(world_size), int(device)
+        cfg.ell, cfg.sf2 = float(ell), float(sf2)
+        mw = np.zeros(3) if mean_w is None else np.asarray(mean_w, np.float64).reshape(-1)
+        for d in range(self.dim):
+            cfg.mean_w[d] = float(mw[d])
+        cfg.mean_c, cfg.noise = float(mean_c), float(noise)
+        cfg.level, cfg.eps, cfg.beta, cfg.beta_delta = float(level), float(eps), float(beta), float(beta_delta)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        st = self.lib.gpis_create(C.byref(self.h), C.byref(cfg))
+        if st != _lib.GPIS_OK:
+            self.h = C.c_void_p()
+            _lib.check(self.lib, None, st)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.gpis_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, st):
+        _lib.check(self.lib, self.h, st)
+
+    # ------------------------------------------------------------------ inputs
+    def set_candidates(self, points, tsdf, normals=None, noise=None, ids=None):
+        p, t = _soa(points), _vec(tsdf)
+        n, z, i = _soa(normals), _vec(noise), _vec(ids, np.int64)
+        assert p.shape == (self.dim, self.N), (p.shape, self.dim, self.N)
+        self._keep = (p, t, n, z, i)
+        self._ck(self.lib.gpis_set_candidates(self.h, _ptr(p), _ptr(t), _ptr(n), _ptr(z), _ptr(i), _stream()))
+
+    # ------------------------------------------------------------------ selection
+    def select(self, first_local, K):
+        self._ck(self.lib.gpis_select(self.h, int(first_local), int(K), _stream()))
+
+    def select_begin(self, first_local):
+        self._ck(self.lib.gpis_select_begin(self.h, int(first_local), _stream()))
+
+    def step_append(self):
+        self._ck(self.lib.gpis_step_append(self.h, _stream()))
+
+    def step_update(self):
+        self._ck(self.lib.gpis_step_update(self.h, _stream()))
+
+    def select_end(self):
+        self._ck(self.lib.gpis_select_end(self.h, _stream()))
+
+    def exchange_buffers(self):
+        s, r, b = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.lib.gpis_exchange_buffers(self.h, C.byref(s), C.byref(r), C.byref(b)))
+        return s.value, r.value, b.value
+
+    def active(self):
+        ids = np.zeros(self.max_active + 1, np.int64)
+        ns, nm = C.c_int32(), C.c_int32()
+        self._ck(self.lib.gpis_get_active(self.h, _ptr(ids), C.byref(ns), C.byref(nm), _stream()))
+        return ids[:ns.value].copy(), nm.value
+
+    def factor(self):
+        rows = C.c_int32()
+        self._ck(self.lib.gpis_get_factor(self.h, None, 0, None, C.byref(rows), _stream()))
+        R = rows.value
+        L, a = np.zeros((R, R)), np.zeros(R)
+        if R:
+            self._ck(self.lib.gpis_get_factor(self.h, _ptr(L), R, _ptr(a), C.byref(rows), _stream()))
+        return L, a
+
+    def fit(self, points, tsdf, normals=None, noise=None):
+        p, t, n, z = _soa(points), _vec(tsdf), _soa(normals), _vec(noise)
+        m = t.shape[0]
+        self._ck(self.lib.gpis_fit(self.h, _ptr(p), _ptr(t), _ptr(n), _ptr(z), m, _stream()))
+
+    # ------------------------------------------------------------------ outputs
+    def predict(self, query, want_normals=False, out_torch=None):
+        q = _soa(query)
+        nq = q.shape[1]
+        on_dev = _is_torch(q) and q.is_cuda if out_torch is None else out_torch
+        if on_dev:
+            dev = q.device if _is_torch(q) else torch.device("cuda")
+            mean = torch.empty(nq, dtype=torch.float64, device=dev)
+            var = torch.empty(nq, dtype=torch.float64, device=dev)
+            nrm = torch.empty((self.dim, nq), dtype=torch.float64, device=dev) if want_normals else None
+        else:
+            mean, var = np.empty(nq), np.empty(nq)
+            nrm = np.empty((self.dim, nq)) if want_normals else None
+        self._ck(self.lib.gpis_predict(self.h, _ptr(q), nq, _ptr(mean), _ptr(var), _ptr(nrm), _stream()))
+        if want_normals:
+            nrm = nrm.t() if on_dev else nrm.T
+        return mean, var, nrm
+
+    def levelset(self):
+        amb = np.empty(self.N)
+        hi, lo, ac = (np.empty(self.N, np.uint8) for _ in range(3))
+        self._ck(self.lib.gpis_get_levelset(self.h, _ptr(amb), _ptr(hi), _ptr(lo), _ptr(ac), _stream()))
+        return amb, hi.astype(bool), lo.astype(bool), ac.astype(bool)
+
+    def candidate_posterior(self):
+        mu, var = np.empty(self.N), np.empty(self.N)
+        self._ck(self.lib.gpis_get_candidate_posterior(self.h, _ptr(mu), _ptr(var), _stream()))
+        return mu, var
+
+    def stats(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.gpis_get_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"kernel_launches": a.value, "live_tiles": b.value, "iterations": c.value, "panel_bytes": d.value}
+
+    def timing(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.gpis_get_timing(self.h, C.byref(a), C.byref(b)))
+        return {"select_ms": a.value, "predict_ms": b.value}

@@ -1,0 +1,158 @@
+/* gpis_b200.h -- C ABI of the B200-native GPIS active-set-selection + prediction engine.
+ *
+ * Drop-in boundary for the reference's accelerated path.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference tree):
+ *
+ *   include/active_set_buffers.h:7-16, include/max_subset_buffers.h:7-12,
+ *   include/classification_buffers.h:7-8      construct_* / free_* / update_* / find_best_*
+ *   include/gpu_active_set_selector.hpp:32-47   GpuActiveSetSelector::SelectFromGrid / SelectChol
+ *   matlab/set_selection/select_active_set.m:1-2, select_active_set_straddle.m:1-147
+ *   matlab/core/create_gpis.m, gp_mean.m, gp_cov.m, predict_2d_grid.m
+ *
+ * Conventions (they fix the reference's: it printf()s and exit(0)s on error,
+ * include/cuda_macros.h:10-35, and never fills its output arrays):
+ *   - every call returns a gpis_status; nothing prints, nothing exits;
+ *   - every pointer argument may be a HOST or a DEVICE pointer (copies are
+ *     cudaMemcpyAsync(..., cudaMemcpyDefault) on the given stream); the engine owns all
+ *     of its device memory;
+ *   - layouts are struct-of-arrays exactly like the reference: pts[i + d*N]
+ *     (src/gpu_active_set_selector.cpp:96-101); normals likewise;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     calls are asynchronous on it unless they return values through host pointers,
+ *     in which case they synchronise the stream before returning;
+ *   - there is no CPU fallback: without a CUDA device gpis_create fails.
+ */
+#ifndef GPIS_B200_H
+#define GPIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpis_engine* gpis_handle;
+typedef int32_t gpis_status;
+
+enum {
+  GPIS_OK = 0,
+  GPIS_ERR_INVALID = -1,   /* bad argument / config                          */
+  GPIS_ERR_CUDA = -2,      /* CUDA runtime error (see gpis_last_error)       */
+  GPIS_ERR_NOMEM = -3,     /* device allocation failed                       */
+  GPIS_ERR_STATE = -4,     /* call out of order (e.g. select before set)     */
+  GPIS_ERR_NOT_PD = -5,    /* covariance block lost positive definiteness    */
+  GPIS_ERR_NO_DEVICE = -6  /* no usable CUDA device: there is no CPU path    */
+};
+
+enum { GPIS_BETA_FIXED = 0,      /* select_active_set_straddle.m:10 (varScale fixed)            */
+       GPIS_BETA_GOTOVOS = 1,    /* matlab/lse/discrete_gp_lse.m:87  2 log(N t pi^2/(6 delta))  */
+       GPIS_BETA_SELECTCHOL = 2  /* gpu_active_set_selector.cpp:493,550  2 log(N pi^2 (k+1)^2/(6 tol)) */ };
+enum { GPIS_VAR_LATENT = 0,      /* gp_cov.m:6 (beta = 0 on the test block)                     */
+       GPIS_VAR_PREDICTIVE = 1   /* max_subset_buffers.cu:113-115 (k(x,x) + noise - reduction)  */ };
+enum { GPIS_PREC_FP64 = 0, GPIS_PREC_TF32 = 1 };
+
+/* Replaces GaussianProcessHyperparams + the scalar arguments of SelectChol
+ * (include/active_set_selection_types.h:10-13, gpu_active_set_selector.hpp:41-46) and the
+ * MATLAB trainingParams / hyp structs (matlab/grasp_metric/setup_and_run_gpis_experiment.m:59-73). */
+typedef struct gpis_config {
+  int32_t struct_size;      /* = sizeof(gpis_config); ABI guard                              */
+  int32_t dim;              /* D, 1..3 (MAX_DIM_INPUT is 10 in the reference; GPIS uses 2,3) */
+  int64_t num_candidates;   /* N on THIS rank (a shard when world_size > 1)                  */
+  int64_t total_candidates; /* N over all ranks (beta schedules use it); 0 = num_candidates  */
+  int64_t id_base;          /* id of local candidate 0 when no explicit ids are given        */
+  int32_t max_active;       /* capacity in points (activeSetSize / maxSize)                  */
+  int32_t use_gradients;    /* normals observed: D+1 rows per point (se_cov_derivative.m)    */
+  int32_t precision;        /* GPIS_PREC_*                                                   */
+  int32_t beta_mode;        /* GPIS_BETA_*                                                   */
+  int32_t variance_mode;    /* GPIS_VAR_*                                                    */
+  int32_t rank, world_size; /* candidate sharding; the factor is replicated                  */
+  int32_t device;           /* CUDA device ordinal, -1 = current                             */
+  double ell, sf2;          /* covSEiso: sf2 * exp(-|x-z|^2 / (2 ell^2))                     */
+  double mean_w[3], mean_c; /* meanSum{meanLinear, meanConst}                                */
+  double noise;             /* scalar noise variance (exp(2*hyp.lik)) when no per-point noise */
+  double level, eps, beta;  /* trainingParams.levelSet / eps / beta                          */
+  double beta_delta;        /* delta (GOTOVOS) or tolerance (SELECTCHOL)                     */
+} gpis_config;
+
+const char* gpis_version(void);
+const char* gpis_status_string(gpis_status s);
+/* Text of the last error on this handle ("" if none). */
+const char* gpis_last_error(gpis_handle h);
+
+/* construct_active_set_buffers + construct_max_subset_buffers + construct_classification_buffers
+ * (active_set_buffers.cu:12-37, max_subset_buffers.cu:12-33, classification_buffers.cu:6-14). */
+gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg);
+/* free_*_buffers (same files). */
+gpis_status gpis_destroy(gpis_handle h);
+
+/* The H2D copy inside construct_max_subset_buffers (max_subset_buffers.cu:17-26) /
+ * shapeParams.{points,tsdf,normals,noise} of select_active_set_straddle.m:4-7.
+ * normals may be NULL iff use_gradients == 0; noise NULL = scalar cfg.noise;
+ * ids NULL = id_base + local index.  ids break ties (lowest wins) and are what
+ * gpis_get_active reports.  Resets any previous selection. */
+gpis_status gpis_set_candidates(gpis_handle h, const double* pts, const double* tsdf,
+                                const double* normals, const double* noise,
+                                const int64_t* ids, void* stream);
+
+/* GpuActiveSetSelector::SelectChol (gpu_active_set_selector.cpp:408-611) with the semantics
+ * of select_active_set_straddle.m:62-126: greedy loop entirely on the device, at most K
+ * points, stops early when nothing is unclassified.  first_local = local index of the first
+ * point (straddle.m:36-37 draws it at random; main.cpp:77 seeds rand()).  world_size must be 1;
+ * sharded runs drive the three step calls below and all-gather the exchange buffer between
+ * gpis_step_update and gpis_step_append. */
+gpis_status gpis_select(gpis_handle h, int64_t first_local, int32_t K, void* stream);
+
+gpis_status gpis_select_begin(gpis_handle h, int64_t first_local_or_neg, void* stream);
+/* update_active_set_buffers + SolveLinearSystemChol, as one incremental row append
+ * (active_set_buffers.cu:212-240, gpu_active_set_selector.cpp:892-917). */
+gpis_status gpis_step_append(gpis_handle h, void* stream);
+/* GpPredictCholBatch over all candidates + find_best_active_set_candidate, fused
+ * (gpu_active_set_selector.cpp:844-890, max_subset_buffers.cu:197-225). */
+gpis_status gpis_step_update(gpis_handle h, void* stream);
+/* Records the last pick (it is selected but, as in straddle.m:129-130, not in the model). */
+gpis_status gpis_select_end(gpis_handle h, void* stream);
+/* Per-rank exchange record: send = this rank's best candidate (score, id, point, its column
+ * of L^-1 K); recv = world_size such records, rank-major.  With world_size == 1 recv == send. */
+gpis_status gpis_exchange_buffers(gpis_handle h, void** send, void** recv, int64_t* bytes_per_rank);
+
+/* What SelectChol should have written to activeInputs/activeTargets and alpha.csv
+ * (gpu_active_set_selector.cpp:584-586; the arrays are never filled there).
+ * ids: selection order, n_selected entries (capacity max_active);
+ * n_in_model <= n_selected rows-in-points of the factor (straddle.m:129-130). */
+gpis_status gpis_get_active(gpis_handle h, int64_t* ids, int32_t* n_selected, int32_t* n_in_model,
+                            void* stream);
+/* Lower factor (Q = L L', point-major rows [f, d1 f, .., dD f] per point) into L[row*ldl + col],
+ * alpha = Q^-1 (y - m) in the same row order.  Either may be NULL.  rows = n_in_model*(D+1 or 1). */
+gpis_status gpis_get_factor(gpis_handle h, double* L, int64_t ldl, double* alpha, int32_t* rows,
+                            void* stream);
+
+/* create_gpis.m:1-101 on a given training set (create_dense_gpis.m): replaces the model
+ * with a dense fit on m points, appended in the given order.  SoA pts / normals. */
+gpis_status gpis_fit(gpis_handle h, const double* pts, const double* tsdf, const double* normals,
+                     const double* noise, int32_t m, void* stream);
+
+/* gp_mean.m + diag(gp_cov.m) (+ the mean's gradient, predict_2d_grid.m:12-16) at nq
+ * arbitrary points, SoA query[i + d*nq].  var is the latent variance.  normals
+ * (SoA D x nq) may be NULL. */
+gpis_status gpis_predict(gpis_handle h, const double* query, int64_t nq, double* mean, double* var,
+                         double* normals, void* stream);
+
+/* Level-set state of the candidates after selection: last ambiguity each candidate was
+ * scored with, and the high / low masks (straddle.m:121-125; ClassificationBuffers). */
+gpis_status gpis_get_levelset(gpis_handle h, double* ambiguity, uint8_t* high, uint8_t* low,
+                              uint8_t* active, void* stream);
+/* Running posterior of the candidates (exact for candidates still unclassified). */
+gpis_status gpis_get_candidate_posterior(gpis_handle h, double* mean, double* var, void* stream);
+
+/* Counters: kernels launched by this handle, live candidate tiles now, iterations run,
+ * bytes of the factor panels.  Any pointer may be NULL. */
+gpis_status gpis_get_stats(gpis_handle h, int64_t* kernel_launches, int64_t* live_tiles,
+                           int64_t* iterations, int64_t* panel_bytes);
+/* Device-side time of the last gpis_select / gpis_predict on their stream (CUDA events), ms,
+ * and the summed device time of the update kernel's launches when profiling is enabled. */
+gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPIS_B200_H */
