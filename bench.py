@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- GPIS active-set selection + posterior grid prediction on B200.
+
+One step = one complete pass of the hot path on BASELINE.json's headline workload
+(configs[2]): 128^3 synthetic box TSDF (2,097,152 candidates), 4000-point level-set active
+set selected greedily, then the full 128^3 posterior mean/variance grid.  It fits one GPU
+(the 67 GB panel store of L^-1 K lives in HBM), so N = 1 runs it whole; N > 1 shards the
+candidates and the query grid across ranks (weak = false: total work fixed -> "strong").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--grid G] [--active M]        (reduced sizes for development only)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HYP_ELL, NOISE, BETA, EPS, LEVEL = 4.0, 0.05, 10.0, 1e-2, 0.0
+
+
+def workload(grid, active):
+    from gpis_b200.synth import box_tsdf, first_index
+    pts, tsdf = box_tsdf(grid)
+    return pts, tsdf, first_index(pts.shape[0])
+
+
+def hyp_dict():
+    return {"cov": np.array([np.log(HYP_ELL), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(NOISE)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU path (NumPy restatement of the MATLAB code, all host threads through
+    OpenBLAS), on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as B
+    pts, tsdf, first = workload(args.grid, args.active)
+    N = pts.shape[0]
+    hyp = hyp_dict()
+    train = {"activeSetSize": args.active, "beta": BETA, "eps": EPS, "levelSet": LEVEL}
+    sel_steps = min(args.active - 1, args.ref_select_steps)
+    nq_sample = min(N, args.ref_predict_points)
+    rng = np.random.default_rng(1)
+    # prediction sample: a dense model of the full active-set size on surface-band points
+    band = np.flatnonzero(np.abs(tsdf) < 0.9)
+    sub = rng.choice(band, size=min(args.active, band.size), replace=False)
+    qidx = rng.choice(N, size=nq_sample, replace=False)
+
+    def one_step():
+        t0 = time.perf_counter()
+        sel = B.select_compact(pts, tsdf, hyp, train, first, max_steps=sel_steps)
+        t_sel = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        L, alpha = B.dense_model(pts[sub], tsdf[sub], hyp)
+        B.predict_dense(pts[sub], (L, alpha), pts[qidx], hyp)
+        t_pred = time.perf_counter() - t1
+        return t_sel, t_pred, sel
+
+    for _ in range(args.warmup_ref):
+        one_step()
+    ts, tp = [], []
+    for _ in range(args.steps):
+        a, b, sel = one_step()
+        ts.append(a); tp.append(b)
+    t_sel, t_pred = float(np.mean(ts)), float(np.mean(tp))
+    # extrapolate the sample to the whole job: selection cost per step is proportional to
+    # (candidates scored) x (rows); use the sample's own scored counts for the measured part and
+    # the dense bound for the rest (no pruning credit beyond the sample: an upper bound on the
+    # CPU time would flatter us, so the unscored remainder is charged at the LAST observed live
+    # count, i.e. assuming no further pruning).
+    scored = sel["scored"].astype(np.float64)
+    done_work = float(np.sum(scored * (np.arange(scored.size) + 1)))
+    rest = np.arange(scored.size, args.active - 1) + 1
+    total_work = done_work + float(scored[-1] * rest.sum()) if scored.size else 1.0
+    est_sel = t_sel * total_work / max(done_work, 1.0)
+    est_pred = t_pred * (N / nq_sample)
+    est_total = est_sel + est_pred
+    value = args.active / est_total
+    cores = os.cpu_count()
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup_ref, "ms_per_step": 1e3 * (t_sel + t_pred),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "grid_pts_per_s": N / est_pred, "select_pts_per_s": args.active / est_sel,
+        "cpu_baseline": {"value": value, "unit": "pts/s", "cores": cores, "kind": "port",
+                         "sample": (f"first {sel_steps} of {args.active - 1} selection steps over all {N} candidates "
+                                    f"({t_sel:.2f} s) + dense {sub.size}-point prediction of {nq_sample} of {N} grid "
+                                    f"points ({t_pred:.2f} s); whole-job time extrapolated (selection by scored-candidates x rows "
+                                    f"with no pruning credit past the sample, prediction linearly): {est_total:.0f} s")},
+        "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+METRIC = "active-set pts selected/s (step = 4000-pt LSE selection + full posterior grid, 128^3 TSDF)"
+
+
+def workload_config(args):
+    return {"workload": f"box TSDF {args.grid}^3 ({args.grid ** 3} candidates), SE ell={HYP_ELL} noise={NOISE}, "
+                        f"{args.active}-pt straddle active set (beta={BETA}, eps={EPS}) + full {args.grid}^3 posterior grid",
+            "grid": args.grid, "active_set": args.active, "precision": "fp64",
+            "l2": "inputs larger than L2 (panel store >> 126 MB); no explicit flush"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from gpis_b200 import GpisEngine
+    from gpis_b200 import dist as gdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pts, tsdf, first = workload(args.grid, args.active)
+    N, D, K = pts.shape[0], 3, args.active
+    lo, hi = gdist.shard_range(N, rank, world)
+    n_loc = hi - lo
+    # host buffers (pinned, SoA) for the end-to-end arm; device copies for the resident arm
+    h_pts = torch.from_numpy(np.ascontiguousarray(pts[lo:hi].T)).pin_memory()
+    h_tsdf = torch.from_numpy(np.ascontiguousarray(tsdf[lo:hi])).pin_memory()
+    d_pts, d_tsdf = h_pts.to(dev), h_tsdf.to(dev)
+    h_mean = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    h_var = torch.empty(n_loc, dtype=torch.float64).pin_memory()
+    d_mean = torch.empty(n_loc, dtype=torch.float64, device=dev)
+    d_var = torch.empty(n_loc, dtype=torch.float64, device=dev)
+
+    eng = GpisEngine(D, n_loc, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA,
+                     rank=rank, world_size=world, total_candidates=N, id_base=lo, device=local_rank)
+    eng.set_profiling(True)
+    sel = gdist.ShardedSelector(eng, rank, world, lo, hi)
+    sel.profile = True
+
+    def step(host):
+        P, T = (h_pts, h_tsdf) if host else (d_pts, d_tsdf)
+        eng.set_candidates(P, T, soa=True)
+        sel.select(first, K)
+        eng.predict_into(P, h_mean if host else d_mean, h_var if host else d_var)
+        if host:
+            ids, n_model = eng.active()
+            return ids, n_model
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = {"select_ms": 0.0, "predict_ms": 0.0, "update_ms": 0.0, "alg_bytes": 0.0, "panel_bytes": 0.0,
+               "update_launches": 0}
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            step(host)
+            t = eng.timing()
+            hst = eng.history()
+            acc["predict_ms"] += t["predict_ms"]
+            acc["update_ms"] += sel.last_update_ms
+            acc["update_launches"] += len(hst["rows"])
+            acc["select_ms"] += sel.last_select_ms
+            r, u, tl = hst["rows"].astype(np.float64), hst["scored"].astype(np.float64), hst["live_tiles"].astype(np.float64)
+            acc["alg_bytes"] += float(np.sum(8.0 * u * (r + 1) + u * (2 * 8 + 2)))
+            acc["panel_bytes"] += float(np.sum(8.0 * 64 * tl * (r + 1)))
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), acc
+
+    for _ in range(args.warmup):
+        step(False)
+    launches0 = eng.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, acc = timed(False, args.steps)
+    launches = eng.stats()["kernel_launches"] - launches0
+    step(True)                                   # warm the host-buffer path once
+    ms_e2e, _ = timed(True, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ids, n_model = eng.active()
+
+    # whole-job aggregates over ranks
+    tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"]], dtype=torch.float64, device=dev)
+    mx = torch.tensor([acc["update_ms"], acc["select_ms"], acc["predict_ms"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_sel = len(ids)
+    s_dev, s_e2e = ms_dev / 1e3 / args.steps, ms_e2e / 1e3 / args.steps
+    upd_s, sel_s, pred_s = (float(x) / 1e3 / args.steps for x in mx)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)) * world
+    achieved = float(tot[0]) / args.steps / upd_s / 1e9
+    R = n_model
+    out = {
+        "metric": METRIC, "value": n_sel / s_dev, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * s_dev, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / pred_s,
+        "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s},
+        "n_selected": n_sel, "n_in_model": n_model,
+        "e2e": {"value": n_sel / s_e2e, "unit": "pts/s", "ms_per_step": 1e3 * s_e2e,
+                "h2d_bytes_per_step": int(N * (D + 1) * 8 + N * D * 8),
+                "d2h_bytes_per_step": int(N * 2 * 8 + n_sel * 8)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_update (candidate update + straddle score + arg-max)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs x n_gpus" if peaks else "fallback 6650 GB/s",
+                     "traffic": None,
+                     "algorithmic_bytes_per_step": float(tot[0]) / args.steps,
+                     "panel_bytes_touched_per_step": float(tot[1]) / args.steps,
+                     "launches_per_step": acc["update_launches"] / args.steps,
+                     "predict_tflops_fp64": (N * float(R) * R + 2.0 * N * R) / pred_s / 1e12},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, pts, tsdf, first)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, pts, tsdf, first):
+    from oracle import cpu_baseline as B          # reported baseline only; never on the product path
+    hyp = hyp_dict()
+    train = {"activeSetSize": args.active, "beta": BETA, "eps": EPS, "levelSet": LEVEL}
+    N = pts.shape[0]
+    steps = min(args.active - 1, args.ref_select_steps)
+    sel = B.select_compact(pts, tsdf, hyp, train, first, max_steps=steps)
+    scored = sel["scored"].astype(np.float64)
+    done = float(np.sum(scored * (np.arange(scored.size) + 1)))
+    rest = np.arange(scored.size, args.active - 1) + 1
+    est_sel = sel["seconds"] * (done + float(scored[-1] * rest.sum())) / max(done, 1.0)
+    rng = np.random.default_rng(1)
+    band = np.flatnonzero(np.abs(tsdf) < 0.9)
+    sub = rng.choice(band, size=min(args.active, band.size), replace=False)
+    nq = min(N, args.ref_predict_points)
+    qidx = rng.choice(N, size=nq, replace=False)
+    t1 = time.perf_counter()
+    L, alpha = B.dense_model(pts[sub], tsdf[sub], hyp)
+    B.predict_dense(pts[sub], (L, alpha), pts[qidx], hyp)
+    t_pred = time.perf_counter() - t1
+    est = est_sel + t_pred * N / nq
+    return {"value": args.active / est, "unit": "pts/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": (f"first {steps} of {args.active - 1} selection steps over all {N} candidates "
+                       f"({sel['seconds']:.2f} s) + dense {sub.size}-pt prediction of {nq} grid points ({t_pred:.2f} s); "
+                       f"whole job extrapolated to {est:.0f} s (no pruning credit past the sample)")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=128)
+    ap.add_argument("--active", type=int, default=4000)
+    ap.add_argument("--ref-select-steps", type=int, default=120)
+    ap.add_argument("--ref-predict-points", type=int, default=16384)
+    ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.warmup_ref = min(args.warmup, 1)
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

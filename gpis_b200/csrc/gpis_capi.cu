@@ -39,7 +39,10 @@ struct gpis_engine {
   cudaGraphExec_t step_graph = nullptr;
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double select_ms = 0.0, predict_ms = 0.0;
+  double select_ms = 0.0, predict_ms = 0.0, update_ms = 0.0;
+  long long update_launches = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
   long long launches = 0;
   std::string err;
   DevState host_state;
@@ -226,6 +229,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     for (int d = 0; d < D; ++d) CU(dalloc(e, &P.AX[d], (size_t)P.M_cap));
     CU(dalloc(e, &P.sel_ids, (size_t)P.M_cap + 1));
     CU(dalloc(e, &P.st, 1));
+    CU(dalloc(e, &P.hist, 3 * ((size_t)P.M_cap + 1)));
+    CU(cudaMemset(P.hist, 0, sizeof(int) * 3 * ((size_t)P.M_cap + 1)));
     CU(cudaMemset(P.st, 0, sizeof(DevState)));
     CU(cudaMemset(P.L, 0, sizeof(double) * (size_t)P.R_cap * P.R_cap));
     CU(dalloc(e, &P.pay_send, (size_t)P.pay_stride));
@@ -273,6 +278,7 @@ gpis_status gpis_destroy(gpis_handle e) {
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return GPIS_OK;
@@ -357,7 +363,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   gpis_status rc = gpis_select_begin(e, first_local, stream);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
-  if (iters > 0 && !e->step_graph) {
+  if (iters > 0 && !e->step_graph && !e->profiling) {
     // capture one (append, update) pair; every argument is constant, all state is on the device
     cudaStream_t cs = nullptr;
     cudaGraph_t g = nullptr;
@@ -374,8 +380,23 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
     cudaStreamDestroy(cs);
     if (!ok) { cudaGetLastError(); e->step_graph = nullptr; }
   }
+  const bool prof = e->profiling;
+  if (prof) {
+    while ((int)e->prof_events.size() < 2 * iters) {
+      cudaEvent_t ev;
+      CU(cudaEventCreate(&ev));
+      e->prof_events.push_back(ev);
+    }
+  }
   for (int it = 0; it < iters; ++it) {
-    if (e->step_graph) {
+    if (prof) {
+      rc = launch_append(e, s, 0, 0);
+      if (rc != GPIS_OK) return rc;
+      CU(cudaEventRecord(e->prof_events[2 * it], s));
+      rc = launch_update(e, s);
+      if (rc != GPIS_OK) return rc;
+      CU(cudaEventRecord(e->prof_events[2 * it + 1], s));
+    } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
       e->launches += 2;
     } else {
@@ -392,6 +413,16 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->select_ms = ms;
+  e->update_ms = 0.0;
+  e->update_launches = 0;
+  if (prof) {
+    for (int it = 0; it < iters; ++it) {
+      float t = 0.f;
+      CU(cudaEventElapsedTime(&t, e->prof_events[2 * it], e->prof_events[2 * it + 1]));
+      e->update_ms += t;
+    }
+    e->update_launches = iters;
+  }
   return read_state(e, s);
 }
 
@@ -604,10 +635,34 @@ gpis_status gpis_get_stats(gpis_handle e, int64_t* kernel_launches, int64_t* liv
   return GPIS_OK;
 }
 
-gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms) {
+gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms, double* update_ms,
+                            int64_t* update_launches) {
   if (!e) return GPIS_ERR_INVALID;
   if (select_ms) *select_ms = e->select_ms;
   if (predict_ms) *predict_ms = e->predict_ms;
+  if (update_ms) *update_ms = e->update_ms;
+  if (update_launches) *update_launches = e->update_launches;
+  return GPIS_OK;
+}
+
+gpis_status gpis_set_profiling(gpis_handle e, int32_t on) {
+  if (!e) return GPIS_ERR_INVALID;
+  e->profiling = on != 0;
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_history(gpis_handle e, int32_t* rows, int32_t* live_tiles, int32_t* scored, int32_t* n) {
+  if (!e) return GPIS_ERR_INVALID;
+  gpis_status rc = read_state(e, 0);
+  if (rc != GPIS_OK && rc != GPIS_ERR_NOT_PD) return rc;
+  const int it = std::min(e->host_state.iter, e->P.M_cap + 1);
+  if (n) *n = it;
+  const size_t cap = (size_t)e->P.M_cap + 1;
+  if (it > 0) {
+    if (rows) CU(cudaMemcpy(rows, e->P.hist, sizeof(int) * it, cudaMemcpyDefault));
+    if (live_tiles) CU(cudaMemcpy(live_tiles, e->P.hist + cap, sizeof(int) * it, cudaMemcpyDefault));
+    if (scored) CU(cudaMemcpy(scored, e->P.hist + 2 * cap, sizeof(int) * it, cudaMemcpyDefault));
+  }
   return GPIS_OK;
 }
 

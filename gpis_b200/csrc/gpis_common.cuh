@@ -28,6 +28,7 @@ struct DevState {
   int err;      // sticky device-side error (GPIS_ERR_*)
   int n_live[2];
   unsigned int blocks_done;
+  int n_scored;  // candidates scored (unclassified at the start) in the running iteration
   long long pending_id;
   double nx[MAXD];          // point appended last
   double Lnn[MAXNB * MAXNB];  // its diagonal block of L
@@ -67,6 +68,7 @@ struct EngineParams {
   long long* sel_ids;      // [M_cap + 1]
   int R_cap, M_cap;
   DevState* st;
+  int* hist;               // [3][M_cap + 1]: rows read, live tiles, candidates scored, per iteration
   BlockBest* partials;
   double* pay_send;
   double* pay_recv;

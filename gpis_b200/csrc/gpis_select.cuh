@@ -95,6 +95,7 @@ __global__ void k_begin(EngineParams P, long long first_local) {
     st->n_live[0] = P.n_tiles;
     st->n_live[1] = 0;
     st->blocks_done = 0;
+    st->n_scored = 0;
     st->pending_id = -1;
   }
   write_record(P, first_local >= 0 ? __longlong_as_double(0x7ff0000000000000LL) : -__longlong_as_double(0x7ff0000000000000LL),
@@ -291,10 +292,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
   extern __shared__ double s_ell[];                 // [NB][ell_chunk]
   __shared__ double s_red[UPD_WARPS][NB][TW];
   __shared__ BlockBest s_best[2];
-  __shared__ int s_flag;
+  __shared__ int s_flag, s_cnt;
   DevState* st = P.st;
   if (st->done) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cnt = 0;
   const int r0 = st->r0;
   const int cur = st->iter & 1;
   const int n_live = st->n_live[cur];
@@ -381,7 +383,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
       const long long j = (long long)tile * TW + c;
       double sc = NEG_INF;
       long long id = 0x7fffffffffffffffLL;
-      bool still = false;
+      bool still = false, was_unc = false;
       if (j < P.N) {
         double tt[NB];
 #pragma unroll
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
         P.mu[j] = mu;
         unsigned char f = P.flags[j];
         if (!(f & (F_ACTIVE | F_HIGH | F_LOW))) {
+          was_unc = true;
           double ve = var;
           if (P.variance_mode == 1) ve = __dadd_rn(var, P.noise ? P.noise[j] : P.noise_scalar);
           const double w = __dmul_rn(sb, ve);                 // variance, not sigma: straddle.m:106-107
@@ -442,9 +445,11 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
         if (better(os, oid, sc, id)) { sc = os; id = oid; jj = oj; }
       }
       const unsigned any_still = __ballot_sync(0xffffffffu, still);
+      const unsigned scored = __ballot_sync(0xffffffffu, was_unc);
       if (lane == 0) {
         s_best[warp].score = sc; s_best[warp].id = id; s_best[warp].local = jj;
         if (any_still) atomicOr(&s_flag, 1);
+        if (scored) atomicAdd(&s_cnt, __popc(scored));
       }
     }
     __syncthreads();
@@ -462,6 +467,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
   __shared__ int s_last;
   if (tid == 0) {
     P.partials[blockIdx.x] = best;
+    if (s_cnt) atomicAdd(&st->n_scored, s_cnt);
     __threadfence();
     const unsigned ticket = atomicAdd(&st->blocks_done, 1u);
     s_last = (ticket == gridDim.x - 1);
@@ -490,6 +496,13 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
     for (int w = 1; w < UPD_WARPS; ++w)
       if (s_part[w].local >= 0 && better(s_part[w].score, s_part[w].id, b.score, b.id)) b = s_part[w];
     s_part[0] = b;
+    const int it = st->iter;
+    if (it <= P.M_cap) {
+      P.hist[it] = r0;
+      P.hist[(P.M_cap + 1) + it] = n_live;
+      P.hist[2 * (P.M_cap + 1) + it] = *(volatile int*)&st->n_scored;
+    }
+    st->n_scored = 0;
     st->n_live[cur] = 0;
     st->blocks_done = 0;
     st->iter = st->iter + 1;

@@ -1,0 +1,109 @@
+"""Multi-GPU host logic: candidates (and query points) are sharded across ranks in contiguous
+index ranges, the active set and its factor are replicated, and each selection step exchanges
+ONE fixed-size record per rank (best local candidate: score, id, point, its column of L^-1 K)
+with an all-gather.  Every rank then appends the same winner (max score, lowest id) to its
+replica of the factor, bit-identically -- no other collective is on the path.
+
+The reference has no multi-GPU code at all; this is new design.
+torch.distributed is plumbing only: NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def shard_range(n, rank, world):
+    """Contiguous split of n candidates in whole 64-candidate tiles (the panel granularity),
+    remainder to the last ranks' tiles; returns [lo, hi)."""
+    tiles = (n + 63) // 64
+    per, extra = divmod(tiles, world)
+    t0 = rank * per + min(rank, extra)
+    t1 = t0 + per + (1 if rank < extra else 0)
+    return min(t0 * 64, n), min(t1 * 64, n)
+
+
+def owner_of(index, n, world):
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        if lo <= index < hi:
+            return r, index - lo
+    raise IndexError(index)
+
+
+class _CudaView:
+    """Expose an engine-owned device buffer to torch through the CUDA array interface."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def engine_exchange_tensors(eng, world):
+    send_p, recv_p, nbytes = eng.exchange_buffers()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    send = torch.as_tensor(_CudaView(send_p, nbytes), device=dev)
+    recv = send if world == 1 else torch.as_tensor(_CudaView(recv_p, nbytes * world), device=dev)
+    return send, recv
+
+
+class ShardedSelector:
+    """Drives the greedy loop.  `eng` needs select_begin / step_append / step_update / select_end
+    (+ select for world == 1); `exchange` returns (send, recv) tensors for the all-gather."""
+
+    def __init__(self, eng, rank, world, lo, hi, exchange=None, group=None):
+        self.eng, self.rank, self.world, self.lo, self.hi = eng, rank, world, lo, hi
+        self.group = group
+        self.last_select_ms = 0.0
+        self.last_update_ms = 0.0
+        self.profile = False
+        self._ex = exchange
+        self._bufs = None
+
+    def _exchange(self):
+        if self._bufs is None:
+            self._bufs = self._ex(self.eng, self.world) if self._ex else engine_exchange_tensors(self.eng, self.world)
+        return self._bufs
+
+    def _gather(self):
+        send, recv = self._exchange()
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+
+    def select(self, first_index, K):
+        """first_index is GLOBAL.  Returns nothing; read results from the engine."""
+        if self.world == 1:
+            self.eng.select(first_index - self.lo, K)
+            t = getattr(self.eng, "timing", None)
+            if t:
+                tt = t()
+                self.last_select_ms, self.last_update_ms = tt["select_ms"], tt["update_ms"]
+            return
+        cuda = torch is not None and torch.cuda.is_available() and self._exchange()[0].is_cuda
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        mine = self.lo <= first_index < self.hi
+        self.eng.select_begin(first_index - self.lo if mine else -1)
+        self._gather()
+        prof = cuda and self.profile
+        evs = []
+        for _ in range(K - 1):
+            self.eng.step_append()
+            if prof:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            self.eng.step_update()
+            if prof:
+                b.record()
+                evs.append((a, b))
+            self._gather()
+        self.eng.select_end()
+        if cuda:
+            e1.record()
+            e1.synchronize()
+            self.last_select_ms = e0.elapsed_time(e1)
+            self.last_update_ms = float(sum(a.elapsed_time(b) for a, b in evs))

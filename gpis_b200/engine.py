@@ -112,9 +112,10 @@ class GpisEngine:
         _lib.check(self.lib, self.h, st)
 
     # ------------------------------------------------------------------ inputs
-    def set_candidates(self, points, tsdf, normals=None, noise=None, ids=None):
-        p, t = _soa(points), _vec(tsdf)
-        n, z, i = _soa(normals), _vec(noise), _vec(ids, np.int64)
+    def set_candidates(self, points, tsdf, normals=None, noise=None, ids=None, soa=False):
+        """soa=True: points / normals are already (D, N) contiguous float64 (no host transpose)."""
+        p, t = (points if soa else _soa(points)), _vec(tsdf)
+        n, z, i = (normals if soa else _soa(normals)), _vec(noise), _vec(ids, np.int64)
         assert p.shape == (self.dim, self.N), (p.shape, self.dim, self.N)
         self._keep = (p, t, n, z, i)
         self._ck(self.lib.gpis_set_candidates(self.h, _ptr(p), _ptr(t), _ptr(n), _ptr(z), _ptr(i), _stream()))
@@ -161,6 +162,12 @@ class GpisEngine:
         self._ck(self.lib.gpis_fit(self.h, _ptr(p), _ptr(t), _ptr(n), _ptr(z), m, _stream()))
 
     # ------------------------------------------------------------------ outputs
+    def predict_into(self, query_soa, mean, var, normals_soa=None):
+        """Raw form: (D, nq) contiguous query, preallocated outputs (host or device)."""
+        nq = query_soa.shape[1]
+        self._ck(self.lib.gpis_predict(self.h, _ptr(query_soa), nq, _ptr(mean), _ptr(var), _ptr(normals_soa),
+                                       _stream()))
+
     def predict(self, query, want_normals=False, out_torch=None):
         q = _soa(query)
         nq = q.shape[1]
@@ -195,6 +202,17 @@ class GpisEngine:
         return {"kernel_launches": a.value, "live_tiles": b.value, "iterations": c.value, "panel_bytes": d.value}
 
     def timing(self):
-        a, b = C.c_double(), C.c_double()
-        self._ck(self.lib.gpis_get_timing(self.h, C.byref(a), C.byref(b)))
-        return {"select_ms": a.value, "predict_ms": b.value}
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self.lib.gpis_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return {"select_ms": a.value, "predict_ms": b.value, "update_ms": c.value, "update_launches": n.value}
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.gpis_set_profiling(self.h, int(bool(on))))
+
+    def history(self):
+        cap = self.max_active + 1
+        rows, tiles, scored = (np.zeros(cap, np.int32) for _ in range(3))
+        n = C.c_int32()
+        self._ck(self.lib.gpis_get_history(self.h, _ptr(rows), _ptr(tiles), _ptr(scored), C.byref(n)))
+        k = n.value
+        return {"rows": rows[:k].copy(), "live_tiles": tiles[:k].copy(), "scored": scored[:k].copy()}

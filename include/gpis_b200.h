@@ -148,9 +148,18 @@ gpis_status gpis_get_candidate_posterior(gpis_handle h, double* mean, double* va
  * bytes of the factor panels.  Any pointer may be NULL. */
 gpis_status gpis_get_stats(gpis_handle h, int64_t* kernel_launches, int64_t* live_tiles,
                            int64_t* iterations, int64_t* panel_bytes);
-/* Device-side time of the last gpis_select / gpis_predict on their stream (CUDA events), ms,
- * and the summed device time of the update kernel's launches when profiling is enabled. */
-gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms);
+/* Device-side time of the last gpis_select / gpis_predict on their stream (CUDA events), ms;
+ * with profiling on (gpis_set_profiling) also the summed device time of the update kernel's
+ * launches in the last gpis_select and their count. */
+gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms, double* update_ms,
+                            int64_t* update_launches);
+/* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
+ * stream (plain launches instead of the captured graph). */
+gpis_status gpis_set_profiling(gpis_handle h, int32_t on);
+/* Per-iteration history of the last selection: factor rows read, live tiles processed and
+ * candidates scored (unclassified at the start of the iteration).  Arrays of capacity
+ * max_active + 1; n = iterations recorded. */
+gpis_status gpis_get_history(gpis_handle h, int32_t* rows, int32_t* live_tiles, int32_t* scored, int32_t* n);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,116 @@
+"""CPU baseline for bench.py: the oracle's incremental straddle selection, restated for speed
+(function-only observations, scalar noise), plus a dense prediction sample.
+
+TEST INFRASTRUCTURE / REPORTED BASELINE ONLY -- see oracle/__init__.py.  Same algorithm as
+oracle.gpis_oracle.select_straddle_incremental (which restates
+matlab/set_selection/select_active_set_straddle.m:62-126); tests/test_oracle_selection.py checks
+that both produce the same index sequence.  Differences are purely mechanical: the columns of
+V = L^-1 K(active, candidates) are kept compacted to the unclassified candidates (the reference
+only predicts on those, straddle.m:79-81,93-96) and re-compacted when a quarter of them has been
+classified, so BLAS works on contiguous memory with all host threads.
+"""
+import time
+
+import numpy as np
+import scipy.linalg as sla
+
+
+def select_compact(points, tsdf, hyp, train, first_index, max_steps=None, time_budget_s=None):
+    pts = np.asarray(points, np.float64)
+    y = np.asarray(tsdf, np.float64).reshape(-1)
+    N, D = pts.shape
+    ell2 = float(np.exp(np.float64(hyp["cov"][0])) ** 2)
+    sf2 = float(np.exp(2.0 * np.float64(hyp["cov"][1])))
+    noise = float(np.exp(2.0 * hyp["lik"]))
+    hm = np.asarray(hyp["mean"], np.float64).reshape(-1)
+    h, s, eps, K = float(train["levelSet"]), np.sqrt(float(train["beta"])), float(train["eps"]), int(train["activeSetSize"])
+    steps = K - 1 if max_steps is None else min(K - 1, int(max_steps))
+
+    cols = np.arange(N)                       # candidate index of each compact column
+    live = np.ones(N, bool)                   # per compact column: still unclassified & not active
+    P = pts.copy()
+    V = np.zeros((steps + 1, N))
+    mu = pts @ hm[:D] + hm[D]
+    var = np.full(N, sf2)
+    Lf = np.zeros((steps + 1, steps + 1))
+    g = np.zeros(steps + 1)
+    active_pos = {}
+    order = [int(first_index)]
+    pending = int(first_index)
+    pend_col = int(first_index)
+    live[pend_col] = False
+    t0 = time.perf_counter()
+    step_times = []
+    scored = []
+    r = 0
+    for it in range(steps):
+        ts = time.perf_counter()
+        # append the pending pick: its column of V is L^-1 k(active, x)
+        xnew = pts[pending]
+        ell = V[:r, pend_col].copy()
+        d = np.sqrt(sf2 + noise - ell @ ell)
+        Lf[r, :r] = ell
+        Lf[r, r] = d
+        g[r] = (y[pending] - (xnew @ hm[:D] + hm[D]) - ell @ g[:r]) / d
+        diff = P - xnew[None, :]
+        k = sf2 * np.exp(-np.einsum("ij,ij->i", diff, diff) / (2.0 * ell2))
+        vnew = (k - ell @ V[:r]) / d
+        V[r] = vnew
+        var -= vnew * vnew
+        mu += vnew * g[r]
+        r += 1
+        if not live.any():
+            break
+        hi = mu + s * var
+        lo = mu - s * var
+        amb = np.where(live, np.minimum(hi - h, h - lo), -np.inf)
+        scored.append(int(live.sum()))
+        mx = amb.max()
+        ties = np.flatnonzero(amb == mx)
+        b = ties[np.argmin(cols[ties])]                 # lowest candidate index among exact ties
+        pend_col, pending = int(b), int(cols[b])
+        order.append(pending)
+        cls = live & ((lo + eps > h) | (hi - eps < h))
+        live[cls] = False
+        live[b] = False
+        # re-compact when a quarter of the stored columns is dead (keep the pending column)
+        if live.sum() + 1 < 0.75 * live.size:
+            keep = live.copy()
+            keep[b] = True
+            idx = np.flatnonzero(keep)
+            V = np.ascontiguousarray(V[:, idx])
+            P, cols, mu, var, live = P[idx], cols[idx], mu[idx], var[idx], live[idx]
+            pend_col = int(np.flatnonzero(cols == pending)[0])
+        step_times.append(time.perf_counter() - ts)
+        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
+            break
+    return {"order": np.asarray(order), "n_in_model": r, "L": Lf[:r, :r], "g": g[:r],
+            "seconds": time.perf_counter() - t0, "step_seconds": np.asarray(step_times),
+            "scored": np.asarray(scored), "X": pts[np.asarray(order[:r])]}
+
+
+def predict_dense(X, yres_alpha_L, query, hyp):
+    """gp_mean + diag(gp_cov) at `query` for a function-only model given (L lower, alpha)."""
+    L, alpha = yres_alpha_L
+    ell2 = float(np.exp(np.float64(hyp["cov"][0])) ** 2)
+    sf2 = float(np.exp(2.0 * np.float64(hyp["cov"][1])))
+    hm = np.asarray(hyp["mean"], np.float64).reshape(-1)
+    D = X.shape[1]
+    d2 = (np.sum(X * X, axis=1)[:, None] + np.sum(query * query, axis=1)[None, :] - 2.0 * X @ query.T)
+    Ks = sf2 * np.exp(-np.maximum(d2, 0.0) / (2.0 * ell2))
+    mu = query @ hm[:D] + hm[D] + alpha @ Ks
+    W = sla.solve_triangular(L, Ks, lower=True, overwrite_b=True, check_finite=False)
+    return mu, sf2 - np.einsum("ij,ij->j", W, W)
+
+
+def dense_model(X, y, hyp):
+    ell2 = float(np.exp(np.float64(hyp["cov"][0])) ** 2)
+    sf2 = float(np.exp(2.0 * np.float64(hyp["cov"][1])))
+    noise = float(np.exp(2.0 * hyp["lik"]))
+    hm = np.asarray(hyp["mean"], np.float64).reshape(-1)
+    D = X.shape[1]
+    d2 = (np.sum(X * X, axis=1)[:, None] + np.sum(X * X, axis=1)[None, :] - 2.0 * X @ X.T)
+    Q = sf2 * np.exp(-np.maximum(d2, 0.0) / (2.0 * ell2)) + noise * np.eye(X.shape[0])
+    L = np.linalg.cholesky(Q)
+    alpha = sla.cho_solve((L, True), y - (X @ hm[:D] + hm[D]))
+    return L, alpha

@@ -58,3 +58,22 @@ def test_function_only_3d_literal_equals_incremental():
     assert np.array_equal(inc["order"], inc2["order"])
     # early steps tie EXACTLY (unobserved points all score sqrt(beta)); lowest index wins on both
     assert lit["min_top2_gap"] == 0.0
+
+
+def test_cpu_baseline_restatement_matches_oracle_sequence():
+    """The speed-oriented baseline used by bench.py picks the same points as the oracle."""
+    from oracle import cpu_baseline as B
+    from gpis_b200.synth import sphere_tsdf
+    pts, tsdf = sphere_tsdf(14, trunc=3.0)
+    hyp = {"cov": np.array([np.log(2.5), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
+    tr = {"activeSetSize": 120, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental({"points": pts, "tsdf": tsdf, "normals": None, "noise": None}, tr, 99, hyp=hyp)
+    fast = B.select_compact(pts, tsdf, hyp, tr, 99)
+    assert np.array_equal(ora["order"], fast["order"])
+    assert fast["n_in_model"] == ora["n_in_model"]
+    assert np.max(np.abs(fast["L"] - ora["gp"].L[:ora["gp"].r, :ora["gp"].r])) < 1e-10
+    # dense prediction sample agrees with the oracle's predict
+    L, alpha = B.dense_model(fast["X"], tsdf[fast["order"][:fast["n_in_model"]]], hyp)
+    mu, var = B.predict_dense(fast["X"], (L, alpha), pts[:500], hyp)
+    m2, v2, _ = O.predict_points(ora["gp"], pts[:500])
+    assert np.max(np.abs(mu - m2)) < 1e-8 and np.max(np.abs(var - v2)) < 1e-8
