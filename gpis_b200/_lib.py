@@ -15,7 +15,7 @@ PREC_FP64, PREC_TF32 = 0, 1
 # every symbol include/gpis_b200.h declares
 SYMBOLS = [
     "gpis_version", "gpis_status_string", "gpis_last_error", "gpis_create", "gpis_destroy",
-    "gpis_set_candidates", "gpis_select", "gpis_select_begin", "gpis_step_append", "gpis_step_update",
+    "gpis_set_candidates", "gpis_set_grid_candidates", "gpis_select", "gpis_select_begin", "gpis_step_append", "gpis_step_update",
     "gpis_select_end", "gpis_exchange_buffers", "gpis_get_active", "gpis_get_factor", "gpis_fit",
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history",
@@ -65,6 +65,7 @@ def load():
         "gpis_create": [C.POINTER(vp), C.POINTER(GpisConfig)],
         "gpis_destroy": [vp],
         "gpis_set_candidates": [vp, dp, dp, dp, dp, vp, vp],
+        "gpis_set_grid_candidates": [vp, vp, vp, vp, C.c_int32, C.c_int32, dp, dp, dp, vp],
         "gpis_select": [vp, C.c_int64, C.c_int32, vp],
         "gpis_select_begin": [vp, C.c_int64, vp],
         "gpis_step_append": [vp, vp],

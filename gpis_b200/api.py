@@ -115,7 +115,31 @@ def predict_grid(gpModel, dims, want_normals=False):
     return {"dims": tuple(dims), "points": pts, "tsdf": mu, "noise": var, "normals": nrm}
 
 
-def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hyp=None, predict=True):
+def detect_lattice(points):
+    """(dims, origin, spacing) if `points` is a full regular lattice listed x fastest
+    (IJK_TO_LINEAR, active_set_selection_types.h:6), else None."""
+    pts = np.asarray(points, np.float64)
+    N, D = pts.shape
+    dims, org, sp = [], [], []
+    for d in range(D):
+        u = np.unique(pts[:, d])
+        h = (u[-1] - u[0]) / (u.size - 1) if u.size > 1 else 1.0
+        if u.size > 1 and not np.allclose(np.diff(u), h, rtol=0, atol=1e-12 * max(1.0, abs(h))):
+            return None
+        dims.append(int(u.size)); org.append(float(u[0])); sp.append(float(h))
+    if int(np.prod(dims)) != N:
+        return None
+    idx, stride = np.arange(N), 1
+    for d in range(D):
+        jd = (idx // stride) % dims[d]
+        stride *= dims[d]
+        if not np.allclose(org[d] + sp[d] * jd, pts[:, d], rtol=0, atol=1e-12 * max(1.0, abs(sp[d]))):
+            return None
+    return dims, org, sp
+
+
+def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hyp=None, predict=True,
+                               backend="auto"):
     """select_active_set_straddle.m:1-147 on the GPU engine.
 
     shapeParams: points (N,D), tsdf (N,), normals (N,D) or None/empty, noise (N,) or None/empty
@@ -135,7 +159,14 @@ def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hy
     eng = GpisEngine(D, N, K, use_gradients=use_grad, level=float(trainingParams["levelSet"]),
                      eps=float(trainingParams["eps"]), beta=float(trainingParams["beta"]),
                      **_hyp_to_cfg(hyp, D))
-    eng.set_candidates(pts, tsdf, normals if use_grad else None, noise if use_noise else None)
+    lat = detect_lattice(pts) if backend in ("auto", "grid") else None
+    if backend == "grid" and lat is None:
+        raise ValueError("backend='grid' needs a full regular lattice listed x fastest")
+    if lat is not None:
+        eng.set_grid_candidates(lat[0], lat[1], lat[2], tsdf, normals if use_grad else None,
+                                noise if use_noise else None)
+    else:
+        eng.set_candidates(pts, tsdf, normals if use_grad else None, noise if use_noise else None)
     eng.select(first, K)
     ids, n_in_model = eng.active()
     mids = ids[:n_in_model]
@@ -144,6 +175,7 @@ def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hy
                         np.asarray(normals, np.float64).reshape(N, D)[mids] if use_grad else None, nz, mids)
     model["order"] = ids
     model["n_in_model"] = n_in_model
+    model["backend"] = "grid" if lat is not None else "panel"
     active = np.zeros(N, bool)
     active[ids] = True
     test = np.flatnonzero(~active)                                      # straddle.m:132

@@ -10,6 +10,7 @@
 
 #include "../../include/gpis_b200.h"
 #include "gpis_common.cuh"
+#include "gpis_grid.cuh"
 #include "gpis_predict.cuh"
 #include "gpis_select.cuh"
 
@@ -32,6 +33,10 @@ struct gpis_engine {
   double* d_alpha = nullptr;
   long long ldw = 0, rk_pad = 0;
   bool have_candidates = false, have_noise = false, have_ids = false;
+  int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
+  int grid_ctas = 0, solve_ctas = 0;
+  size_t table_bytes[MAXD] = {0, 0, 0};
+  size_t w_bytes = 0;
   bool selecting = false;
   int inverse_rows = -1;        // rows Wt/alpha are valid for
   int upd_grid = 0;
@@ -77,11 +82,16 @@ struct Dispatch {
   void (*append)(EngineParams, int, int);
   void (*update)(EngineParams);
   void (*predict)(PredictParams);
+  void (*g_point)(EngineParams, int);
+  void (*g_solve)(EngineParams);
+  void (*g_wrow)(EngineParams);
+  void (*g_update)(EngineParams);
 };
 
 template <int NB, int D>
 Dispatch make_dispatch() {
-  return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>};
+  return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
+                  k_grid_point<NB, D>, k_grid_solve<NB>, k_grid_wrow<NB>, k_grid_update<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -99,15 +109,26 @@ constexpr size_t PRED_SMEM = (2 * PKC * PSB + 2 * PKC * PQ + 32 * PQ) * sizeof(d
 
 gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int finalize_only) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
-  d.append<<<1, APP_THREADS, 0, s>>>(e->P, external, finalize_only);
-  e->launches++;
+  if (e->backend == 2 && !external) {
+    d.g_point<<<1, 1024, 0, s>>>(e->P, finalize_only);
+    e->launches++;
+    if (!finalize_only) {
+      d.g_solve<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+      d.g_wrow<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+      e->launches += 2;
+    }
+  } else {
+    d.append<<<1, APP_THREADS, 0, s>>>(e->P, external, finalize_only);
+    e->launches++;
+  }
   CU(cudaGetLastError());
   return GPIS_OK;
 }
 
 gpis_status launch_update(gpis_engine* e, cudaStream_t s) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
-  d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
+  if (e->backend == 2) d.g_update<<<e->grid_ctas, GUPD_THREADS, GUPD_SMEM, s>>>(e->P);
+  else d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
   e->launches++;
   CU(cudaGetLastError());
   return GPIS_OK;
@@ -127,14 +148,18 @@ gpis_status ensure_inverse(gpis_engine* e, cudaStream_t s) {
   if (rc != GPIS_OK) return rc;
   const int R = e->host_state.r;
   if (e->inverse_rows == R) return GPIS_OK;
-  CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
+  const bool have_wt = e->backend == 2 && e->selecting;   // the grid backend maintains W' itself
+  if (!have_wt) CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
   if (R > 0) {
     const int blocks = (R * 32 + 255) / 256;
-    k_invert_factor<<<blocks, 256, 0, s>>>(e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
-    CU(cudaGetLastError());
+    if (!have_wt) {
+      k_invert_factor<<<blocks, 256, 0, s>>>(e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
+      CU(cudaGetLastError());
+      e->launches++;
+    }
     k_alpha<<<blocks, 256, 0, s>>>(e->d_Wt, e->ldw, e->P.g, R, e->d_alpha);
     CU(cudaGetLastError());
-    e->launches += 2;
+    e->launches += 1;
   }
   e->inverse_rows = R;
   return GPIS_OK;
@@ -223,7 +248,6 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     CU(dalloc(e, &P.flags, Nn));
     CU(dalloc(e, &P.live[0], (size_t)P.n_tiles + 1));
     CU(dalloc(e, &P.live[1], (size_t)P.n_tiles + 1));
-    CU(dalloc(e, &P.V, (size_t)P.n_tiles * (size_t)P.tile_stride));
     CU(dalloc(e, &P.L, (size_t)P.R_cap * P.R_cap));
     CU(dalloc(e, &P.g, (size_t)P.R_cap));
     for (int d = 0; d < D; ++d) CU(dalloc(e, &P.AX[d], (size_t)P.M_cap));
@@ -241,6 +265,9 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->rk_pad = ((long long)P.R_cap + PKC - 1) / PKC * PKC;
     CU(dalloc(e, &e->d_Wt, (size_t)e->ldw * e->rk_pad));
     CU(dalloc(e, &e->d_alpha, (size_t)P.R_cap));
+    CU(dalloc(e, &P.kvec, (size_t)MAXNB * P.R_cap));
+    P.Wt = e->d_Wt;
+    P.ldW = e->ldw;
     for (int d = 0; d < D; ++d) { P.cx[d] = e->d_pts + (size_t)d * Nn; }
     P.tsdf = e->d_tsdf;
 
@@ -252,6 +279,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->upd_smem = sizeof(double) * NB * (size_t)P.ell_chunk;
     CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
     CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
+    CU(cudaFuncSetAttribute((const void*)disp.g_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GUPD_SMEM));
+    e->solve_ctas = e->num_sms * 2;
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)disp.update, UPD_THREADS, e->upd_smem));
     if (occ < 1) return fail(e, GPIS_ERR_CUDA, "update kernel does not fit on an SM");
@@ -301,11 +330,76 @@ gpis_status gpis_set_candidates(gpis_handle e, const double* pts, const double* 
   for (int d = 0; d < e->D; ++d) e->P.nrm[d] = normals ? e->d_nrm + (size_t)d * (N ? N : 1) : nullptr;
   e->P.noise = noise ? e->d_noise : nullptr;
   e->P.ids = ids ? e->d_ids : nullptr;
+  if (!e->P.V) CU(dalloc(e, &e->P.V, (size_t)e->P.n_tiles * (size_t)e->P.tile_stride));
+  for (int d = 0; d < MAXD; ++d) e->P.glen[d] = 0;
+  for (int d = 0; d < e->D; ++d) e->P.cx[d] = e->d_pts + (size_t)d * (N ? N : 1);
+  e->backend = 1;
   e->have_candidates = true;
   e->selecting = false;
   if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return GPIS_OK;
 }
+
+gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const double* origin,
+                                     const double* spacing, int32_t z0, int32_t nz_total, const double* tsdf,
+                                     const double* normals, const double* noise, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (!dims || !origin || !spacing || !tsdf) return fail(e, GPIS_ERR_INVALID, "dims, origin, spacing and tsdf are required");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = e->D;
+  long long n = 1;
+  for (int d = 0; d < D; ++d) { if (dims[d] < 1) return fail(e, GPIS_ERR_INVALID, "dims must be >= 1"); n *= dims[d]; }
+  if (n != e->P.N) return fail(e, GPIS_ERR_INVALID, "product of dims differs from num_candidates");
+  if (e->NB > 1 && !normals) return fail(e, GPIS_ERR_INVALID, "use_gradients needs normals");
+  if (D < 3) { z0 = 0; nz_total = 1; }
+  if (nz_total < dims[D - 1] + z0 && D == 3) nz_total = dims[2] + z0;
+  EngineParams& P = e->P;
+  const size_t N = (size_t)P.N;
+  CU(cudaMemcpyAsync(e->d_tsdf, tsdf, sizeof(double) * N, cudaMemcpyDefault, s));
+  if (normals) CU(cudaMemcpyAsync(e->d_nrm, normals, sizeof(double) * N * D, cudaMemcpyDefault, s));
+  if (noise) CU(cudaMemcpyAsync(e->d_noise, noise, sizeof(double) * N, cudaMemcpyDefault, s));
+  for (int d = 0; d < D; ++d) P.nrm[d] = normals ? e->d_nrm + (size_t)d * N : nullptr;
+  P.noise = noise ? e->d_noise : nullptr;
+  P.ids = nullptr;
+  for (int d = 0; d < MAXD; ++d) {
+    P.cx[d] = nullptr;
+    P.glen[d] = d < D ? dims[d] : 1;
+    P.gorg[d] = d < D ? origin[d] : 0.0;
+    P.gh[d] = d < D ? spacing[d] : 1.0;
+    // axis 2's table spans the global z range; tiles read whole 128-wide rows of axes 0 and 1
+    const long long len = (d == 2 && D == 3) ? nz_total : P.glen[d];
+    P.gtlen[d] = (int)len;
+    const int ld = (int)((len + GT - 1) / GT * GT);
+    const size_t bytes = sizeof(double) * (size_t)(e->rk_pad + GKC) * ld;
+    if (bytes > e->table_bytes[d]) {
+      CU(dalloc(e, &P.T[d], bytes / sizeof(double)));
+      e->table_bytes[d] = bytes;
+    }
+    P.ldt[d] = ld;
+  }
+  P.gz0 = z0;
+  if (!P.W) {
+    CU(dalloc(e, &P.W, (size_t)e->rk_pad * e->ldw));
+    e->w_bytes = sizeof(double) * (size_t)e->rk_pad * e->ldw;
+  }
+  const int tiles = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT) * P.glen[2];
+  e->grid_ctas = tiles;
+  if ((size_t)tiles > (size_t)e->upd_grid) {
+    CU(dalloc(e, &P.partials, (size_t)tiles));
+  }
+  e->backend = 2;
+  e->have_candidates = true;
+  e->selecting = false;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return GPIS_OK;
+}
+
+namespace {
+__global__ void k_fill_ones_col0(double* T, int ld, long long rows) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r < rows) T[r * ld] = 1.0;
+}
+}  // namespace
 
 gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
@@ -317,6 +411,18 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
     k_init_candidates<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->P);
     CU(cudaGetLastError());
     e->launches++;
+  }
+  if (e->backend == 2) {
+    CU(cudaMemsetAsync(e->P.W, 0, e->w_bytes, s));
+    CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
+    for (int d = 0; d < MAXD; ++d) {
+      CU(cudaMemsetAsync(e->P.T[d], 0, e->table_bytes[d], s));
+      if (d >= e->D) {    // unused axes: constant-one tables
+        const long long rows = e->rk_pad + GKC;
+        k_fill_ones_col0<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(e->P.T[d], e->P.ldt[d], rows);
+        e->launches++;
+      }
+    }
   }
   k_begin<<<1, 32, 0, s>>>(e->P, first_local < 0 ? -1 : first_local);
   CU(cudaGetLastError());
@@ -398,7 +504,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       CU(cudaEventRecord(e->prof_events[2 * it + 1], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += 2;
+      e->launches += e->backend == 2 ? 4 : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;

@@ -75,6 +75,17 @@ struct EngineParams {
   long long pay_stride;    // slots per record
   int rank, world;
   int ell_chunk;           // factor rows staged in shared memory per pass
+  // grid backend (glen[0] > 0): lattice geometry, separable axis tables, explicit W = L^-1
+  int glen[MAXD];          // candidates per axis on THIS rank (z: the local slab)
+  int gz0;                 // first global z index of the local slab
+  int gtlen[MAXD];         // axis-table lengths (axis 2: the GLOBAL z count)
+  double gorg[MAXD], gh[MAXD];   // x = gorg + gh * global index
+  double* T[MAXD];         // [rows][ldt]: axis tables (axis 2 spans the GLOBAL z range)
+  int ldt[MAXD];
+  double* W;               // [rows][ldW] lower triangular L^-1
+  double* Wt;              // its transpose (shared with the predict kernel)
+  long long ldW;
+  double* kvec;            // [MAXNB][R_cap] covariance of the new rows with the model rows
   // model
   double inv_ell2, sf2, level, eps, beta, beta_delta, noise_scalar;
   double mean_w[MAXD], mean_c;

@@ -1,0 +1,444 @@
+// Grid backend: candidates on a regular axis-aligned lattice (the reference's SelectFromGrid
+// case, gpu_active_set_selector.cpp:170-201, and every BASELINE.json config).
+//
+// The SE kernel separates over axes, so the covariance of model row rho with lattice point
+// (jx, jy, jz) is Tx[rho][jx] * Ty[rho][jy] * Tz[rho][jz] (gradient rows carry the factor
+// (x_j - x_rho)/ell^2 in their own axis table).  With W = L^-1 maintained explicitly, the new
+// row of V = L^-1 K(rows, candidates) is
+//     v[jy, jx] = sum_rho (W[r, rho] Tz[rho][jz]) * Ty[rho][jy] * Tx[rho][jx]
+// -- a dense [ny x r] x [r x nx] contraction per z-slice, run on the fp64 tensor pipe (DMMA).
+// V is never stored: the per-step HBM traffic drops from 8*N*r bytes (panel backend) to the
+// posterior arrays (~42 bytes per candidate), and the step becomes compute-bound.
+#pragma once
+#include "gpis_common.cuh"
+#include "gpis_select.cuh"
+
+namespace gpis {
+
+constexpr int GT = 128;         // tile edge (jy x jx) of the update GEMM
+constexpr int GKC = 16;         // model rows per pipeline stage
+constexpr int GLD = GT + 4;     // padded smem row (conflict-free DMMA fragment loads)
+constexpr int GSTAGES = 3;
+constexpr int GUPD_THREADS = 512;
+constexpr int GSOLVE_THREADS = 256;
+constexpr size_t GUPD_SMEM = (size_t)GSTAGES * (2 * GKC * GLD + GKC) * sizeof(double);
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void g_cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void g_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ int pick_winner(const EngineParams& P) {
+  int win = -1;
+  double bs = 0.0;
+  long long bid = 0;
+  for (int w = 0; w < P.world; ++w) {
+    const double* pay = P.pay_recv + (long long)w * P.pay_stride;
+    const long long* pl = reinterpret_cast<const long long*>(pay);
+    if (pl[PAY_LOCAL] < 0) continue;
+    if (win < 0 || better(pay[PAY_SCORE], pl[PAY_ID], bs, bid)) { win = w; bs = pay[PAY_SCORE]; bid = pl[PAY_ID]; }
+  }
+  return win;
+}
+
+// ---------------------------------------------------------------------------------------
+// K0 (one CTA): winner, its covariance with the model rows (kvec), its axis-table rows.
+// ---------------------------------------------------------------------------------------
+template <int NB, int D>
+__global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int finalize_only) {
+  DevState* st = P.st;
+  __shared__ int s_win;
+  if (st->done) return;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int win = pick_winner(P);
+    if (win < 0) st->done = 1;
+    else if (!finalize_only && st->m >= P.M_cap) { st->done = 1; win = -1; }
+    s_win = win;
+  }
+  __syncthreads();
+  const int win = s_win;
+  if (win < 0) return;
+  const double* pay = P.pay_recv + (long long)win * P.pay_stride;
+  const long long* pl = reinterpret_cast<const long long*>(pay);
+  const int r0 = st->r, m = st->m;
+  if (tid == 0) {
+    if (win == P.rank) P.flags[pl[PAY_LOCAL]] |= F_ACTIVE;
+    P.sel_ids[m] = pl[PAY_ID];
+    st->n_sel = m + 1;
+  }
+  if (finalize_only) return;
+  double nx[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) nx[d] = pay[PAY_X + d];
+  // covariance of the new rows with the old rows -> kvec[a][rho]
+  for (int i = tid; i < m; i += blockDim.x) {
+    double z[D], c[NB][NB];
+#pragma unroll
+    for (int d = 0; d < D; ++d) z[d] = P.AX[d][i];
+    cov_rows_rows<NB, D>(P, nx, z, c);
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+#pragma unroll
+      for (int b = 0; b < NB; ++b) P.kvec[(long long)a * P.R_cap + i * NB + b] = c[a][b];
+  }
+  // axis tables of the new rows: T_d[row][j] = exp(-(x_j - p_d)^2 / (2 ell^2)), times
+  // (x_j - p_d)/ell^2 on the row's own axis for gradient rows; sf2 is folded into axis 0.
+  for (int d = 0; d < D; ++d) {
+    const int len = P.gtlen[d];
+    for (int e = tid; e < len * NB; e += blockDim.x) {
+      const int a = e / len, j = e % len;
+      const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
+      double v = exp(-0.5 * diff * diff * P.inv_ell2);
+      if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;     // [d_a f(x_rho), f(x_j)]
+      if (d == 0) v *= P.sf2;
+      P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) { st->nx[d] = nx[d]; P.AX[d][m] = nx[d]; }
+    st->nnoise = pay[PAY_NOISE];
+    st->r0 = r0;
+    // residual targets of the new rows, consumed by k_grid_wrow
+    double mf = P.mean_c;
+#pragma unroll
+    for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
+    st->gnew[0] = pay[PAY_TSDF] - mf;
+    for (int a = 1; a < NB; ++a) st->gnew[a] = pay[PAY_NRM + a - 1] - P.mean_w[a - 1];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: X = W[0:r0, 0:r0] kvec  (= L^-1 Q(old, new)); one warp per row, written into L's new rows.
+// ---------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
+  const DevState* st = P.st;
+  if (st->done) return;
+  const int r0 = st->r0;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int s = wid; s < r0; s += nw) {
+    const double* wrow = P.W + (long long)s * P.ldW;
+    double acc[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) acc[a] = 0.0;
+    for (int c = lane; c <= s; c += 32) {
+      const double w = wrow[c];
+#pragma unroll
+      for (int a = 0; a < NB; ++a) acc[a] += w * P.kvec[(long long)a * P.R_cap + c];
+    }
+#pragma unroll
+    for (int a = 0; a < NB; ++a) {
+      double v = acc[a];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) P.L[(long long)(r0 + a) * P.R_cap + s] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: S = Q(new,new) - X'X = Lnn Lnn';  new rows of W = Lnn^-1 [-X'W | I]  (and of W');
+//     g_new = Lnn^-1 (y - m - X'g).  Every CTA recomputes the small Gram block.
+// ---------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
+  DevState* st = P.st;
+  if (st->done) return;
+  __shared__ double s_red[GSOLVE_THREADS / 32];
+  __shared__ double s_dot[NB][NB + 1];
+  __shared__ double s_linv[NB][NB];
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r0 = st->r0;
+  const double* X[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) X[a] = P.L + (long long)(r0 + a) * P.R_cap;
+  for (int a = 0; a < NB; ++a)
+    for (int b = 0; b <= a + 1; ++b) {
+      double p = 0.0;
+      if (b <= a) { for (int s = tid; s < r0; s += GSOLVE_THREADS) p += X[a][s] * X[b][s]; }
+      else        { for (int s = tid; s < r0; s += GSOLVE_THREADS) p += X[a][s] * P.g[s]; }
+      const double tot = block_reduce_sum(p, s_red);
+      if (tid == 0) { if (b <= a) s_dot[a][b] = tot; else s_dot[a][NB] = tot; }
+    }
+  __syncthreads();
+  if (tid == 0) {
+    const double nnoise = st->nnoise;
+    double Qn[NB][NB], Ln[NB][NB], Li[NB][NB];
+    for (int a = 0; a < NB; ++a)
+      for (int b = 0; b < NB; ++b) Qn[a][b] = 0.0;
+    Qn[0][0] = P.sf2 + nnoise;
+    for (int d = 1; d < NB; ++d) Qn[d][d] = (P.sf2 + nnoise) * P.inv_ell2;   // noise leak, se_cov_derivative.m:28-35
+    bool ok = true;
+    for (int a = 0; a < NB; ++a) {
+      for (int b = 0; b <= a; ++b) {
+        double s = Qn[a][b] - s_dot[a][b];
+        for (int t = 0; t < b; ++t) s -= Ln[a][t] * Ln[b][t];
+        if (a == b) { if (!(s > 0.0)) { ok = false; s = 1.0; } Ln[a][a] = sqrt(s); }
+        else Ln[a][b] = s / Ln[b][b];
+      }
+      for (int b = a + 1; b < NB; ++b) Ln[a][b] = 0.0;
+    }
+    for (int c = 0; c < NB; ++c)                       // Li = Ln^-1 (lower), column by column
+      for (int a = 0; a < NB; ++a) {
+        double s = (a == c) ? 1.0 : 0.0;
+        for (int t = 0; t < a; ++t) s -= Ln[a][t] * Li[t][c];
+        Li[a][c] = (a >= c) ? s / Ln[a][a] : 0.0;
+      }
+    for (int a = 0; a < NB; ++a)
+      for (int b = 0; b < NB; ++b) s_linv[a][b] = Li[a][b];
+    s_ok = ok;
+    if (blockIdx.x == 0) {
+      double gn[NB];
+      for (int a = 0; a < NB; ++a) {
+        double s = st->gnew[a] - s_dot[a][NB];
+        for (int t = 0; t < a; ++t) s -= Ln[a][t] * gn[t];
+        gn[a] = s / Ln[a][a];
+      }
+      for (int a = 0; a < NB; ++a) {
+        P.g[r0 + a] = gn[a];
+        for (int b = 0; b <= a; ++b) {
+          P.L[(long long)(r0 + a) * P.R_cap + r0 + b] = Ln[a][b];
+          P.W[(long long)(r0 + a) * P.ldW + r0 + b] = Li[a][b];
+          P.Wt[(long long)(r0 + b) * P.ldW + r0 + a] = Li[a][b];
+        }
+      }
+      for (int a = 0; a < NB; ++a) st->gnew[a] = gn[a];
+      st->r = r0 + NB;
+      st->m = st->m + 1;
+      if (!ok) { st->err = -5; st->done = 1; }
+    }
+  }
+  __syncthreads();
+  const int wid = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int rho = wid; rho < r0; rho += nw) {
+    const double* wt = P.Wt + (long long)rho * P.ldW;     // Wt[rho][s] = W[s][rho], s >= rho
+    double acc[NB];
+#pragma unroll
+    for (int a = 0; a < NB; ++a) acc[a] = 0.0;
+    for (int s = rho + lane; s < r0; s += 32) {
+      const double w = wt[s];
+#pragma unroll
+      for (int a = 0; a < NB; ++a) acc[a] += w * X[a][s];
+    }
+#pragma unroll
+    for (int a = 0; a < NB; ++a)
+      for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < NB; ++a) {
+        double v = 0.0;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+          if (b <= a) v -= s_linv[a][b] * acc[b];
+        P.W[(long long)(r0 + a) * P.ldW + rho] = v;
+        P.Wt[(long long)rho * P.ldW + r0 + a] = v;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: the per-step update as a GEMM on the fp64 tensor pipe + straddle scoring + arg-max.
+// CTA tile: 128 (jy) x 128 (jx) at one jz; 16 warps, 32 x 32 each = 4 x 4 DMMA.8x8x4 tiles.
+// ---------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P) {
+  extern __shared__ __align__(16) double g_smem[];
+  DevState* st = P.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int r0 = st->r0;
+  const int nx = P.glen[0], ny = P.glen[1];
+  const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
+  const int tz = blockIdx.x / (tiles_x * tiles_y);
+  const int ty = (blockIdx.x / tiles_x) % tiles_y, tx = blockIdx.x % tiles_x;
+  const int gz = P.gz0 + tz;
+  const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
+  double beta = P.beta;
+  if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
+  else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
+  const double sb = sqrt(beta);
+
+  double best_s = NEG_INF;
+  long long best_id = 0x7fffffffffffffffLL, best_j = -1;
+  int n_scored = 0;
+
+  for (int a = 0; a < NB; ++a) {
+    const double* wrow = P.W + (long long)(r0 + a) * P.ldW;
+    const double ga = st->gnew[a];
+    const int klen = r0 + a + 1;
+    const int nchunks = (klen + GKC - 1) / GKC;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    auto issue = [&](int c) {
+      double* As = g_smem + (size_t)(c % GSTAGES) * (2 * GKC * GLD + GKC);
+      double* Bs = As + GKC * GLD;
+      double* cs = Bs + GKC * GLD;
+      const long long rho0 = (long long)c * GKC;
+#pragma unroll
+      for (int i = 0; i < (GKC * GT / 2) / GUPD_THREADS; ++i) {
+        const int q = tid + i * GUPD_THREADS;
+        const int kk = q / (GT / 2), c2 = q % (GT / 2);
+        g_cp_async16(As + kk * GLD + c2 * 2, P.T[1] + (rho0 + kk) * P.ldt[1] + ty * GT + c2 * 2);
+        g_cp_async16(Bs + kk * GLD + c2 * 2, P.T[0] + (rho0 + kk) * P.ldt[0] + tx * GT + c2 * 2);
+      }
+      if (tid < GKC) {
+        const long long rho = rho0 + tid;
+        double cv = rho < klen ? wrow[rho] : 0.0;
+        if (P.T[2]) cv *= P.T[2][rho * P.ldt[2] + gz];
+        cs[tid] = cv;
+      }
+      g_cp_commit();
+    };
+
+    issue(0);
+    if (nchunks > 1) issue(1); else g_cp_commit();
+    for (int c = 0; c < nchunks; ++c) {
+      g_cp_wait<1>();
+      __syncthreads();
+      if (c + 2 < nchunks) issue(c + 2); else g_cp_commit();
+      const double* As = g_smem + (size_t)(c % GSTAGES) * (2 * GKC * GLD + GKC);
+      const double* Bs = As + GKC * GLD;
+      const double* cs = Bs + GKC * GLD;
+#pragma unroll
+      for (int k4 = 0; k4 < GKC / 4; ++k4) {
+        const int kb = k4 * 4 + (lane & 3);
+        const double cv = cs[kb];
+        double af[4], bf[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = As[kb * GLD + wm * 32 + i * 8 + (lane >> 2)] * cv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = Bs[kb * GLD + wn * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+    }
+    g_cp_wait<0>();
+    __syncthreads();
+
+    // epilogue: posterior update; scoring on the last pass
+    const bool last = (a == NB - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int jy = ty * GT + wm * 32 + i * 8 + (lane >> 2);
+      if (jy >= ny) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jx0 = tx * GT + wn * 32 + j * 8 + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jx = jx0 + e;
+          if (jx >= nx) continue;
+          const long long jl = (long long)jx + (long long)nx * (jy + (long long)ny * tz);
+          const double v = acc[i][j][e];
+          const double var = P.var[jl] - v * v;
+          const double mu = P.mu[jl] + v * ga;
+          P.var[jl] = var;
+          P.mu[jl] = mu;
+          if (last) {
+            unsigned char f = P.flags[jl];
+            if (!(f & (F_ACTIVE | F_HIGH | F_LOW))) {
+              ++n_scored;
+              double ve = var;
+              if (P.variance_mode == 1) ve = __dadd_rn(var, P.noise ? P.noise[jl] : P.noise_scalar);
+              const double w = __dmul_rn(sb, ve);
+              const double hi = __dadd_rn(mu, w), lo = __dadd_rn(mu, -w);
+              double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
+              P.amb[jl] = sc;
+              if (__dadd_rn(lo, P.eps) > P.level) f |= F_HIGH;
+              if (__dadd_rn(hi, -P.eps) < P.level) f |= F_LOW;
+              P.flags[jl] = f;
+              if (sc == sc) {
+                const long long id = cand_id(P, jl);
+                if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // CTA arg-max, then grid arg-max by the last CTA
+  __shared__ BlockBest s_bb[GUPD_THREADS / 32];
+  __shared__ int s_cnt[GUPD_THREADS / 32];
+  __shared__ int s_last;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
+    const long long oid = __shfl_xor_sync(0xffffffffu, best_id, o);
+    const long long oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+    if (oj >= 0 && better(os, oid, best_s, best_id)) { best_s = os; best_id = oid; best_j = oj; }
+    n_scored += __shfl_xor_sync(0xffffffffu, n_scored, o);
+  }
+  if (lane == 0) { s_bb[warp].score = best_s; s_bb[warp].id = best_id; s_bb[warp].local = best_j; s_cnt[warp] = n_scored; }
+  __syncthreads();
+  if (tid == 0) {
+    BlockBest b = s_bb[0];
+    int cnt = s_cnt[0];
+    for (int w = 1; w < GUPD_THREADS / 32; ++w) {
+      cnt += s_cnt[w];
+      if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
+    }
+    P.partials[blockIdx.x] = b;
+    if (cnt) atomicAdd(&st->n_scored, cnt);
+    __threadfence();
+    const unsigned ticket = atomicAdd(&st->blocks_done, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  BlockBest b;
+  b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
+  for (int i = tid; i < (int)gridDim.x; i += GUPD_THREADS) {
+    const volatile BlockBest* pp = &P.partials[i];
+    const double ps = pp->score;
+    const long long pid = pp->id, ploc = pp->local;
+    if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
+    const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
+    const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
+    if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; }
+  }
+  __syncthreads();
+  if (lane == 0) s_bb[warp] = b;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < GUPD_THREADS / 32; ++w)
+      if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
+    s_bb[0] = b;
+    const int it = st->iter;
+    if (it <= P.M_cap) {
+      P.hist[it] = r0;
+      P.hist[(P.M_cap + 1) + it] = (int)gridDim.x;
+      P.hist[2 * (P.M_cap + 1) + it] = *(volatile int*)&st->n_scored;
+    }
+    st->n_scored = 0;
+    st->blocks_done = 0;
+    st->iter = it + 1;
+  }
+  __syncthreads();
+  b = s_bb[0];
+  write_record(P, b.score, b.local, 0);
+}
+
+}  // namespace gpis

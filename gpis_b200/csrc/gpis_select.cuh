@@ -76,13 +76,21 @@ __device__ inline void write_record(const EngineParams& P, double score, long lo
     if (j >= 0) {
       pay[PAY_TSDF] = P.tsdf[j];
       pay[PAY_NOISE] = P.noise ? P.noise[j] : P.noise_scalar;
+      long long rem = j;
       for (int d = 0; d < MAXD; ++d) {
-        pay[PAY_X + d] = P.cx[d] ? P.cx[d][j] : 0.0;
+        if (P.glen[0] > 0) {       // grid backend: coordinates from the lattice index
+          const long long len = P.glen[d] > 0 ? P.glen[d] : 1;
+          const long long jd = rem % len + (d == 2 ? P.gz0 : 0);
+          rem /= len;
+          pay[PAY_X + d] = P.gorg[d] + P.gh[d] * (double)jd;
+        } else {
+          pay[PAY_X + d] = P.cx[d] ? P.cx[d][j] : 0.0;
+        }
         pay[PAY_NRM + d] = P.nrm[d] ? P.nrm[d][j] : 0.0;
       }
     }
   }
-  if (j >= 0) {
+  if (j >= 0 && rows > 0) {
     const double* col = P.V + (j / TW) * P.tile_stride + (j % TW);
     for (int s = threadIdx.x; s < rows; s += blockDim.x) pay[PAY_HDR + s] = __ldcg(col + (long long)s * TW);
   }

@@ -120,6 +120,20 @@ class GpisEngine:
         self._keep = (p, t, n, z, i)
         self._ck(self.lib.gpis_set_candidates(self.h, _ptr(p), _ptr(t), _ptr(n), _ptr(z), _ptr(i), _stream()))
 
+    def set_grid_candidates(self, dims, origin, spacing, tsdf, normals=None, noise=None, z0=0, nz_total=None,
+                            soa=False):
+        """Candidates = every point of a regular lattice (x fastest); selects the grid backend."""
+        D = self.dim
+        dims_a = np.ascontiguousarray(np.asarray(dims, np.int32).reshape(-1)[:D])
+        org = np.ascontiguousarray(np.asarray(origin, np.float64).reshape(-1)[:D])
+        sp = np.ascontiguousarray(np.asarray(spacing, np.float64).reshape(-1)[:D])
+        t, z = _vec(tsdf), _vec(noise)
+        n = normals if soa else _soa(normals)
+        nzt = int(nz_total) if nz_total is not None else (int(dims_a[2]) + int(z0) if D == 3 else 1)
+        self._keep = (dims_a, org, sp, t, n, z)
+        self._ck(self.lib.gpis_set_grid_candidates(self.h, _ptr(dims_a), _ptr(org), _ptr(sp), int(z0), nzt,
+                                                   _ptr(t), _ptr(n), _ptr(z), _stream()))
+
     # ------------------------------------------------------------------ selection
     def select(self, first_local, K):
         self._ck(self.lib.gpis_select(self.h, int(first_local), int(K), _stream()))

@@ -94,6 +94,19 @@ gpis_status gpis_set_candidates(gpis_handle h, const double* pts, const double* 
                                 const double* normals, const double* noise,
                                 const int64_t* ids, void* stream);
 
+/* GpuActiveSetSelector::SelectFromGrid (gpu_active_set_selector.cpp:170-201, ReadCsv :75-113):
+ * the candidates are ALL points of a regular lattice, x fastest (IJK_TO_LINEAR,
+ * active_set_selection_types.h:6): point (i,j,k) = origin + spacing * (i, j, z0 + k),
+ * dims = {nx, ny, nz_local}.  tsdf / normals / noise are indexed by the linear lattice index.
+ * z0 / nz_total describe this rank's z-slab of the whole lattice (0 / dims[2] when unsharded).
+ * This selects the grid backend: the SE kernel's separability over axes turns each selection
+ * step into a dense contraction on the fp64 tensor pipe and the running posterior is exact for
+ * every lattice point (gpis_get_candidate_posterior is then the full posterior grid). */
+gpis_status gpis_set_grid_candidates(gpis_handle h, const int32_t* dims, const double* origin,
+                                     const double* spacing, int32_t z0, int32_t nz_total,
+                                     const double* tsdf, const double* normals, const double* noise,
+                                     void* stream);
+
 /* GpuActiveSetSelector::SelectChol (gpu_active_set_selector.cpp:408-611) with the semantics
  * of select_active_set_straddle.m:62-126: greedy loop entirely on the device, at most K
  * points, stops early when nothing is unclassified.  first_local = local index of the first

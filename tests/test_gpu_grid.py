@@ -1,0 +1,128 @@
+"""GPU parity of the grid (separable, DMMA) backend against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import gpis_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    assert torch.cuda.is_available()
+    import gpis_b200
+    return gpis_b200
+
+
+def sphere(g, ell=3.0, with_normals=False):
+    from gpis_b200.synth import sphere_tsdf
+    out = sphere_tsdf(g, trunc=3.0, with_normals=with_normals)
+    hyp = {"cov": np.array([np.log(ell), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
+    shape = {"points": out[0], "tsdf": out[1], "normals": out[2] if with_normals else None, "noise": None}
+    return shape, hyp
+
+
+def first_divergence(a, b):
+    n = min(len(a), len(b))
+    return int(np.argmin(np.r_[np.asarray(a[:n]) == np.asarray(b[:n]), False]))
+
+
+@pytest.mark.parametrize("g,K,first", [(20, 160, 4321), (24, 200, 777)])
+def test_grid_backend_sequence_and_posterior_grid(G, g, K, first):
+    shape, hyp = sphere(g)
+    tr = {"activeSetSize": K, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental(shape, tr, first, hyp=hyp, prune=False)
+    mdl, pred, test = G.select_active_set(shape, tr, first_index=first, hyp=hyp, backend="grid")
+    assert mdl["backend"] == "grid"
+    assert np.array_equal(ora["order"], mdl["order"]), f"diverged at {first_divergence(ora['order'], mdl['order'])}"
+    assert mdl["n_in_model"] == ora["n_in_model"]
+    assert np.array_equal(pred["high"], ora["high"]) and np.array_equal(pred["low"], ora["low"])
+    # the running posterior IS the full posterior grid (no candidate is ever frozen)
+    mu, var = mdl.engine.candidate_posterior()
+    fm, fv, _ = O.predict_points(ora["gp"], shape["points"])
+    assert np.max(np.abs(mu - fm)) < 1e-8
+    assert np.max(np.abs(var - fv) / np.maximum(np.abs(fv), 1e-3)) < 1e-5          # north_star fp64 bar
+    # factor and dense prediction through W' maintained by the grid backend
+    L = ora["gp"].L[:ora["gp"].r, :ora["gp"].r]
+    assert np.max(np.abs(mdl["L"] - L)) < 1e-9
+    assert np.max(np.abs(pred["tsdf"] - fm[test])) < 1e-8 and np.max(np.abs(pred["noise"] - fv[test])) < 1e-8
+    # same picks as the panel backend
+    mdl2, _, _ = G.select_active_set(shape, tr, first_index=first, hyp=hyp, backend="panel")
+    assert mdl2["backend"] == "panel" and np.array_equal(mdl2["order"], mdl["order"])
+
+
+def test_grid_backend_with_gradient_observations(G):
+    shape, hyp = sphere(12, ell=2.5, with_normals=True)
+    tr = {"activeSetSize": 70, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental(shape, tr, 500, hyp=hyp, prune=False)
+    mdl, pred, test = G.select_active_set(shape, tr, first_index=500, hyp=hyp, backend="grid")
+    assert np.array_equal(ora["order"], mdl["order"]), f"diverged at {first_divergence(ora['order'], mdl['order'])}"
+    mu, var = mdl.engine.candidate_posterior()
+    fm, fv, fn = O.predict_points(ora["gp"], shape["points"], want_normals=True)
+    assert np.max(np.abs(mu - fm)) < 1e-8 and np.max(np.abs(var - fv)) < 1e-8
+    assert np.max(np.abs(pred["normals"] - fn[test])) < 1e-8
+
+
+def test_grid_backend_2d_lattice_and_odd_sizes(G):
+    rng = np.random.default_rng(2)
+    for dims in [(25, 25), (7, 5), (33, 9), (130, 3)]:
+        nx, ny = dims
+        ii = np.indices((ny, nx)).reshape(2, -1)[::-1].T.astype(np.float64) + 1.0     # 1-based like meshgrid(1:g)
+        c = np.array([nx * 0.52, ny * 0.47])
+        tsdf = np.clip((np.linalg.norm(ii - c, axis=1) - min(dims) * 0.3) / 2.0, -1, 1) + 1e-3 * rng.standard_normal(ii.shape[0])
+        shape = {"points": ii, "tsdf": tsdf, "normals": None, "noise": None}
+        hyp = {"cov": np.array([0.6, 0.0]), "mean": np.zeros(3), "lik": 0.5 * np.log(0.05)}
+        tr = {"activeSetSize": min(40, ii.shape[0]), "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+        ora = O.select_straddle_incremental(shape, tr, 3, hyp=hyp, prune=False)
+        mdl, pred, test = G.select_active_set(shape, tr, first_index=3, hyp=hyp, backend="grid")
+        assert np.array_equal(ora["order"], mdl["order"]), dims
+        mu, var = mdl.engine.candidate_posterior()
+        fm, fv, _ = O.predict_points(ora["gp"], ii)
+        assert np.max(np.abs(mu - fm)) < 1e-8 and np.max(np.abs(var - fv)) < 1e-8
+
+
+def test_two_slab_shards_on_one_gpu_match_single_engine(G):
+    """world_size = 2 emulated in one process: the records are exchanged by device copies."""
+    import torch
+    from gpis_b200.dist import engine_exchange_tensors
+    g, K, first = 16, 90, 1000
+    shape, hyp = sphere(g)
+    tr = {"activeSetSize": K, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ref, _, _ = G.select_active_set(shape, tr, first_index=first, hyp=hyp, backend="grid")
+    cfg = dict(ell=float(np.exp(hyp["cov"][0])), noise=0.05, level=0.0, eps=1e-2, beta=10.0)
+    z_split = 7
+    engs, views = [], []
+    for r, (z0, z1) in enumerate([(0, z_split), (z_split, g)]):
+        n = g * g * (z1 - z0)
+        e = G.GpisEngine(3, n, K, rank=r, world_size=2, total_candidates=g ** 3, id_base=g * g * z0, **cfg)
+        e.set_grid_candidates((g, g, z1 - z0), (0, 0, 0), (1, 1, 1), shape["tsdf"][g * g * z0:g * g * z1], z0=z0, nz_total=g)
+        engs.append(e)
+        views.append(engine_exchange_tensors(e, 2))
+
+    def gather():
+        for send, recv in views:
+            n = send.numel()
+            for r2, (s2, _) in enumerate(views):
+                recv[r2 * n:(r2 + 1) * n].copy_(s2)
+        torch.cuda.synchronize()
+
+    for r, e in enumerate(engs):
+        lo = g * g * (0 if r == 0 else z_split)
+        hi = g * g * (z_split if r == 0 else g)
+        e.select_begin(first - lo if lo <= first < hi else -1)
+    gather()
+    for _ in range(K - 1):
+        for e in engs:
+            e.step_append()
+            e.step_update()
+        gather()
+    for e in engs:
+        e.select_end()
+    ids0, m0 = engs[0].active()
+    ids1, m1 = engs[1].active()
+    assert np.array_equal(ids0, ids1) and m0 == m1
+    assert np.array_equal(ids0, ref["order"]) and m0 == ref["n_in_model"]
+    mu = np.concatenate([e.candidate_posterior()[0] for e in engs])
+    rmu, _ = ref.engine.candidate_posterior()
+    assert np.max(np.abs(mu - rmu)) < 1e-10
