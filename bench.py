@@ -153,8 +153,9 @@ METRIC = "active-set pts selected/s (step = 4000-pt LSE selection + full posteri
 def workload_config(args):
     return {"workload": f"box TSDF {args.grid}^3 ({args.grid ** 3} candidates), SE ell={HYP_ELL} noise={NOISE}, "
                         f"{args.active}-pt straddle active set (beta={BETA}, eps={EPS}) + full {args.grid}^3 posterior grid",
-            "grid": args.grid, "active_set": args.active, "precision": "fp64",
-            "l2": "inputs larger than L2 (panel store >> 126 MB); no explicit flush"}
+            "grid": args.grid, "active_set": args.active, "precision": "fp64", "backend": getattr(args, "backend", "grid"),
+            "l2": ("per-step working set (W rows, axis tables, posterior arrays: > 300 MB over a step's kernels) exceeds L2; no explicit flush"
+                   if getattr(args, "backend", "grid") == "grid" else "inputs larger than L2 (panel store >> 126 MB); no explicit flush")}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -175,7 +176,13 @@ def run_ours(args):
 
     pts, tsdf, first = workload(args.grid, args.active)
     N, D, K = pts.shape[0], 3, args.active
-    lo, hi = gdist.shard_range(N, rank, world)
+    g = args.grid
+    grid_backend = args.backend == "grid"
+    if grid_backend:       # z-slabs of the lattice
+        z0, z1 = gdist.slab_range(g, rank, world)
+        lo, hi = g * g * z0, g * g * z1
+    else:
+        lo, hi = gdist.shard_range(N, rank, world)
     n_loc = hi - lo
     # host buffers (pinned, SoA) for the end-to-end arm; device copies for the resident arm
     h_pts = torch.from_numpy(np.ascontiguousarray(pts[lo:hi].T)).pin_memory()
@@ -188,15 +195,21 @@ def run_ours(args):
 
     eng = GpisEngine(D, n_loc, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA,
                      rank=rank, world_size=world, total_candidates=N, id_base=lo, device=local_rank)
-    eng.set_profiling(True)
+    eng.set_profiling(not args.no_profile)
     sel = gdist.ShardedSelector(eng, rank, world, lo, hi)
-    sel.profile = True
+    sel.profile = not args.no_profile
 
     def step(host):
         P, T = (h_pts, h_tsdf) if host else (d_pts, d_tsdf)
-        eng.set_candidates(P, T, soa=True)
-        sel.select(first, K)
-        eng.predict_into(P, h_mean if host else d_mean, h_var if host else d_var)
+        if grid_backend:
+            eng.set_grid_candidates((g, g, z1 - z0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), T, z0=z0, nz_total=g)
+            sel.select(first, K)
+            # the running posterior of the lattice IS the posterior grid: copy it out
+            eng.candidate_posterior_into(h_mean if host else d_mean, h_var if host else d_var)
+        else:
+            eng.set_candidates(P, T, soa=True)
+            sel.select(first, K)
+            eng.predict_into(P, h_mean if host else d_mean, h_var if host else d_var)
         if host:
             ids, n_model = eng.active()
             return ids, n_model
@@ -210,20 +223,21 @@ def run_ours(args):
     def timed(host, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"select_ms": 0.0, "predict_ms": 0.0, "update_ms": 0.0, "alg_bytes": 0.0, "panel_bytes": 0.0,
-               "update_launches": 0}
+               "update_launches": 0, "alg_flops": 0.0}
         barrier()
         e0.record()
         for _ in range(steps):
             step(host)
             t = eng.timing()
             hst = eng.history()
-            acc["predict_ms"] += t["predict_ms"]
+            acc["predict_ms"] += 0.0 if grid_backend else t["predict_ms"]
             acc["update_ms"] += sel.last_update_ms
             acc["update_launches"] += len(hst["rows"])
             acc["select_ms"] += sel.last_select_ms
             r, u, tl = hst["rows"].astype(np.float64), hst["scored"].astype(np.float64), hst["live_tiles"].astype(np.float64)
             acc["alg_bytes"] += float(np.sum(8.0 * u * (r + 1) + u * (2 * 8 + 2)))
             acc["panel_bytes"] += float(np.sum(8.0 * 64 * tl * (r + 1)))
+            acc["alg_flops"] += float(np.sum(2.0 * n_loc * (r + 1)))
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -245,7 +259,7 @@ def run_ours(args):
     ids, n_model = eng.active()
 
     # whole-job aggregates over ranks
-    tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"]], dtype=torch.float64, device=dev)
+    tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"], acc["alg_flops"]], dtype=torch.float64, device=dev)
     mx = torch.tensor([acc["update_ms"], acc["select_ms"], acc["predict_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -257,6 +271,8 @@ def run_ours(args):
     n_sel = len(ids)
     s_dev, s_e2e = ms_dev / 1e3 / args.steps, ms_e2e / 1e3 / args.steps
     upd_s, sel_s, pred_s = (float(x) / 1e3 / args.steps for x in mx)
+    if args.no_profile:
+        upd_s = sel_s
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -265,25 +281,42 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0)) * world
     achieved = float(tot[0]) / args.steps / upd_s / 1e9
     R = n_model
+    if grid_backend:
+        fp64 = {}
+        try:
+            fp64 = json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json")))
+        except Exception:
+            pass
+        tpeak = float(fp64.get("dmma_m8n8k4_tflops", 37.2)) * world
+        tach = float(tot[2]) / args.steps / upd_s / 1e12
+        roof = {"kernel": "k_grid_update (per-step [ny x r] x [r x nx] contraction on the fp64 tensor pipe "
+                          "+ posterior update + straddle score + arg-max)",
+                "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
+                "peak_source": ("fp64 DMMA.8x8x4 peak measured on this pool's B200 by scripts/fp64_peak.cu "
+                                "(profiles/r01_fp64_peak.json) x n_gpus; MEASURED_PEAKS.json has no fp64 figure"),
+                "traffic": None, "algorithmic_flops_per_step": float(tot[2]) / args.steps,
+                "launches_per_step": acc["update_launches"] / args.steps}
+    else:
+        roof = None
     out = {
         "metric": METRIC, "value": n_sel / s_dev, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * s_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-        "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / pred_s,
+        "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / max(s_dev - sel_s, 1e-9) if grid_backend else N / pred_s,
         "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s},
         "n_selected": n_sel, "n_in_model": n_model,
         "e2e": {"value": n_sel / s_e2e, "unit": "pts/s", "ms_per_step": 1e3 * s_e2e,
-                "h2d_bytes_per_step": int(N * (D + 1) * 8 + N * D * 8),
+                "h2d_bytes_per_step": int(N * 8) if grid_backend else int(N * (D + 1) * 8 + N * D * 8),
                 "d2h_bytes_per_step": int(N * 2 * 8 + n_sel * 8)},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_update (candidate update + straddle score + arg-max)", "bound": "hbm",
+        "roofline": roof if roof else {"kernel": "k_update (candidate update + straddle score + arg-max)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs x n_gpus" if peaks else "fallback 6650 GB/s",
                      "traffic": None,
                      "algorithmic_bytes_per_step": float(tot[0]) / args.steps,
                      "panel_bytes_touched_per_step": float(tot[1]) / args.steps,
                      "launches_per_step": acc["update_launches"] / args.steps,
-                     "predict_tflops_fp64": (N * float(R) * R + 2.0 * N * R) / pred_s / 1e12},
+                     "predict_tflops_fp64": (N * float(R) * R + 2.0 * N * R) / max(pred_s, 1e-9) / 1e12},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -332,6 +365,9 @@ def main():
     ap.add_argument("--ref-predict-points", type=int, default=16384)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
+    ap.add_argument("--backend", default="grid", choices=["grid", "panel"],
+                    help="grid: lattice candidates, separable DMMA path (default); panel: arbitrary-point HBM path")
     args = ap.parse_args()
     if args.impl == "reference":
         args.warmup_ref = min(args.warmup, 1)

@@ -36,7 +36,7 @@ struct gpis_engine {
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
-  size_t w_bytes = 0;
+  size_t w_bytes = 0, gws_bytes = 0;
   bool selecting = false;
   int inverse_rows = -1;        // rows Wt/alpha are valid for
   int upd_grid = 0;
@@ -85,13 +85,14 @@ struct Dispatch {
   void (*g_point)(EngineParams, int);
   void (*g_solve)(EngineParams);
   void (*g_wrow)(EngineParams);
-  void (*g_update)(EngineParams);
+  void (*g_gemm)(EngineParams);
+  void (*g_epi)(EngineParams);
 };
 
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB>, k_grid_wrow<NB>, k_grid_update<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -127,9 +128,14 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
 
 gpis_status launch_update(gpis_engine* e, cudaStream_t s) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
-  if (e->backend == 2) d.g_update<<<e->grid_ctas, GUPD_THREADS, GUPD_SMEM, s>>>(e->P);
-  else d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
-  e->launches++;
+  if (e->backend == 2) {
+    d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
+    d.g_epi<<<4 * e->grid_ctas, 128, 0, s>>>(e->P);
+    e->launches += 2;
+  } else {
+    d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
+    e->launches++;
+  }
   CU(cudaGetLastError());
   return GPIS_OK;
 }
@@ -279,7 +285,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->upd_smem = sizeof(double) * NB * (size_t)P.ell_chunk;
     CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
     CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
-    CU(cudaFuncSetAttribute((const void*)disp.g_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GUPD_SMEM));
+    CU(cudaFuncSetAttribute((const void*)disp.g_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     e->solve_ctas = e->num_sms * 2;
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)disp.update, UPD_THREADS, e->upd_smem));
@@ -384,8 +390,17 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   }
   const int tiles = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT) * P.glen[2];
   e->grid_ctas = tiles;
-  if ((size_t)tiles > (size_t)e->upd_grid) {
-    CU(dalloc(e, &P.partials, (size_t)tiles));
+  if ((size_t)4 * tiles > (size_t)e->upd_grid) {
+    CU(dalloc(e, &P.partials, (size_t)4 * tiles));
+  }
+  P.gemm_ctas = e->num_sms;
+  P.gws_segmax = P.gemm_ctas / tiles + 2;
+  {
+    const size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
+    if (need > e->gws_bytes) {
+      CU(dalloc(e, &P.gws, need / sizeof(double)));
+      e->gws_bytes = need;
+    }
   }
   e->backend = 2;
   e->have_candidates = true;
@@ -504,7 +519,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       CU(cudaEventRecord(e->prof_events[2 * it + 1], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += e->backend == 2 ? 4 : 2;
+      e->launches += e->backend == 2 ? 5 : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;

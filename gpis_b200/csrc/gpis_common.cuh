@@ -86,6 +86,9 @@ struct EngineParams {
   double* Wt;              // its transpose (shared with the predict kernel)
   long long ldW;
   double* kvec;            // [MAXNB][R_cap] covariance of the new rows with the model rows
+  double* gws;             // split-K workspace [NB][tiles][gws_segmax][128*128]
+  int gws_segmax;
+  int gemm_ctas;           // persistent grid of the update GEMM
   // model
   double inv_ell2, sf2, level, eps, beta, beta_delta, noise_scalar;
   double mean_w[MAXD], mean_c;

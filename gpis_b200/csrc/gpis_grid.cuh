@@ -18,10 +18,10 @@ namespace gpis {
 constexpr int GT = 128;         // tile edge (jy x jx) of the update GEMM
 constexpr int GKC = 16;         // model rows per pipeline stage
 constexpr int GLD = GT + 4;     // padded smem row (conflict-free DMMA fragment loads)
-constexpr int GSTAGES = 3;
-constexpr int GUPD_THREADS = 512;
+
+
 constexpr int GSOLVE_THREADS = 256;
-constexpr size_t GUPD_SMEM = (size_t)GSTAGES * (2 * GKC * GLD + GKC) * sizeof(double);
+
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -131,8 +131,19 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
     double acc[NB];
 #pragma unroll
     for (int a = 0; a < NB; ++a) acc[a] = 0.0;
-    for (int c = lane; c <= s; c += 32) {
-      const double w = wrow[c];
+    // 8 independent 256-byte row segments in flight per warp (the pass is bandwidth-bound)
+    int c = lane;
+    for (; c + 32 * 7 <= s; c += 32 * 8) {
+      double w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(wrow + c + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int a = 0; a < NB; ++a) acc[a] += w[u] * P.kvec[(long long)a * P.R_cap + c + 32 * u];
+    }
+    for (; c <= s; c += 32) {
+      const double w = __ldg(wrow + c);
 #pragma unroll
       for (int a = 0; a < NB; ++a) acc[a] += w * P.kvec[(long long)a * P.R_cap + c];
     }
@@ -225,8 +236,18 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
     double acc[NB];
 #pragma unroll
     for (int a = 0; a < NB; ++a) acc[a] = 0.0;
-    for (int s = rho + lane; s < r0; s += 32) {
-      const double w = wt[s];
+    int s = rho + lane;
+    for (; s + 32 * 7 < r0; s += 32 * 8) {
+      double w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(wt + s + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int a = 0; a < NB; ++a) acc[a] += w[u] * X[a][s + 32 * u];
+    }
+    for (; s < r0; s += 32) {
+      const double w = __ldg(wt + s);
 #pragma unroll
       for (int a = 0; a < NB; ++a) acc[a] += w * X[a][s];
     }
@@ -248,22 +269,185 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
 }
 
 // ---------------------------------------------------------------------------------------
-// K3: the per-step update as a GEMM on the fp64 tensor pipe + straddle scoring + arg-max.
-// CTA tile: 128 (jy) x 128 (jx) at one jz; 16 warps, 32 x 32 each = 4 x 4 DMMA.8x8x4 tiles.
+// K3a: the per-step update as a split-K GEMM on the fp64 tensor pipe (DMMA.8x8x4).
+//
+// Persistent: one CTA per SM.  Work unit = (128x128 tile of one z-slice, 16-row chunk of the
+// model); the flattened unit range is cut into gridDim.x equal pieces (stream-K style), so
+// every SM gets the same share whatever the tile count is (128 tiles on 148 SMs; 16 tiles per
+// GPU when the lattice is sharded 8 ways).  Each CTA writes the partial accumulators of the
+// (at most a few) tile segments it covered to a workspace; K3b sums them and runs the epilogue.
+//
+// Warp-specialised: the last warp is the producer -- one bulk async copy (TMA engine, UBLKCP) per
+// 1 KB axis-table row into padded shared-memory rows, completion on an mbarrier; warps 0-7
+// consume (32x64 warp tiles = 4x8 DMMA tiles) and hand stages back through "empty" mbarriers.
+// No CTA-wide barrier in the main loop.
 // ---------------------------------------------------------------------------------------
+constexpr int GSTAGE_DOUBLES = 2 * GKC * GLD + GKC;
+constexpr int GPIPE = 4;
+constexpr int GEMM_CWARPS = 8;                       // consumer warps: 4 (jy) x 2 (jx), 32 x 64 each
+constexpr int GEMM_THREADS = (GEMM_CWARPS + 1) * 32;   // + 1 producer warp
+constexpr size_t GEMM_SMEM = (size_t)GPIPE * GSTAGE_DOUBLES * sizeof(double) + 2 * GPIPE * sizeof(unsigned long long);
+constexpr int GTILE_ELEMS = GT * GT;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// owner CTA of flattened unit u when U units are cut into G ranges [g*U/G, (g+1)*U/G)
+__device__ __forceinline__ int unit_owner(long long u, long long U, int G) {
+  return (int)(((u + 1) * G + U - 1) / U) - 1;
+}
+
 template <int NB>
-__global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
   extern __shared__ __align__(16) double g_smem[];
-  DevState* st = P.st;
+  const DevState* st = P.st;
   if (st->done) return;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(g_smem + (size_t)GPIPE * GSTAGE_DOUBLES);
+  unsigned long long* empty = full + GPIPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  if (tid == 0) {
+    for (int i = 0; i < GPIPE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], GEMM_CWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
   const int r0 = st->r0;
   const int nx = P.glen[0], ny = P.glen[1];
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
-  const int tz = blockIdx.x / (tiles_x * tiles_y);
-  const int ty = (blockIdx.x / tiles_x) % tiles_y, tx = blockIdx.x % tiles_x;
-  const int gz = P.gz0 + tz;
+  const int T = tiles_x * tiles_y * P.glen[2];
+  const int C = (r0 + NB + GKC - 1) / GKC;           // chunks per tile (all passes share the count)
+  const long long U = (long long)T * C;
+  // fewer units than CTAs: only the first U CTAs work, so every working CTA's range is non-empty
+  const int G = (int)min((long long)gridDim.x, U), g = blockIdx.x;
+  if (g >= G) return;
+  const long long u0 = (long long)g * U / G, u1 = (long long)(g + 1) * U / G;
+  int stage = 0;
+  unsigned phase = 0;
+
+  if (warp == GEMM_CWARPS) {
+    // ------------------------------- producer -------------------------------
+    for (int a = 0; a < NB; ++a) {
+      const double* wrow = P.W + (long long)(r0 + a) * P.ldW;
+      const int klen = r0 + a + 1;
+      for (long long u = u0; u < u1; ++u) {
+        const int tile = (int)(u / C), c = (int)(u % C);
+        const int tz = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
+        mbar_wait(&empty[stage], phase ^ 1);
+        double* As = g_smem + (size_t)stage * GSTAGE_DOUBLES;
+        double* Bs = As + GKC * GLD;
+        double* cs = Bs + GKC * GLD;
+        const long long rho0 = (long long)c * GKC;
+        if (lane < GKC) {
+          const long long rho = rho0 + lane;
+          double cv = rho < klen ? wrow[rho] : 0.0;
+          cv *= P.T[2][rho * P.ldt[2] + P.gz0 + tz];
+          cs[lane] = cv;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], 2 * GKC * GT * (unsigned)sizeof(double));
+        __syncwarp();
+        if (lane < GKC)
+          bulk_g2s(As + lane * GLD, P.T[1] + (rho0 + lane) * P.ldt[1] + ty * GT, GT * sizeof(double), &full[stage]);
+        else
+          bulk_g2s(Bs + (lane - GKC) * GLD, P.T[0] + (rho0 + lane - GKC) * P.ldt[0] + tx * GT, GT * sizeof(double), &full[stage]);
+        if (++stage == GPIPE) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // --------------------------------- consumers ---------------------------------
+  const int wm = warp >> 1, wn = warp & 1;
+  for (int a = 0; a < NB; ++a) {
+    long long u = u0;
+    while (u < u1) {
+      const int tile = (int)(u / C);
+      const long long uend = min(u1, (long long)(tile + 1) * C);
+      double acc[4][8][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (; u < uend; ++u) {
+        mbar_wait(&full[stage], phase);
+        const double* As = g_smem + (size_t)stage * GSTAGE_DOUBLES;
+        const double* Bs = As + GKC * GLD;
+        const double* cs = Bs + GKC * GLD;
+#pragma unroll
+        for (int k4 = 0; k4 < GKC / 4; ++k4) {
+          const int kb = k4 * 4 + (lane & 3);
+          const double cv = cs[kb];
+          double af[4], bf[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) af[i] = As[kb * GLD + wm * 32 + i * 8 + (lane >> 2)] * cv;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bf[j] = Bs[kb * GLD + wn * 64 + j * 8 + (lane >> 2)];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == GPIPE) { stage = 0; phase ^= 1; }
+      }
+      // partial accumulators of this (tile, segment) -> workspace, fragment-native layout
+      const int seg = g - unit_owner((long long)tile * C, U, G);
+      double2* ws = reinterpret_cast<double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax + seg) * GTILE_ELEMS);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          ws[(warp * 32 + i * 8 + j) * 32 + lane] = make_double2(acc[i][j][0], acc[i][j][1]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3b: sum the split-K partials, update the posterior, straddle score, classify, arg-max.
+// One CTA (128 threads) per (tile, warp row) of the GEMM's fragment layout.
+// ---------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(128) k_grid_epilogue(EngineParams P) {
+  DevState* st = P.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, ew = tid >> 5;
+  const int wn = ew >> 1, jh = ew & 1;        // GEMM warp column, half of its 8 DMMA column tiles
+  const int tile = blockIdx.x >> 2, wm = blockIdx.x & 3;
+  const int r0 = st->r0;
+  const int nx = P.glen[0], ny = P.glen[1];
+  const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
+  const int T = tiles_x * tiles_y * P.glen[2];
+  const int tz = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
+  const int C = (r0 + NB + GKC - 1) / GKC;
+  const long long U = (long long)T * C;
+  const int G = (int)min((long long)P.gemm_ctas, U);
+  const int g_first = unit_owner((long long)tile * C, U, G);
+  const int nseg = unit_owner((long long)(tile + 1) * C - 1, U, G) - g_first + 1;
+  const int gwarp = wm * 2 + wn;
   const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
   double beta = P.beta;
   if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
@@ -273,112 +457,63 @@ __global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P)
   double best_s = NEG_INF;
   long long best_id = 0x7fffffffffffffffLL, best_j = -1;
   int n_scored = 0;
+  double gn[NB];
+#pragma unroll
+  for (int a = 0; a < NB; ++a) gn[a] = st->gnew[a];
 
-  for (int a = 0; a < NB; ++a) {
-    const double* wrow = P.W + (long long)(r0 + a) * P.ldW;
-    const double ga = st->gnew[a];
-    const int klen = r0 + a + 1;
-    const int nchunks = (klen + GKC - 1) / GKC;
-    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 4; ++i) {
+    const int jy = ty * GT + wm * 32 + i * 8 + (lane >> 2);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    auto issue = [&](int c) {
-      double* As = g_smem + (size_t)(c % GSTAGES) * (2 * GKC * GLD + GKC);
-      double* Bs = As + GKC * GLD;
-      double* cs = Bs + GKC * GLD;
-      const long long rho0 = (long long)c * GKC;
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = jh * 4 + jj;
+      const int jx0 = tx * GT + wn * 64 + j * 8 + 2 * (lane & 3);
+      double dv[2] = {0.0, 0.0}, dm[2] = {0.0, 0.0};
 #pragma unroll
-      for (int i = 0; i < (GKC * GT / 2) / GUPD_THREADS; ++i) {
-        const int q = tid + i * GUPD_THREADS;
-        const int kk = q / (GT / 2), c2 = q % (GT / 2);
-        g_cp_async16(As + kk * GLD + c2 * 2, P.T[1] + (rho0 + kk) * P.ldt[1] + ty * GT + c2 * 2);
-        g_cp_async16(Bs + kk * GLD + c2 * 2, P.T[0] + (rho0 + kk) * P.ldt[0] + tx * GT + c2 * 2);
+      for (int a = 0; a < NB; ++a) {
+        const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS)
+                            + (gwarp * 32 + i * 8 + j) * 32 + lane;
+        double v0 = 0.0, v1 = 0.0;
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          const double2 p = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2));
+          v0 += p.x; v1 += p.y;
+        }
+        dv[0] += v0 * v0; dv[1] += v1 * v1;
+        dm[0] += v0 * gn[a]; dm[1] += v1 * gn[a];
       }
-      if (tid < GKC) {
-        const long long rho = rho0 + tid;
-        double cv = rho < klen ? wrow[rho] : 0.0;
-        if (P.T[2]) cv *= P.T[2][rho * P.ldt[2] + gz];
-        cs[tid] = cv;
-      }
-      g_cp_commit();
-    };
-
-    issue(0);
-    if (nchunks > 1) issue(1); else g_cp_commit();
-    for (int c = 0; c < nchunks; ++c) {
-      g_cp_wait<1>();
-      __syncthreads();
-      if (c + 2 < nchunks) issue(c + 2); else g_cp_commit();
-      const double* As = g_smem + (size_t)(c % GSTAGES) * (2 * GKC * GLD + GKC);
-      const double* Bs = As + GKC * GLD;
-      const double* cs = Bs + GKC * GLD;
-#pragma unroll
-      for (int k4 = 0; k4 < GKC / 4; ++k4) {
-        const int kb = k4 * 4 + (lane & 3);
-        const double cv = cs[kb];
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = As[kb * GLD + wm * 32 + i * 8 + (lane >> 2)] * cv;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = Bs[kb * GLD + wn * 32 + j * 8 + (lane >> 2)];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-      }
-    }
-    g_cp_wait<0>();
-    __syncthreads();
-
-    // epilogue: posterior update; scoring on the last pass
-    const bool last = (a == NB - 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int jy = ty * GT + wm * 32 + i * 8 + (lane >> 2);
       if (jy >= ny) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int jx0 = tx * GT + wn * 32 + j * 8 + 2 * (lane & 3);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int jx = jx0 + e;
-          if (jx >= nx) continue;
-          const long long jl = (long long)jx + (long long)nx * (jy + (long long)ny * tz);
-          const double v = acc[i][j][e];
-          const double var = P.var[jl] - v * v;
-          const double mu = P.mu[jl] + v * ga;
-          P.var[jl] = var;
-          P.mu[jl] = mu;
-          if (last) {
-            unsigned char f = P.flags[jl];
-            if (!(f & (F_ACTIVE | F_HIGH | F_LOW))) {
-              ++n_scored;
-              double ve = var;
-              if (P.variance_mode == 1) ve = __dadd_rn(var, P.noise ? P.noise[jl] : P.noise_scalar);
-              const double w = __dmul_rn(sb, ve);
-              const double hi = __dadd_rn(mu, w), lo = __dadd_rn(mu, -w);
-              double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-              P.amb[jl] = sc;
-              if (__dadd_rn(lo, P.eps) > P.level) f |= F_HIGH;
-              if (__dadd_rn(hi, -P.eps) < P.level) f |= F_LOW;
-              P.flags[jl] = f;
-              if (sc == sc) {
-                const long long id = cand_id(P, jl);
-                if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
-              }
-            }
+      for (int e = 0; e < 2; ++e) {
+        const int jx = jx0 + e;
+        if (jx >= nx) continue;
+        const long long jl = (long long)jx + (long long)nx * (jy + (long long)ny * tz);
+        const double var = P.var[jl] - dv[e];
+        const double mu = P.mu[jl] + dm[e];
+        P.var[jl] = var;
+        P.mu[jl] = mu;
+        unsigned char f = P.flags[jl];
+        if (!(f & (F_ACTIVE | F_HIGH | F_LOW))) {
+          ++n_scored;
+          double ve = var;
+          if (P.variance_mode == 1) ve = __dadd_rn(var, P.noise ? P.noise[jl] : P.noise_scalar);
+          const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
+          const double hi = __dadd_rn(mu, w), lo = __dadd_rn(mu, -w);
+          const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
+          P.amb[jl] = sc;
+          if (__dadd_rn(lo, P.eps) > P.level) f |= F_HIGH;     // :122-125
+          if (__dadd_rn(hi, -P.eps) < P.level) f |= F_LOW;
+          P.flags[jl] = f;
+          if (sc == sc) {
+            const long long id = cand_id(P, jl);
+            if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
           }
         }
       }
     }
   }
 
-  // CTA arg-max, then grid arg-max by the last CTA
-  __shared__ BlockBest s_bb[GUPD_THREADS / 32];
-  __shared__ int s_cnt[GUPD_THREADS / 32];
+  __shared__ BlockBest s_bb[4];
+  __shared__ int s_cnt[4];
   __shared__ int s_last;
   for (int o = 16; o > 0; o >>= 1) {
     const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
@@ -387,12 +522,12 @@ __global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P)
     if (oj >= 0 && better(os, oid, best_s, best_id)) { best_s = os; best_id = oid; best_j = oj; }
     n_scored += __shfl_xor_sync(0xffffffffu, n_scored, o);
   }
-  if (lane == 0) { s_bb[warp].score = best_s; s_bb[warp].id = best_id; s_bb[warp].local = best_j; s_cnt[warp] = n_scored; }
+  if (lane == 0) { s_bb[ew].score = best_s; s_bb[ew].id = best_id; s_bb[ew].local = best_j; s_cnt[ew] = n_scored; }
   __syncthreads();
   if (tid == 0) {
     BlockBest b = s_bb[0];
     int cnt = s_cnt[0];
-    for (int w = 1; w < GUPD_THREADS / 32; ++w) {
+    for (int w = 1; w < 4; ++w) {
       cnt += s_cnt[w];
       if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
     }
@@ -407,7 +542,7 @@ __global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P)
   __threadfence();
   BlockBest b;
   b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
-  for (int i = tid; i < (int)gridDim.x; i += GUPD_THREADS) {
+  for (int i = tid; i < (int)gridDim.x; i += 128) {
     const volatile BlockBest* pp = &P.partials[i];
     const double ps = pp->score;
     const long long pid = pp->id, ploc = pp->local;
@@ -420,16 +555,16 @@ __global__ void __launch_bounds__(GUPD_THREADS, 1) k_grid_update(EngineParams P)
     if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; }
   }
   __syncthreads();
-  if (lane == 0) s_bb[warp] = b;
+  if (lane == 0) s_bb[ew] = b;
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < GUPD_THREADS / 32; ++w)
+    for (int w = 1; w < 4; ++w)
       if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
     s_bb[0] = b;
     const int it = st->iter;
     if (it <= P.M_cap) {
       P.hist[it] = r0;
-      P.hist[(P.M_cap + 1) + it] = (int)gridDim.x;
+      P.hist[(P.M_cap + 1) + it] = T;
       P.hist[2 * (P.M_cap + 1) + it] = *(volatile int*)&st->n_scored;
     }
     st->n_scored = 0;

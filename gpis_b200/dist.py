@@ -27,6 +27,13 @@ def shard_range(n, rank, world):
     return min(t0 * 64, n), min(t1 * 64, n)
 
 
+def slab_range(nz, rank, world):
+    """z-slabs of a lattice for the grid backend: [z0, z1)."""
+    per, extra = divmod(nz, world)
+    z0 = rank * per + min(rank, extra)
+    return z0, z0 + per + (1 if rank < extra else 0)
+
+
 def owner_of(index, n, world):
     for r in range(world):
         lo, hi = shard_range(n, r, world)

@@ -210,6 +210,10 @@ class GpisEngine:
         self._ck(self.lib.gpis_get_candidate_posterior(self.h, _ptr(mu), _ptr(var), _stream()))
         return mu, var
 
+    def candidate_posterior_into(self, mean, var):
+        """Raw form: preallocated host or device outputs."""
+        self._ck(self.lib.gpis_get_candidate_posterior(self.h, _ptr(mean), _ptr(var), _stream()))
+
     def stats(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         self._ck(self.lib.gpis_get_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
