@@ -36,7 +36,7 @@ struct gpis_engine {
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
-  size_t w_bytes = 0, gws_bytes = 0;
+  size_t w_bytes = 0, gws_bytes = 0, partials_cap = 0, state_cap = 0, grid_slots = 0;
   bool selecting = false;
   int inverse_rows = -1;        // rows Wt/alpha are valid for
   int upd_grid = 0;
@@ -130,7 +130,7 @@ gpis_status launch_update(gpis_engine* e, cudaStream_t s) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2) {
     d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
-    d.g_epi<<<4 * e->grid_ctas, 128, 0, s>>>(e->P);
+    d.g_epi<<<GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s>>>(e->P);
     e->launches += 2;
   } else {
     d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
@@ -292,6 +292,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     if (occ < 1) return fail(e, GPIS_ERR_CUDA, "update kernel does not fit on an SM");
     e->upd_grid = e->num_sms * occ;
     CU(dalloc(e, &P.partials, (size_t)e->upd_grid));
+    e->partials_cap = (size_t)e->upd_grid;
+    e->state_cap = Nn;
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
     return GPIS_OK;
@@ -390,8 +392,18 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   }
   const int tiles = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT) * P.glen[2];
   e->grid_ctas = tiles;
-  if ((size_t)4 * tiles > (size_t)e->upd_grid) {
-    CU(dalloc(e, &P.partials, (size_t)4 * tiles));
+  if ((size_t)GEPI_CTAS_PER_TILE * tiles > e->partials_cap) {
+    CU(dalloc(e, &P.partials, (size_t)GEPI_CTAS_PER_TILE * tiles));
+    e->partials_cap = (size_t)GEPI_CTAS_PER_TILE * tiles;
+  }
+  // per-candidate state in tile/fragment order (padded to whole tiles)
+  e->grid_slots = (size_t)tiles * GTILE_ELEMS;
+  if (e->grid_slots > e->state_cap) {
+    CU(dalloc(e, &P.mu, e->grid_slots));
+    CU(dalloc(e, &P.var, e->grid_slots));
+    CU(dalloc(e, &P.amb, e->grid_slots));
+    CU(dalloc(e, &P.flags, e->grid_slots));
+    e->state_cap = e->grid_slots;
   }
   P.gemm_ctas = e->num_sms;
   P.gws_segmax = P.gemm_ctas / tiles + 2;
@@ -422,7 +434,11 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   if (first_local >= e->P.N) return fail(e, GPIS_ERR_INVALID, "first index out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = std::max<long long>(e->P.N, e->P.n_tiles);
-  if (n > 0) {
+  if (e->backend == 2) {
+    k_grid_init_state<<<(unsigned)((e->grid_slots + 255) / 256), 256, 0, s>>>(e->P, (long long)e->grid_slots);
+    CU(cudaGetLastError());
+    e->launches++;
+  } else if (n > 0) {
     k_init_candidates<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->P);
     CU(cudaGetLastError());
     e->launches++;
@@ -714,21 +730,32 @@ gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, u
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
   if (!N) return GPIS_OK;
-  if (ambiguity) CU(cudaMemcpyAsync(ambiguity, e->P.amb, sizeof(double) * N, cudaMemcpyDefault, s));
-  if (high || low || active) {
-    unsigned char* tmp = nullptr;
-    CU(cudaMalloc(&tmp, 3 * N));
-    k_split_flags<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P.flags, (long long)N, tmp, tmp + N, tmp + 2 * N);
+  double* tmp_amb = nullptr;
+  unsigned char* tmp = nullptr;
+  cudaError_t ce = cudaMalloc(&tmp, 4 * N);
+  if (ce == cudaSuccess && e->backend == 2) ce = cudaMalloc(&tmp_amb, sizeof(double) * N);
+  const double* amb_src = e->P.amb;
+  const unsigned char* flag_src = e->P.flags;
+  if (ce == cudaSuccess && e->backend == 2) {     // state is stored in tile/fragment order: export it
+    k_grid_export<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P, nullptr, nullptr, tmp_amb, tmp + 3 * N);
     e->launches++;
-    cudaError_t ce = cudaGetLastError();
+    amb_src = tmp_amb;
+    flag_src = tmp + 3 * N;
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess && ambiguity) ce = cudaMemcpyAsync(ambiguity, amb_src, sizeof(double) * N, cudaMemcpyDefault, s);
+  if (ce == cudaSuccess && (high || low || active)) {
+    k_split_flags<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(flag_src, (long long)N, tmp, tmp + N, tmp + 2 * N);
+    e->launches++;
+    ce = cudaGetLastError();
     if (ce == cudaSuccess && high) ce = cudaMemcpyAsync(high, tmp, N, cudaMemcpyDefault, s);
     if (ce == cudaSuccess && low) ce = cudaMemcpyAsync(low, tmp + N, N, cudaMemcpyDefault, s);
     if (ce == cudaSuccess && active) ce = cudaMemcpyAsync(active, tmp + 2 * N, N, cudaMemcpyDefault, s);
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
-    cudaFree(tmp);
-    if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
   }
-  CU(cudaStreamSynchronize(s));
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  if (tmp) cudaFree(tmp);
+  if (tmp_amb) cudaFree(tmp_amb);
+  if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
   return GPIS_OK;
 }
 
@@ -736,8 +763,32 @@ gpis_status gpis_get_candidate_posterior(gpis_handle e, double* mean, double* va
   if (!e) return GPIS_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
-  if (mean && N) CU(cudaMemcpyAsync(mean, e->P.mu, sizeof(double) * N, cudaMemcpyDefault, s));
-  if (var && N) CU(cudaMemcpyAsync(var, e->P.var, sizeof(double) * N, cudaMemcpyDefault, s));
+  if (!N) return GPIS_OK;
+  if (e->backend == 2) {
+    // export from tile/fragment order; straight into the caller's buffers when they are device memory
+    cudaPointerAttributes at;
+    auto on_device = [&](const void* p) {
+      if (!p) return true;
+      if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+    };
+    const bool dev = on_device(mean) && on_device(var);
+    double* tmp = nullptr;
+    if (!dev) CU(cudaMalloc(&tmp, sizeof(double) * 2 * N));
+    k_grid_export<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P, dev ? mean : tmp, dev ? var : tmp + N, nullptr, nullptr);
+    e->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (!dev) {
+      if (ce == cudaSuccess && mean) ce = cudaMemcpyAsync(mean, tmp, sizeof(double) * N, cudaMemcpyDeviceToHost, s);
+      if (ce == cudaSuccess && var) ce = cudaMemcpyAsync(var, tmp + N, sizeof(double) * N, cudaMemcpyDeviceToHost, s);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    if (tmp) cudaFree(tmp);
+    if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
+    return GPIS_OK;
+  }
+  if (mean) CU(cudaMemcpyAsync(mean, e->P.mu, sizeof(double) * N, cudaMemcpyDefault, s));
+  if (var) CU(cudaMemcpyAsync(var, e->P.var, sizeof(double) * N, cudaMemcpyDefault, s));
   CU(cudaStreamSynchronize(s));
   return GPIS_OK;
 }

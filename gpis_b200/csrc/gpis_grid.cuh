@@ -27,6 +27,76 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+// Internal layout of the per-candidate state (mu, var, ambiguity, flags) in the grid backend:
+// tile-major, and inside a 128x128 tile the order of the update GEMM's accumulator fragments,
+// so that the epilogue streams it with fully coalesced 16-byte accesses.
+__host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, int jy, int tz) {
+  const int tiles_x = (P.glen[0] + GT - 1) / GT, tiles_y = (P.glen[1] + GT - 1) / GT;
+  const long long tile = ((long long)tz * tiles_y + jy / GT) * tiles_x + jx / GT;
+  const int my = jy % GT, mx = jx % GT;
+  const int gwarp = (my / 32) * 2 + mx / 64;
+  const int frag = (gwarp * 32 + ((my % 32) / 8) * 8 + (mx % 64) / 8) * 32 + (my % 8) * 4 + (mx % 8) / 2;
+  return tile * (GT * GT) + frag * 2 + (mx & 1);
+}
+__host__ __device__ inline long long grid_slot_of_local(const EngineParams& P, long long jl) {
+  const int nx = P.glen[0], ny = P.glen[1];
+  return grid_slot(P, (int)(jl % nx), (int)((jl / nx) % ny), (int)(jl / ((long long)nx * ny)));
+}
+// inverse: slot -> (jx, jy, tz); returns false for padding slots
+__host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
+  const int tiles_x = (P.glen[0] + GT - 1) / GT, tiles_y = (P.glen[1] + GT - 1) / GT;
+  const long long tile = slot / (GT * GT);
+  const int w = (int)(slot % (GT * GT));
+  const int e = w & 1, frag = w >> 1;
+  const int lane = frag & 31, t = frag >> 5;
+  const int j = t & 7, i = (t >> 3) & 3, gwarp = t >> 5;
+  const int my = (gwarp >> 1) * 32 + i * 8 + (lane >> 2);
+  const int mx = (gwarp & 1) * 64 + j * 8 + (lane & 3) * 2 + e;
+  tz = (int)(tile / (tiles_x * tiles_y));
+  jy = (int)((tile / tiles_x) % tiles_y) * GT + my;
+  jx = (int)(tile % tiles_x) * GT + mx;
+  return jx < P.glen[0] && jy < P.glen[1];
+}
+
+__global__ void k_grid_init_state(EngineParams P, long long nslots) {
+  const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (slot >= nslots) return;
+  int jx, jy, tz;
+  if (grid_unslot(P, slot, jx, jy, tz)) {
+    const int jd[3] = {jx, jy, tz + P.gz0};
+    double m = P.mean_c;
+    for (int d = 0; d < MAXD; ++d) m += P.mean_w[d] * (P.gorg[d] + P.gh[d] * (double)jd[d]);
+    P.mu[slot] = m;
+    P.var[slot] = P.sf2;
+    P.flags[slot] = 0;
+  } else {                         // padding of partial tiles: never scored
+    P.mu[slot] = 0.0;
+    P.var[slot] = 0.0;
+    P.flags[slot] = F_HIGH | F_LOW;
+  }
+  P.amb[slot] = 0.0;
+}
+
+// natural-order copies of the state for the getters
+__global__ void k_grid_export(EngineParams P, double* mu, double* var, double* amb, unsigned char* flags) {
+  const long long jl = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (jl >= P.N) return;
+  const long long slot = grid_slot_of_local(P, jl);
+  if (mu) mu[jl] = P.mu[slot];
+  if (var) var[jl] = P.var[slot];
+  if (amb) {      // straddle score of the current posterior (select_active_set_straddle.m:106-108)
+    double beta = P.beta;
+    const double it = (double)(P.st->iter > 0 ? P.st->iter : 1);
+    if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * it * 9.869604401089358 / (6.0 * P.beta_delta));
+    else if (P.beta_mode == 2) beta = 2.0 * log((double)P.N_total * 9.869604401089358 * it * it / (6.0 * P.beta_delta));
+    double ve = P.var[slot];
+    if (P.variance_mode == 1) ve += P.noise ? P.noise[jl] : P.noise_scalar;
+    const double w = sqrt(beta) * ve, m = P.mu[slot];
+    amb[jl] = fmin(m + w - P.level, P.level - (m - w));
+  }
+  if (flags) flags[jl] = P.flags[slot];
+}
+
 __device__ __forceinline__ void g_cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -70,7 +140,7 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
   const long long* pl = reinterpret_cast<const long long*>(pay);
   const int r0 = st->r, m = st->m;
   if (tid == 0) {
-    if (win == P.rank) P.flags[pl[PAY_LOCAL]] |= F_ACTIVE;
+    if (win == P.rank) P.flags[grid_slot_of_local(P, pl[PAY_LOCAL])] |= F_ACTIVE;
     P.sel_ids[m] = pl[PAY_ID];
     st->n_sel = m + 1;
   }
@@ -428,92 +498,91 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
 
 // ---------------------------------------------------------------------------------------
 // K3b: sum the split-K partials, update the posterior, straddle score, classify, arg-max.
-// One CTA (128 threads) per (tile, warp row) of the GEMM's fragment layout.
+// One thread per accumulator fragment slot (two x-adjacent candidates): every access to the
+// workspace and to the per-candidate state is a coalesced 16-byte (flags: 2-byte) access.
 // ---------------------------------------------------------------------------------------
+constexpr int GEPI_THREADS = 256;
+constexpr int GEPI_CTAS_PER_TILE = (GTILE_ELEMS / 2) / GEPI_THREADS;
+
 template <int NB>
-__global__ void __launch_bounds__(128) k_grid_epilogue(EngineParams P) {
+__global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) {
   DevState* st = P.st;
   if (st->done) return;
   const int tid = threadIdx.x, lane = tid & 31, ew = tid >> 5;
-  const int wn = ew >> 1, jh = ew & 1;        // GEMM warp column, half of its 8 DMMA column tiles
-  const int tile = blockIdx.x >> 2, wm = blockIdx.x & 3;
+  const int tile = blockIdx.x / GEPI_CTAS_PER_TILE;
+  const int q = (blockIdx.x % GEPI_CTAS_PER_TILE) * GEPI_THREADS + tid;      // double2 slot in the tile
   const int r0 = st->r0;
   const int nx = P.glen[0], ny = P.glen[1];
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
   const int T = tiles_x * tiles_y * P.glen[2];
-  const int tz = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
   const int C = (r0 + NB + GKC - 1) / GKC;
   const long long U = (long long)T * C;
   const int G = (int)min((long long)P.gemm_ctas, U);
   const int g_first = unit_owner((long long)tile * C, U, G);
   const int nseg = unit_owner((long long)(tile + 1) * C - 1, U, G) - g_first + 1;
-  const int gwarp = wm * 2 + wn;
   const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
   double beta = P.beta;
   if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
   else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
   const double sb = sqrt(beta);
 
+  double dv[2] = {0.0, 0.0}, dm[2] = {0.0, 0.0};
+#pragma unroll
+  for (int a = 0; a < NB; ++a) {
+    const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS) + q;
+    double v0 = 0.0, v1 = 0.0;
+    for (int sgi = 0; sgi < nseg; ++sgi) {
+      const double2 p = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2));
+      v0 += p.x; v1 += p.y;
+    }
+    const double ga = st->gnew[a];
+    dv[0] += v0 * v0; dv[1] += v1 * v1;
+    dm[0] += v0 * ga; dm[1] += v1 * ga;
+  }
+  const long long slot2 = (long long)tile * (GTILE_ELEMS / 2) + q;
+  double2 mu = reinterpret_cast<double2*>(P.mu)[slot2];
+  double2 var = reinterpret_cast<double2*>(P.var)[slot2];
+  uchar2 fl = reinterpret_cast<uchar2*>(P.flags)[slot2];
+  mu.x += dm[0]; mu.y += dm[1];
+  var.x -= dv[0]; var.y -= dv[1];
+  reinterpret_cast<double2*>(P.mu)[slot2] = mu;
+  reinterpret_cast<double2*>(P.var)[slot2] = var;
+
   double best_s = NEG_INF;
   long long best_id = 0x7fffffffffffffffLL, best_j = -1;
   int n_scored = 0;
-  double gn[NB];
+  unsigned char f[2] = {fl.x, fl.y};
+  const double mus[2] = {mu.x, mu.y}, vars[2] = {var.x, var.y};
+  if (!((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW)))) {
+    int jx, jy, tz;
+    grid_unslot(P, slot2 * 2, jx, jy, tz);
+    double sc2[2] = {0.0, 0.0};
 #pragma unroll
-  for (int a = 0; a < NB; ++a) gn[a] = st->gnew[a];
-
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int jy = ty * GT + wm * 32 + i * 8 + (lane >> 2);
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = jh * 4 + jj;
-      const int jx0 = tx * GT + wn * 64 + j * 8 + 2 * (lane & 3);
-      double dv[2] = {0.0, 0.0}, dm[2] = {0.0, 0.0};
-#pragma unroll
-      for (int a = 0; a < NB; ++a) {
-        const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS)
-                            + (gwarp * 32 + i * 8 + j) * 32 + lane;
-        double v0 = 0.0, v1 = 0.0;
-        for (int sgi = 0; sgi < nseg; ++sgi) {
-          const double2 p = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2));
-          v0 += p.x; v1 += p.y;
-        }
-        dv[0] += v0 * v0; dv[1] += v1 * v1;
-        dm[0] += v0 * gn[a]; dm[1] += v1 * gn[a];
-      }
-      if (jy >= ny) continue;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int jx = jx0 + e;
-        if (jx >= nx) continue;
-        const long long jl = (long long)jx + (long long)nx * (jy + (long long)ny * tz);
-        const double var = P.var[jl] - dv[e];
-        const double mu = P.mu[jl] + dm[e];
-        P.var[jl] = var;
-        P.mu[jl] = mu;
-        unsigned char f = P.flags[jl];
-        if (!(f & (F_ACTIVE | F_HIGH | F_LOW))) {
-          ++n_scored;
-          double ve = var;
-          if (P.variance_mode == 1) ve = __dadd_rn(var, P.noise ? P.noise[jl] : P.noise_scalar);
-          const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
-          const double hi = __dadd_rn(mu, w), lo = __dadd_rn(mu, -w);
-          const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-          P.amb[jl] = sc;
-          if (__dadd_rn(lo, P.eps) > P.level) f |= F_HIGH;     // :122-125
-          if (__dadd_rn(hi, -P.eps) < P.level) f |= F_LOW;
-          P.flags[jl] = f;
-          if (sc == sc) {
-            const long long id = cand_id(P, jl);
-            if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
-          }
-        }
+    for (int e = 0; e < 2; ++e) {
+      if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
+      ++n_scored;
+      const long long jl = (long long)(jx + e) + (long long)nx * (jy + (long long)ny * tz);
+      double ve = vars[e];
+      if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise ? P.noise[jl] : P.noise_scalar);
+      const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
+      const double hi = __dadd_rn(mus[e], w), lo = __dadd_rn(mus[e], -w);
+      const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
+      sc2[e] = sc;
+      if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
+      if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
+      if (sc == sc) {
+        const long long id = cand_id(P, jl);
+        if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
       }
     }
+    // the ambiguity is not stored per step (16 bytes of traffic per candidate): the getter
+    // recomputes it from the running posterior
+    (void)sc2;
+    if (f[0] != fl.x || f[1] != fl.y) reinterpret_cast<uchar2*>(P.flags)[slot2] = make_uchar2(f[0], f[1]);
   }
 
-  __shared__ BlockBest s_bb[4];
-  __shared__ int s_cnt[4];
+  __shared__ BlockBest s_bb[GEPI_THREADS / 32];
+  __shared__ int s_cnt[GEPI_THREADS / 32];
   __shared__ int s_last;
   for (int o = 16; o > 0; o >>= 1) {
     const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
@@ -527,7 +596,7 @@ __global__ void __launch_bounds__(128) k_grid_epilogue(EngineParams P) {
   if (tid == 0) {
     BlockBest b = s_bb[0];
     int cnt = s_cnt[0];
-    for (int w = 1; w < 4; ++w) {
+    for (int w = 1; w < GEPI_THREADS / 32; ++w) {
       cnt += s_cnt[w];
       if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
     }
@@ -542,7 +611,7 @@ __global__ void __launch_bounds__(128) k_grid_epilogue(EngineParams P) {
   __threadfence();
   BlockBest b;
   b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
-  for (int i = tid; i < (int)gridDim.x; i += 128) {
+  for (int i = tid; i < (int)gridDim.x; i += GEPI_THREADS) {
     const volatile BlockBest* pp = &P.partials[i];
     const double ps = pp->score;
     const long long pid = pp->id, ploc = pp->local;
@@ -558,7 +627,7 @@ __global__ void __launch_bounds__(128) k_grid_epilogue(EngineParams P) {
   if (lane == 0) s_bb[ew] = b;
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 4; ++w)
+    for (int w = 1; w < GEPI_THREADS / 32; ++w)
       if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
     s_bb[0] = b;
     const int it = st->iter;
