@@ -198,6 +198,8 @@ def run_ours(args):
     eng.set_profiling(not args.no_profile)
     sel = gdist.ShardedSelector(eng, rank, world, lo, hi)
     sel.profile = not args.no_profile
+    if world > 1 and args.exchange == "peer":
+        sel.enable_peer_exchange()
 
     def step(host):
         P, T = (h_pts, h_tsdf) if host else (d_pts, d_tsdf)
@@ -257,6 +259,11 @@ def run_ours(args):
     ms_e2e, _ = timed(True, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ids, n_model = eng.active()
+    # checksum of the posterior grid (sum of mean and of variance over all lattice points)
+    cs = torch.stack([h_mean.sum(), h_var.sum()]).to(dev)
+    if world > 1:
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    post_sum = [float(cs[0]), float(cs[1])]
 
     # whole-job aggregates over ranks
     tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"], acc["alg_flops"]], dtype=torch.float64, device=dev)
@@ -305,6 +312,8 @@ def run_ours(args):
         "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / max(s_dev - sel_s, 1e-9) if grid_backend else N / pred_s,
         "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s},
         "n_selected": n_sel, "n_in_model": n_model,
+        "ids_crc32": int(__import__("zlib").crc32(np.asarray(ids, np.int64).tobytes())),
+        "posterior_checksum": post_sum,
         "e2e": {"value": n_sel / s_e2e, "unit": "pts/s", "ms_per_step": 1e3 * s_e2e,
                 "h2d_bytes_per_step": int(N * 8) if grid_backend else int(N * (D + 1) * 8 + N * D * 8),
                 "d2h_bytes_per_step": int(N * 2 * 8 + n_sel * 8)},
@@ -366,6 +375,8 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")
     ap.add_argument("--backend", default="grid", choices=["grid", "panel"],
                     help="grid: lattice candidates, separable DMMA path (default); panel: arbitrary-point HBM path")
     args = ap.parse_args()

@@ -51,6 +51,10 @@ struct gpis_engine {
   long long launches = 0;
   std::string err;
   DevState host_state;
+  unsigned epoch = 0;
+  void* xchg_base = nullptr;       // peer exchange region (cudaMalloc, IPC-exported)
+  size_t xchg_bytes = 0;
+  std::vector<void*> ipc_opened;
 };
 
 namespace {
@@ -145,6 +149,8 @@ gpis_status read_state(gpis_engine* e, cudaStream_t s) {
   CU(cudaStreamSynchronize(s));
   if (e->host_state.err == GPIS_ERR_NOT_PD)
     return fail(e, GPIS_ERR_NOT_PD, "covariance block lost positive definiteness while appending a point");
+  if (e->host_state.err == -7)
+    return fail(e, GPIS_ERR_CUDA, "timed out waiting for a peer's exchange record");
   return GPIS_OK;
 }
 
@@ -316,6 +322,7 @@ gpis_status gpis_destroy(gpis_handle e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return GPIS_OK;
@@ -455,7 +462,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
       }
     }
   }
-  k_begin<<<1, 32, 0, s>>>(e->P, first_local < 0 ? -1 : first_local);
+  k_begin<<<1, 32, 0, s>>>(e->P, first_local < 0 ? -1 : first_local, ++e->epoch);
   CU(cudaGetLastError());
   e->launches++;
   e->selecting = true;
@@ -490,11 +497,62 @@ gpis_status gpis_exchange_buffers(gpis_handle e, void** send, void** recv, int64
   return GPIS_OK;
 }
 
+gpis_status gpis_peer_export(gpis_handle e, void* handle64) {
+  if (!e || !handle64) return GPIS_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  EngineParams& P = e->P;
+  if (!e->xchg_base) {
+    const size_t rec = sizeof(double) * 2 * (size_t)P.world * P.pay_stride;
+    e->xchg_bytes = rec + sizeof(unsigned long long) * 2 * P.world;
+    CU(dalloc(e, reinterpret_cast<char**>(&e->xchg_base), e->xchg_bytes));
+    CU(cudaMemset(e->xchg_base, 0, e->xchg_bytes));
+    P.xchg = static_cast<double*>(e->xchg_base);
+    P.xflag = reinterpret_cast<unsigned long long*>(static_cast<char*>(e->xchg_base) + rec);
+  }
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, e->xchg_base));
+  memcpy(handle64, &hd, 64);
+  return GPIS_OK;
+}
+
+gpis_status gpis_peer_import(gpis_handle e, const void* handles, int32_t same_process) {
+  if (!e || !handles) return GPIS_ERR_INVALID;
+  EngineParams& P = e->P;
+  if (!e->xchg_base) return fail(e, GPIS_ERR_STATE, "gpis_peer_export has not been called");
+  const size_t rec = sizeof(double) * 2 * (size_t)P.world * P.pay_stride;
+  std::vector<double*> xp(P.world);
+  std::vector<unsigned long long*> fp(P.world);
+  for (int r = 0; r < P.world; ++r) {
+    void* base = nullptr;
+    if (r == P.rank) base = e->xchg_base;
+    else if (same_process) base = static_cast<void* const*>(handles)[r];
+    else {
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, static_cast<const char*>(handles) + 64 * (size_t)r, 64);
+      CU(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+      e->ipc_opened.push_back(base);
+    }
+    xp[r] = static_cast<double*>(base);
+    fp[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + rec);
+  }
+  if (!P.peer_xchg) {
+    CU(dalloc(e, &P.peer_xchg, (size_t)P.world));
+    CU(dalloc(e, &P.peer_xflag, (size_t)P.world));
+  }
+  CU(cudaMemcpy(P.peer_xchg, xp.data(), sizeof(double*) * P.world, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(P.peer_xflag, fp.data(), sizeof(unsigned long long*) * P.world, cudaMemcpyHostToDevice));
+  P.peer_mode = 1;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
+  return GPIS_OK;
+}
+
 gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
-  if (e->P.world != 1) return fail(e, GPIS_ERR_STATE, "gpis_select needs world_size == 1; drive the step calls");
+  if (e->P.world != 1 && !e->P.peer_mode)
+    return fail(e, GPIS_ERR_STATE, "gpis_select with world_size > 1 needs the peer exchange (gpis_peer_import); "
+                                   "otherwise drive the step calls and all-gather the exchange buffer");
   if (K < 1 || K > e->P.M_cap) return fail(e, GPIS_ERR_INVALID, "K must be in 1..max_active");
-  if (first_local < 0) return fail(e, GPIS_ERR_INVALID, "first index out of range");
+  if (first_local < 0 && e->P.world == 1) return fail(e, GPIS_ERR_INVALID, "first index out of range");
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaEventRecord(e->ev0, s));
   gpis_status rc = gpis_select_begin(e, first_local, stream);
@@ -609,7 +667,11 @@ gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const
   if (normals) CU(cudaMemcpyAsync(hn.data(), normals, sizeof(double) * m * D, cudaMemcpyDefault, s));
   if (noise) CU(cudaMemcpyAsync(hz.data(), noise, sizeof(double) * m, cudaMemcpyDefault, s));
   CU(cudaStreamSynchronize(s));
-  k_begin<<<1, 32, 0, s>>>(e->P, -1);
+  {
+    EngineParams q = e->P;
+    q.peer_mode = 0;
+    k_begin<<<1, 32, 0, s>>>(q, -1, ++e->epoch);
+  }
   CU(cudaGetLastError());
   e->launches++;
   e->selecting = false;
@@ -636,6 +698,7 @@ gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const
     e->P.pay_recv = d_recs + (size_t)i * PAY_HDR;
     e->P.world = 1;
     e->P.rank = 0;
+    e->P.peer_mode = 0;
     rc = launch_append(e, s, 1, 0);
   }
   e->P = saved;

@@ -29,6 +29,7 @@ struct DevState {
   int n_live[2];
   unsigned int blocks_done;
   int n_scored;  // candidates scored (unclassified at the start) in the running iteration
+  unsigned int epoch;  // selection counter: tags the peer-exchange flags of this selection
   long long pending_id;
   double nx[MAXD];          // point appended last
   double Lnn[MAXNB * MAXNB];  // its diagonal block of L
@@ -74,6 +75,13 @@ struct EngineParams {
   double* pay_recv;
   long long pay_stride;    // slots per record
   int rank, world;
+  // peer exchange over NVLink (peer_mode): every rank stores its record straight into all peers'
+  // exchange regions [2 parities][world slots][pay_stride] and raises a flag there; no collective call
+  int peer_mode;
+  double* xchg;
+  unsigned long long* xflag;       // [2][world]
+  double** peer_xchg;              // device array of world pointers (own region included)
+  unsigned long long** peer_xflag;
   int ell_chunk;           // factor rows staged in shared memory per pass
   // grid backend (glen[0] > 0): lattice geometry, separable axis tables, explicit W = L^-1
   int glen[MAXD];          // candidates per axis on THIS rank (z: the local slab)

@@ -105,12 +105,12 @@ __device__ __forceinline__ void g_cp_commit() { asm volatile("cp.async.commit_gr
 template <int N>
 __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ int pick_winner(const EngineParams& P) {
+__device__ __forceinline__ int pick_winner(const EngineParams& P, const double* recs) {
   int win = -1;
   double bs = 0.0;
   long long bid = 0;
   for (int w = 0; w < P.world; ++w) {
-    const double* pay = P.pay_recv + (long long)w * P.pay_stride;
+    const double* pay = recs + (long long)w * P.pay_stride;
     const long long* pl = reinterpret_cast<const long long*>(pay);
     if (pl[PAY_LOCAL] < 0) continue;
     if (win < 0 || better(pay[PAY_SCORE], pl[PAY_ID], bs, bid)) { win = w; bs = pay[PAY_SCORE]; bid = pl[PAY_ID]; }
@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
   __shared__ int s_win;
   if (st->done) return;
   const int tid = threadIdx.x;
+  const int gen = st->iter;
+  if (!wait_records(P, st, gen)) return;
+  const double* recs = records_ptr(P, gen);
   if (tid == 0) {
-    int win = pick_winner(P);
+    int win = pick_winner(P, recs);
     if (win < 0) st->done = 1;
     else if (!finalize_only && st->m >= P.M_cap) { st->done = 1; win = -1; }
     s_win = win;
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
   __syncthreads();
   const int win = s_win;
   if (win < 0) return;
-  const double* pay = P.pay_recv + (long long)win * P.pay_stride;
+  const double* pay = recs + (long long)win * P.pay_stride;
   const long long* pl = reinterpret_cast<const long long*>(pay);
   const int r0 = st->r, m = st->m;
   if (tid == 0) {
@@ -643,6 +646,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   __syncthreads();
   b = s_bb[0];
   write_record(P, b.score, b.local, 0);
+  publish_record(P, st, st->iter, 0);
 }
 
 }  // namespace gpis

@@ -96,7 +96,65 @@ __device__ inline void write_record(const EngineParams& P, double score, long lo
   }
 }
 
-__global__ void k_begin(EngineParams P, long long first_local) {
+
+// ---------------------------------------------------------------------------------------
+// Exchange records.  Collective mode: the host all-gathers pay_send into pay_recv between the
+// update and the append kernels.  Peer mode: the producing kernel stores the record into every
+// rank's exchange region over NVLink and raises a generation flag; the consuming kernel spins on
+// its local flags.  Generation g of a selection is consumed by update iteration g; regions are
+// double-buffered by parity (a rank can be at most one generation ahead of a peer).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ const double* records_ptr(const EngineParams& P, int gen) {
+  return P.peer_mode ? P.xchg + (long long)(gen & 1) * P.world * P.pay_stride : P.pay_recv;
+}
+
+__device__ __forceinline__ unsigned long long record_tag(unsigned epoch, int gen) {
+  return ((unsigned long long)epoch << 32) | (unsigned)(gen + 1);
+}
+
+// whole block; returns false on timeout (a peer died): the caller stops the selection
+__device__ inline bool wait_records(const EngineParams& P, DevState* st, int gen) {
+  if (!P.peer_mode) return true;
+  __shared__ int s_to;
+  if (threadIdx.x == 0) s_to = 0;
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
+    const unsigned long long want = record_tag(st->epoch, gen);
+    volatile unsigned long long* f = P.xflag + (gen & 1) * P.world + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f != want) {
+      if (clock64() - t0 > 6000000000LL) { s_to = 1; break; }     // ~3 s
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (s_to) {
+    if (threadIdx.x == 0) { st->err = -7; st->done = 1; }
+    return false;
+  }
+  return true;
+}
+
+// whole block, after pay_send holds the record (header + `rows` column entries)
+__device__ inline void publish_record(const EngineParams& P, const DevState* st, int gen, int rows) {
+  if (!P.peer_mode) return;
+  __threadfence();
+  __syncthreads();
+  const int n = PAY_HDR + rows;
+  for (int p = 0; p < P.world; ++p) {
+    double* dst = P.peer_xchg[p] + ((long long)(gen & 1) * P.world + P.rank) * P.pay_stride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = P.pay_send[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
+    volatile unsigned long long* f = P.peer_xflag[threadIdx.x] + (gen & 1) * P.world + P.rank;
+    *f = record_tag(st->epoch, gen);
+  }
+}
+
+__global__ void k_begin(EngineParams P, long long first_local, unsigned epoch) {
   DevState* st = P.st;
   if (threadIdx.x == 0) {
     st->r = st->r0 = st->m = st->n_sel = st->done = st->iter = st->err = 0;
@@ -105,9 +163,12 @@ __global__ void k_begin(EngineParams P, long long first_local) {
     st->blocks_done = 0;
     st->n_scored = 0;
     st->pending_id = -1;
+    st->epoch = epoch;
   }
+  __syncthreads();
   write_record(P, first_local >= 0 ? __longlong_as_double(0x7ff0000000000000LL) : -__longlong_as_double(0x7ff0000000000000LL),
                first_local, 0);
+  publish_record(P, st, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -127,12 +188,15 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
   __shared__ double s_dot[NB][NB + 1];
   if (st->done) return;
   const int tid = threadIdx.x;
+  const int gen = st->iter;
+  if (!external && !wait_records(P, st, gen)) return;
+  const double* recs = external ? P.pay_recv : records_ptr(P, gen);
   if (tid == 0) {
     int win = -1;
     double bs = 0.0;
     long long bid = 0;
     for (int w = 0; w < P.world; ++w) {
-      const double* pay = P.pay_recv + (long long)w * P.pay_stride;
+      const double* pay = recs + (long long)w * P.pay_stride;
       const long long* pl = reinterpret_cast<const long long*>(pay);
       if (pl[PAY_LOCAL] < 0) continue;
       if (win < 0 || better(pay[PAY_SCORE], pl[PAY_ID], bs, bid)) { win = w; bs = pay[PAY_SCORE]; bid = pl[PAY_ID]; }
@@ -144,7 +208,7 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
   __syncthreads();
   const int win = s_win;
   if (win < 0) return;
-  const double* pay = P.pay_recv + (long long)win * P.pay_stride;
+  const double* pay = recs + (long long)win * P.pay_stride;
   const long long* pl = reinterpret_cast<const long long*>(pay);
   const int r0 = st->r, m = st->m;
   if (tid == 0) {
@@ -518,6 +582,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
   __syncthreads();
   b = s_part[0];
   write_record(P, b.score, b.local, r0 + NB);
+  publish_record(P, st, st->iter, b.local >= 0 ? r0 + NB : 0);
 }
 
 }  // namespace gpis

@@ -76,14 +76,25 @@ class ShardedSelector:
             self._bufs = self._ex(self.eng, self.world) if self._ex else engine_exchange_tensors(self.eng, self.world)
         return self._bufs
 
+    def enable_peer_exchange(self):
+        """Replace the per-step all-gather by P2P stores over NVLink from inside the kernels:
+        exchange CUDA IPC handles of the engines' exchange regions once, then the whole loop
+        runs in gpis_select (captured CUDA graph, no host call per step)."""
+        mine = self.eng.peer_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine, group=self.group)
+        self.eng.peer_import(handles)
+        dist.barrier(group=self.group)
+
     def _gather(self):
         send, recv = self._exchange()
         dist.all_gather_into_tensor(recv, send, group=self.group)
 
     def select(self, first_index, K):
         """first_index is GLOBAL.  Returns nothing; read results from the engine."""
-        if self.world == 1:
-            self.eng.select(first_index - self.lo, K)
+        if self.world == 1 or getattr(self.eng, "peer_mode", False):
+            mine = self.lo <= first_index < self.hi
+            self.eng.select(first_index - self.lo if mine else -1, K)
             t = getattr(self.eng, "timing", None)
             if t:
                 tt = t()

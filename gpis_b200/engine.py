@@ -84,6 +84,7 @@ class GpisEngine:
         cfg.mean_c, cfg.noise = float(mean_c), float(noise)
         cfg.level, cfg.eps, cfg.beta, cfg.beta_delta = float(level), float(eps), float(beta), float(beta_delta)
         self.cfg = cfg
+        self.peer_mode = False
         self.h = C.c_void_p()
         st = self.lib.gpis_create(C.byref(self.h), C.byref(cfg))
         if st != _lib.GPIS_OK:
@@ -154,6 +155,18 @@ class GpisEngine:
         s, r, b = C.c_void_p(), C.c_void_p(), C.c_int64()
         self._ck(self.lib.gpis_exchange_buffers(self.h, C.byref(s), C.byref(r), C.byref(b)))
         return s.value, r.value, b.value
+
+    def peer_export(self):
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.lib.gpis_peer_export(self.h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_import(self, handles):
+        """handles: list of world_size 64-byte IPC handles, rank-major."""
+        blob = b"".join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.gpis_peer_import(self.h, C.cast(buf, C.c_void_p), 0))
+        self.peer_mode = True
 
     def active(self):
         ids = np.zeros(self.max_active + 1, np.int64)

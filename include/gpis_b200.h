@@ -110,9 +110,10 @@ gpis_status gpis_set_grid_candidates(gpis_handle h, const int32_t* dims, const d
 /* GpuActiveSetSelector::SelectChol (gpu_active_set_selector.cpp:408-611) with the semantics
  * of select_active_set_straddle.m:62-126: greedy loop entirely on the device, at most K
  * points, stops early when nothing is unclassified.  first_local = local index of the first
- * point (straddle.m:36-37 draws it at random; main.cpp:77 seeds rand()).  world_size must be 1;
- * sharded runs drive the three step calls below and all-gather the exchange buffer between
- * gpis_step_update and gpis_step_append. */
+ * point (straddle.m:36-37 draws it at random; main.cpp:77 seeds rand()), or -1 on the ranks
+ * that do not own it.  With world_size > 1 this needs the peer exchange (gpis_peer_import);
+ * without it sharded runs drive the step calls below and all-gather the exchange buffer
+ * between gpis_step_update and gpis_step_append. */
 gpis_status gpis_select(gpis_handle h, int64_t first_local, int32_t K, void* stream);
 
 gpis_status gpis_select_begin(gpis_handle h, int64_t first_local_or_neg, void* stream);
@@ -127,6 +128,16 @@ gpis_status gpis_select_end(gpis_handle h, void* stream);
 /* Per-rank exchange record: send = this rank's best candidate (score, id, point, its column
  * of L^-1 K); recv = world_size such records, rank-major.  With world_size == 1 recv == send. */
 gpis_status gpis_exchange_buffers(gpis_handle h, void** send, void** recv, int64_t* bytes_per_rank);
+
+/* Peer exchange (one process per GPU, world_size > 1): instead of a collective call per step,
+ * every rank stores its record straight into all peers' exchange regions over NVLink (P2P stores
+ * from the last CTA of the update kernel) and the next kernel waits on local flags -- the whole
+ * loop then runs inside gpis_select with no host involvement.  gpis_peer_export writes this
+ * rank's 64-byte CUDA IPC handle; gather the handles of all ranks (any transport) and pass the
+ * world_size x 64 bytes, rank-major, to gpis_peer_import.  same_process != 0: `handles` is an
+ * array of world_size device pointers (regions exported by engines of the same process). */
+gpis_status gpis_peer_export(gpis_handle h, void* handle64);
+gpis_status gpis_peer_import(gpis_handle h, const void* handles, int32_t same_process);
 
 /* What SelectChol should have written to activeInputs/activeTargets and alpha.csv
  * (gpu_active_set_selector.cpp:584-586; the arrays are never filled there).
