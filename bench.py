@@ -225,7 +225,7 @@ def run_ours(args):
     def timed(host, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"select_ms": 0.0, "predict_ms": 0.0, "update_ms": 0.0, "alg_bytes": 0.0, "panel_bytes": 0.0,
-               "update_launches": 0, "alg_flops": 0.0}
+               "update_launches": 0, "alg_flops": 0.0, "append_ms": 0.0, "main_ms": 0.0, "epilogue_ms": 0.0}
         barrier()
         e0.record()
         for _ in range(steps):
@@ -234,6 +234,8 @@ def run_ours(args):
             hst = eng.history()
             acc["predict_ms"] += 0.0 if grid_backend else t["predict_ms"]
             acc["update_ms"] += sel.last_update_ms
+            for k in ("append_ms", "main_ms", "epilogue_ms"):
+                acc[k] += t[k]
             acc["update_launches"] += len(hst["rows"])
             acc["select_ms"] += sel.last_select_ms
             r, u, tl = hst["rows"].astype(np.float64), hst["scored"].astype(np.float64), hst["live_tiles"].astype(np.float64)
@@ -310,7 +312,9 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * s_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / max(s_dev - sel_s, 1e-9) if grid_backend else N / pred_s,
-        "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s},
+        "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
+                     "rank0_append_kernels": acc["append_ms"] / args.steps, "rank0_main_kernel": acc["main_ms"] / args.steps,
+                     "rank0_epilogue_kernel": acc["epilogue_ms"] / args.steps},
         "n_selected": n_sel, "n_in_model": n_model,
         "ids_crc32": int(__import__("zlib").crc32(np.asarray(ids, np.int64).tobytes())),
         "posterior_checksum": post_sum,

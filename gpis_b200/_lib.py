@@ -18,7 +18,7 @@ SYMBOLS = [
     "gpis_set_candidates", "gpis_set_grid_candidates", "gpis_select", "gpis_select_begin", "gpis_step_append", "gpis_step_update",
     "gpis_select_end", "gpis_exchange_buffers", "gpis_get_active", "gpis_get_factor", "gpis_fit",
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
-    "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import",
+    "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
 ]
 
 
@@ -81,6 +81,7 @@ def load():
         "gpis_get_stats": [vp, i64p, i64p, i64p, i64p],
         "gpis_get_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), i64p],
         "gpis_set_profiling": [vp, C.c_int32],
+        "gpis_get_phase_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "gpis_peer_export": [vp, vp],
         "gpis_peer_import": [vp, vp, C.c_int32],
         "gpis_get_history": [vp, vp, vp, vp, i32p],

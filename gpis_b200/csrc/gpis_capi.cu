@@ -35,6 +35,8 @@ struct gpis_engine {
   bool have_candidates = false, have_noise = false, have_ids = false;
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
+  bool fused_solve = false;
+  size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
   size_t w_bytes = 0, gws_bytes = 0, partials_cap = 0, state_cap = 0, grid_slots = 0;
   bool selecting = false;
@@ -44,7 +46,7 @@ struct gpis_engine {
   cudaGraphExec_t step_graph = nullptr;
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double select_ms = 0.0, predict_ms = 0.0, update_ms = 0.0;
+  double select_ms = 0.0, predict_ms = 0.0, update_ms = 0.0, append_ms = 0.0, main_ms = 0.0, epilogue_ms = 0.0;
   long long update_launches = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -88,6 +90,7 @@ struct Dispatch {
   void (*predict)(PredictParams);
   void (*g_point)(EngineParams, int);
   void (*g_solve)(EngineParams);
+  void (*g_solve_fused)(EngineParams);
   void (*g_wrow)(EngineParams);
   void (*g_gemm)(EngineParams);
   void (*g_epi)(EngineParams);
@@ -96,7 +99,7 @@ struct Dispatch {
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -115,10 +118,17 @@ constexpr size_t PRED_SMEM = (2 * PKC * PSB + 2 * PKC * PQ + 32 * PQ) * sizeof(d
 gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int finalize_only) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2 && !external) {
-    d.g_point<<<1, 1024, 0, s>>>(e->P, finalize_only);
-    e->launches++;
-    if (!finalize_only) {
-      d.g_solve<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+    if (finalize_only) {
+      d.g_point<<<1, 1024, 0, s>>>(e->P, 1);
+      e->launches++;
+    } else {
+      if (e->fused_solve) {
+        d.g_solve_fused<<<e->solve_ctas + 1, GSOLVE_THREADS, e->solve_smem, s>>>(e->P);
+      } else {
+        d.g_point<<<1, 1024, 0, s>>>(e->P, 0);
+        d.g_solve<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+        e->launches++;
+      }
       d.g_wrow<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
       e->launches += 2;
     }
@@ -130,10 +140,11 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
   return GPIS_OK;
 }
 
-gpis_status launch_update(gpis_engine* e, cudaStream_t s) {
+gpis_status launch_update(gpis_engine* e, cudaStream_t s, cudaEvent_t mid = nullptr) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2) {
     d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
+    if (mid) cudaEventRecord(mid, s);
     d.g_epi<<<GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s>>>(e->P);
     e->launches += 2;
   } else {
@@ -292,7 +303,12 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
     CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    e->solve_ctas = e->num_sms * 2;
+    e->solve_ctas = e->num_sms * 4;
+    e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
+    e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
+    if (e->fused_solve)
+      CU(cudaFuncSetAttribute((const void*)disp.g_solve_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)e->solve_smem));
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)disp.update, UPD_THREADS, e->upd_smem));
     if (occ < 1) return fail(e, GPIS_ERR_CUDA, "update kernel does not fit on an SM");
@@ -577,7 +593,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   }
   const bool prof = e->profiling;
   if (prof) {
-    while ((int)e->prof_events.size() < 2 * iters) {
+    while ((int)e->prof_events.size() < 4 * iters) {
       cudaEvent_t ev;
       CU(cudaEventCreate(&ev));
       e->prof_events.push_back(ev);
@@ -585,15 +601,17 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   }
   for (int it = 0; it < iters; ++it) {
     if (prof) {
+      CU(cudaEventRecord(e->prof_events[4 * it], s));
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;
-      CU(cudaEventRecord(e->prof_events[2 * it], s));
-      rc = launch_update(e, s);
+      CU(cudaEventRecord(e->prof_events[4 * it + 1], s));
+      rc = launch_update(e, s, e->backend == 2 ? e->prof_events[4 * it + 2] : nullptr);
       if (rc != GPIS_OK) return rc;
-      CU(cudaEventRecord(e->prof_events[2 * it + 1], s));
+      if (e->backend != 2) CU(cudaEventRecord(e->prof_events[4 * it + 2], s));
+      CU(cudaEventRecord(e->prof_events[4 * it + 3], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += e->backend == 2 ? 5 : 2;
+      e->launches += e->backend == 2 ? (e->fused_solve ? 4 : 5) : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;
@@ -608,12 +626,18 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
   e->select_ms = ms;
-  e->update_ms = 0.0;
+  e->update_ms = e->append_ms = e->main_ms = e->epilogue_ms = 0.0;
   e->update_launches = 0;
   if (prof) {
     for (int it = 0; it < iters; ++it) {
       float t = 0.f;
-      CU(cudaEventElapsedTime(&t, e->prof_events[2 * it], e->prof_events[2 * it + 1]));
+      CU(cudaEventElapsedTime(&t, e->prof_events[4 * it], e->prof_events[4 * it + 1]));
+      e->append_ms += t;
+      CU(cudaEventElapsedTime(&t, e->prof_events[4 * it + 1], e->prof_events[4 * it + 2]));
+      e->main_ms += t;
+      CU(cudaEventElapsedTime(&t, e->prof_events[4 * it + 2], e->prof_events[4 * it + 3]));
+      e->epilogue_ms += t;
+      CU(cudaEventElapsedTime(&t, e->prof_events[4 * it + 1], e->prof_events[4 * it + 3]));
       e->update_ms += t;
     }
     e->update_launches = iters;
@@ -877,6 +901,14 @@ gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms
   if (predict_ms) *predict_ms = e->predict_ms;
   if (update_ms) *update_ms = e->update_ms;
   if (update_launches) *update_launches = e->update_launches;
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_phase_timing(gpis_handle e, double* append_ms, double* main_ms, double* epilogue_ms) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (append_ms) *append_ms = e->append_ms;
+  if (main_ms) *main_ms = e->main_ms;
+  if (epilogue_ms) *epilogue_ms = e->epilogue_ms;
   return GPIS_OK;
 }
 

@@ -21,6 +21,7 @@ constexpr int GLD = GT + 4;     // padded smem row (conflict-free DMMA fragment 
 
 
 constexpr int GSOLVE_THREADS = 256;
+constexpr int GSU = 16;         // independent 256-byte row segments in flight per warp in the W passes
 
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
@@ -102,6 +103,16 @@ __device__ __forceinline__ void g_cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void g_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// Non-coherent 8-byte load the compiler may not sink below the fence that follows a batch of them:
+// all GSU loads of a batch are issued before the first dependent FMA (one memory round trip per
+// batch instead of one per ~6 loads).
+__device__ __forceinline__ double ld_nc_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+  return v;
+}
+#define GPIS_ISSUE_FENCE() asm volatile("" ::: "memory")
+
 template <int N>
 __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -191,34 +202,109 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
 
 // ---------------------------------------------------------------------------------------
 // K1: X = W[0:r0, 0:r0] kvec  (= L^-1 Q(old, new)); one warp per row, written into L's new rows.
+// FUSED = true folds K0 into this launch: every CTA waits for the records, picks the winner and
+// computes kvec into shared memory itself (r0 kernel evaluations, cheaper than a dependent
+// launch); one extra CTA (the last) does K0's bookkeeping and table rows instead of rows of W.
 // ---------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, int D, bool FUSED>
 __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
-  const DevState* st = P.st;
+  extern __shared__ double s_kv[];                   // FUSED: [NB][R_cap]
+  DevState* st = P.st;
   if (st->done) return;
-  const int r0 = st->r0;
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  int r0, m = 0;
+  const double* kv = P.kvec;
+  long long kvld = P.R_cap;
+  int nctas = gridDim.x;
+  if (FUSED) {
+    __shared__ int s_win;
+    const int gen = st->iter;
+    if (!wait_records(P, st, gen)) return;
+    const double* recs = records_ptr(P, gen);
+    m = st->m;
+    if (tid == 0) {
+      int win = pick_winner(P, recs);
+      if (win >= 0 && m >= P.M_cap) win = -1;
+      s_win = win;
+    }
+    __syncthreads();
+    const int win = s_win;
+    const bool book = (blockIdx.x == gridDim.x - 1);
+    if (win < 0) {
+      if (book && tid == 0) st->done = 1;            // nothing unclassified / capacity
+      return;
+    }
+    const double* pay = recs + (long long)win * P.pay_stride;
+    const long long* pl = reinterpret_cast<const long long*>(pay);
+    r0 = st->r;
+    double nx[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) nx[d] = pay[PAY_X + d];
+    if (book) {
+      if (tid == 0) {
+        if (win == P.rank) P.flags[grid_slot_of_local(P, pl[PAY_LOCAL])] |= F_ACTIVE;
+        P.sel_ids[m] = pl[PAY_ID];
+        st->n_sel = m + 1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { st->nx[d] = nx[d]; P.AX[d][m] = nx[d]; }
+        st->nnoise = pay[PAY_NOISE];
+        st->r0 = r0;
+        double mf = P.mean_c;
+#pragma unroll
+        for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
+        st->gnew[0] = pay[PAY_TSDF] - mf;
+        for (int a = 1; a < NB; ++a) st->gnew[a] = pay[PAY_NRM + a - 1] - P.mean_w[a - 1];
+      }
+      for (int d = 0; d < D; ++d) {
+        const int len = P.gtlen[d];
+        for (int e = tid; e < len * NB; e += blockDim.x) {
+          const int a = e / len, j = e % len;
+          const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
+          double v = exp(-0.5 * diff * diff * P.inv_ell2);
+          if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;
+          if (d == 0) v *= P.sf2;
+          P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
+        }
+      }
+      return;
+    }
+    for (int i = tid; i < m; i += blockDim.x) {
+      double z[D], c[NB][NB];
+#pragma unroll
+      for (int d = 0; d < D; ++d) z[d] = P.AX[d][i];
+      cov_rows_rows<NB, D>(P, nx, z, c);
+#pragma unroll
+      for (int a = 0; a < NB; ++a)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) s_kv[(long long)a * P.R_cap + i * NB + b] = c[a][b];
+    }
+    __syncthreads();
+    kv = s_kv;
+    nctas = gridDim.x - 1;
+  } else {
+    r0 = st->r0;
+  }
+  const int wid = (blockIdx.x * blockDim.x + tid) >> 5, nw = (nctas * blockDim.x) >> 5;
   for (int s = wid; s < r0; s += nw) {
     const double* wrow = P.W + (long long)s * P.ldW;
     double acc[NB];
 #pragma unroll
     for (int a = 0; a < NB; ++a) acc[a] = 0.0;
-    // 8 independent 256-byte row segments in flight per warp (the pass is bandwidth-bound)
     int c = lane;
-    for (; c + 32 * 7 <= s; c += 32 * 8) {
-      double w[8];
+    for (; c + 32 * (GSU - 1) <= s; c += 32 * GSU) {
+      double w[GSU];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = __ldg(wrow + c + 32 * u);
+      for (int u = 0; u < GSU; ++u) w[u] = ld_nc_f64(wrow + c + 32 * u);
+      GPIS_ISSUE_FENCE();
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < GSU; ++u)
 #pragma unroll
-        for (int a = 0; a < NB; ++a) acc[a] += w[u] * P.kvec[(long long)a * P.R_cap + c + 32 * u];
+        for (int a = 0; a < NB; ++a) acc[a] += w[u] * kv[(long long)a * kvld + c + 32 * u];
     }
     for (; c <= s; c += 32) {
       const double w = __ldg(wrow + c);
 #pragma unroll
-      for (int a = 0; a < NB; ++a) acc[a] += w * P.kvec[(long long)a * P.R_cap + c];
+      for (int a = 0; a < NB; ++a) acc[a] += w * kv[(long long)a * kvld + c];
     }
 #pragma unroll
     for (int a = 0; a < NB; ++a) {
@@ -237,7 +323,6 @@ template <int NB>
 __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
   DevState* st = P.st;
   if (st->done) return;
-  __shared__ double s_red[GSOLVE_THREADS / 32];
   __shared__ double s_dot[NB][NB + 1];
   __shared__ double s_linv[NB][NB];
   __shared__ int s_ok;
@@ -246,14 +331,45 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
   const double* X[NB];
 #pragma unroll
   for (int a = 0; a < NB; ++a) X[a] = P.L + (long long)(r0 + a) * P.R_cap;
-  for (int a = 0; a < NB; ++a)
-    for (int b = 0; b <= a + 1; ++b) {
-      double p = 0.0;
-      if (b <= a) { for (int s = tid; s < r0; s += GSOLVE_THREADS) p += X[a][s] * X[b][s]; }
-      else        { for (int s = tid; s < r0; s += GSOLVE_THREADS) p += X[a][s] * P.g[s]; }
-      const double tot = block_reduce_sum(p, s_red);
-      if (tid == 0) { if (b <= a) s_dot[a][b] = tot; else s_dot[a][NB] = tot; }
+  {
+    // Gram block X'X (lower) and X'g in ONE sweep over the rows, one block reduction
+    constexpr int ND = NB * (NB + 1) / 2 + NB;
+    __shared__ double s_gram[GSOLVE_THREADS / 32][ND];
+    double p[ND];
+#pragma unroll
+    for (int i = 0; i < ND; ++i) p[i] = 0.0;
+    for (int s = tid; s < r0; s += GSOLVE_THREADS) {
+      double x[NB];
+#pragma unroll
+      for (int a = 0; a < NB; ++a) x[a] = X[a][s];
+      const double gs = P.g[s];
+      int i = 0;
+#pragma unroll
+      for (int a = 0; a < NB; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) p[i++] += x[a] * x[b];
+        p[i++] += x[a] * gs;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+      for (int o = 16; o > 0; o >>= 1) p[i] += __shfl_xor_sync(0xffffffffu, p[i], o);
+    if (lane == 0)
+#pragma unroll
+      for (int i = 0; i < ND; ++i) s_gram[tid >> 5][i] = p[i];
+    __syncthreads();
+    if (tid == 0) {
+      int i = 0;
+      for (int a = 0; a < NB; ++a) {
+        for (int b = 0; b <= a + 1; ++b) {
+          double t = 0.0;
+          for (int w = 0; w < GSOLVE_THREADS / 32; ++w) t += s_gram[w][i];
+          ++i;
+          if (b <= a) s_dot[a][b] = t; else s_dot[a][NB] = t;
+        }
+      }
+    }
+  }
   __syncthreads();
   if (tid == 0) {
     const double nnoise = st->nnoise;
@@ -310,12 +426,13 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow(EngineParams P) {
 #pragma unroll
     for (int a = 0; a < NB; ++a) acc[a] = 0.0;
     int s = rho + lane;
-    for (; s + 32 * 7 < r0; s += 32 * 8) {
-      double w[8];
+    for (; s + 32 * (GSU - 1) < r0; s += 32 * GSU) {
+      double w[GSU];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = __ldg(wt + s + 32 * u);
+      for (int u = 0; u < GSU; ++u) w[u] = ld_nc_f64(wt + s + 32 * u);
+      GPIS_ISSUE_FENCE();
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < GSU; ++u)
 #pragma unroll
         for (int a = 0; a < NB; ++a) acc[a] += w[u] * X[a][s + 32 * u];
     }
@@ -505,7 +622,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
 // workspace and to the per-candidate state is a coalesced 16-byte (flags: 2-byte) access.
 // ---------------------------------------------------------------------------------------
 constexpr int GEPI_THREADS = 256;
-constexpr int GEPI_CTAS_PER_TILE = (GTILE_ELEMS / 2) / GEPI_THREADS;
+constexpr int GEPI_SPT = 4;                                         // fragment slots per thread
+constexpr int GEPI_CTAS_PER_TILE = (GTILE_ELEMS / 2) / (GEPI_THREADS * GEPI_SPT);
 
 template <int NB>
 __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) {
@@ -513,53 +631,79 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   if (st->done) return;
   const int tid = threadIdx.x, lane = tid & 31, ew = tid >> 5;
   const int tile = blockIdx.x / GEPI_CTAS_PER_TILE;
-  const int q = (blockIdx.x % GEPI_CTAS_PER_TILE) * GEPI_THREADS + tid;      // double2 slot in the tile
-  const int r0 = st->r0;
+  const int q0 = (blockIdx.x % GEPI_CTAS_PER_TILE) * (GEPI_THREADS * GEPI_SPT) + tid;   // + k * GEPI_THREADS
   const int nx = P.glen[0], ny = P.glen[1];
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
   const int T = tiles_x * tiles_y * P.glen[2];
-  const int C = (r0 + NB + GKC - 1) / GKC;
-  const long long U = (long long)T * C;
-  const int G = (int)min((long long)P.gemm_ctas, U);
-  const int g_first = unit_owner((long long)tile * C, U, G);
-  const int nseg = unit_owner((long long)(tile + 1) * C - 1, U, G) - g_first + 1;
   const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
-  double beta = P.beta;
-  if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
-  else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
-  const double sb = sqrt(beta);
+  __shared__ int s_nseg;
+  __shared__ double s_sb, s_gn[NB];
+  if (tid == 0) {                       // CTA-uniform: split-K segment count of this tile, sqrt(beta_t)
+    const int r0 = st->r0;
+    const int C = (r0 + NB + GKC - 1) / GKC;
+    const long long U = (long long)T * C;
+    const int G = (int)min((long long)P.gemm_ctas, U);
+    const int g_first = unit_owner((long long)tile * C, U, G);
+    s_nseg = unit_owner((long long)(tile + 1) * C - 1, U, G) - g_first + 1;
+    double beta = P.beta;
+    if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
+    else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
+    s_sb = sqrt(beta);
+    for (int a = 0; a < NB; ++a) s_gn[a] = st->gnew[a];
+  }
+  __syncthreads();
+  const int nseg = s_nseg;
+  const double sb = s_sb;
 
-  double dv[2] = {0.0, 0.0}, dm[2] = {0.0, 0.0};
+  // phase 1: all loads of the thread's slots in flight together
+  double dv[GEPI_SPT][2], dm[GEPI_SPT][2];
+#pragma unroll
+  for (int k = 0; k < GEPI_SPT; ++k) dv[k][0] = dv[k][1] = dm[k][0] = dm[k][1] = 0.0;
 #pragma unroll
   for (int a = 0; a < NB; ++a) {
-    const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS) + q;
-    double v0 = 0.0, v1 = 0.0;
-    for (int sgi = 0; sgi < nseg; ++sgi) {
-      const double2 p = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2));
-      v0 += p.x; v1 += p.y;
+    const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS) + q0;
+    double2 v[GEPI_SPT];
+#pragma unroll
+    for (int k = 0; k < GEPI_SPT; ++k) v[k] = __ldcg(ws + k * GEPI_THREADS);
+    for (int sgi = 1; sgi < nseg; ++sgi) {
+      double2 pz[GEPI_SPT];
+#pragma unroll
+      for (int k = 0; k < GEPI_SPT; ++k) pz[k] = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2) + k * GEPI_THREADS);
+#pragma unroll
+      for (int k = 0; k < GEPI_SPT; ++k) { v[k].x += pz[k].x; v[k].y += pz[k].y; }
     }
-    const double ga = st->gnew[a];
-    dv[0] += v0 * v0; dv[1] += v1 * v1;
-    dm[0] += v0 * ga; dm[1] += v1 * ga;
+    const double ga = s_gn[a];
+#pragma unroll
+    for (int k = 0; k < GEPI_SPT; ++k) {
+      dv[k][0] += v[k].x * v[k].x; dv[k][1] += v[k].y * v[k].y;
+      dm[k][0] += v[k].x * ga;     dm[k][1] += v[k].y * ga;
+    }
   }
-  const long long slot2 = (long long)tile * (GTILE_ELEMS / 2) + q;
-  double2 mu = reinterpret_cast<double2*>(P.mu)[slot2];
-  double2 var = reinterpret_cast<double2*>(P.var)[slot2];
-  uchar2 fl = reinterpret_cast<uchar2*>(P.flags)[slot2];
-  mu.x += dm[0]; mu.y += dm[1];
-  var.x -= dv[0]; var.y -= dv[1];
-  reinterpret_cast<double2*>(P.mu)[slot2] = mu;
-  reinterpret_cast<double2*>(P.var)[slot2] = var;
+  const long long slot_base = (long long)tile * (GTILE_ELEMS / 2) + q0;
+  double2 mu[GEPI_SPT], var[GEPI_SPT];
+  uchar2 fl[GEPI_SPT];
+#pragma unroll
+  for (int k = 0; k < GEPI_SPT; ++k) {
+    mu[k] = reinterpret_cast<const double2*>(P.mu)[slot_base + k * GEPI_THREADS];
+    var[k] = reinterpret_cast<const double2*>(P.var)[slot_base + k * GEPI_THREADS];
+    fl[k] = reinterpret_cast<const uchar2*>(P.flags)[slot_base + k * GEPI_THREADS];
+  }
 
   double best_s = NEG_INF;
   long long best_id = 0x7fffffffffffffffLL, best_j = -1;
   int n_scored = 0;
-  unsigned char f[2] = {fl.x, fl.y};
-  const double mus[2] = {mu.x, mu.y}, vars[2] = {var.x, var.y};
-  if (!((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW)))) {
+#pragma unroll
+  for (int k = 0; k < GEPI_SPT; ++k) {
+    const long long slot2 = slot_base + k * GEPI_THREADS;
+    mu[k].x += dm[k][0]; mu[k].y += dm[k][1];
+    var[k].x -= dv[k][0]; var[k].y -= dv[k][1];
+    reinterpret_cast<double2*>(P.mu)[slot2] = mu[k];
+    reinterpret_cast<double2*>(P.var)[slot2] = var[k];
+    unsigned char f[2] = {fl[k].x, fl[k].y};
+    if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) continue;
+    const double mus[2] = {mu[k].x, mu[k].y}, vars[2] = {var[k].x, var[k].y};
     int jx, jy, tz;
     grid_unslot(P, slot2 * 2, jx, jy, tz);
-    double sc2[2] = {0.0, 0.0};
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
@@ -570,7 +714,6 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
       const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
       const double hi = __dadd_rn(mus[e], w), lo = __dadd_rn(mus[e], -w);
       const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-      sc2[e] = sc;
       if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
       if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
       if (sc == sc) {
@@ -580,9 +723,9 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
     }
     // the ambiguity is not stored per step (16 bytes of traffic per candidate): the getter
     // recomputes it from the running posterior
-    (void)sc2;
-    if (f[0] != fl.x || f[1] != fl.y) reinterpret_cast<uchar2*>(P.flags)[slot2] = make_uchar2(f[0], f[1]);
+    if (f[0] != fl[k].x || f[1] != fl[k].y) reinterpret_cast<uchar2*>(P.flags)[slot2] = make_uchar2(f[0], f[1]);
   }
+  const int r0 = st->r0;
 
   __shared__ BlockBest s_bb[GEPI_THREADS / 32];
   __shared__ int s_cnt[GEPI_THREADS / 32];
@@ -604,7 +747,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
       if (s_bb[w].local >= 0 && better(s_bb[w].score, s_bb[w].id, b.score, b.id)) b = s_bb[w];
     }
     P.partials[blockIdx.x] = b;
-    if (cnt) atomicAdd(&st->n_scored, cnt);
+    (void)cnt;      // the scored count is not accumulated here: every lattice point is updated each step
     __threadfence();
     const unsigned ticket = atomicAdd(&st->blocks_done, 1u);
     s_last = (ticket == gridDim.x - 1);
@@ -637,7 +780,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
     if (it <= P.M_cap) {
       P.hist[it] = r0;
       P.hist[(P.M_cap + 1) + it] = T;
-      P.hist[2 * (P.M_cap + 1) + it] = *(volatile int*)&st->n_scored;
+      P.hist[2 * (P.M_cap + 1) + it] = (int)min(P.N, (long long)0x7fffffff);
     }
     st->n_scored = 0;
     st->blocks_done = 0;

@@ -235,7 +235,10 @@ class GpisEngine:
     def timing(self):
         a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
         self._ck(self.lib.gpis_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
-        return {"select_ms": a.value, "predict_ms": b.value, "update_ms": c.value, "update_launches": n.value}
+        p, q, r = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.gpis_get_phase_timing(self.h, C.byref(p), C.byref(q), C.byref(r)))
+        return {"select_ms": a.value, "predict_ms": b.value, "update_ms": c.value, "update_launches": n.value,
+                "append_ms": p.value, "main_ms": q.value, "epilogue_ms": r.value}
 
     def set_profiling(self, on=True):
         self._ck(self.lib.gpis_set_profiling(self.h, int(bool(on))))

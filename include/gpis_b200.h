@@ -177,6 +177,9 @@ gpis_status gpis_get_stats(gpis_handle h, int64_t* kernel_launches, int64_t* liv
  * launches in the last gpis_select and their count. */
 gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms, double* update_ms,
                             int64_t* update_launches);
+/* Profiling only: summed device time of the last gpis_select's factor-append kernels, of the
+ * main update kernel (k_update / k_grid_gemm) and of the grid backend's epilogue kernel. */
+gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main_ms, double* epilogue_ms);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
  * stream (plain launches instead of the captured graph). */
 gpis_status gpis_set_profiling(gpis_handle h, int32_t on);
