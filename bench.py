@@ -195,9 +195,7 @@ def run_ours(args):
 
     eng = GpisEngine(D, n_loc, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA,
                      rank=rank, world_size=world, total_candidates=N, id_base=lo, device=local_rank)
-    eng.set_profiling(not args.no_profile)
     sel = gdist.ShardedSelector(eng, rank, world, lo, hi)
-    sel.profile = not args.no_profile
     if world > 1 and args.exchange == "peer":
         sel.enable_peer_exchange()
 
@@ -249,16 +247,31 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), acc
 
+    # (1) production mode: captured CUDA graph, no per-launch events -> value / ms_per_step
+    eng.set_profiling(False)
+    sel.profile = False
     for _ in range(args.warmup):
         step(False)
     launches0 = eng.stats()["kernel_launches"]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev, acc = timed(False, args.steps)
+    ms_dev, _ = timed(False, args.steps)
     launches = eng.stats()["kernel_launches"] - launches0
-    step(True)                                   # warm the host-buffer path once
+    # (2) end to end through the public API with pinned HOST buffers
+    step(True)
     ms_e2e, _ = timed(True, args.steps)
+    # (3) instrumented: the same steps with a CUDA event pair around every update-kernel launch on
+    #     the launching stream (plain launches instead of the graph) -> roofline numerator/denominator
+    ms_inst, acc = ms_dev, None
+    if not args.no_profile:
+        eng.set_profiling(True)
+        sel.profile = True
+        step(False)
+        ms_inst, acc = timed(False, args.steps)
+    else:
+        _, acc = timed(False, 1)
+        acc = {k: v * args.steps for k, v in acc.items()}
     clocks = sampler.stop() if rank == 0 else None
     ids, n_model = eng.active()
     # checksum of the posterior grid (sum of mean and of variance over all lattice points)
@@ -269,7 +282,7 @@ def run_ours(args):
 
     # whole-job aggregates over ranks
     tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"], acc["alg_flops"]], dtype=torch.float64, device=dev)
-    mx = torch.tensor([acc["update_ms"], acc["select_ms"], acc["predict_ms"]], dtype=torch.float64, device=dev)
+    mx = torch.tensor([acc["update_ms"], acc["select_ms"], acc["predict_ms"], acc["main_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -279,9 +292,11 @@ def run_ours(args):
         return
     n_sel = len(ids)
     s_dev, s_e2e = ms_dev / 1e3 / args.steps, ms_e2e / 1e3 / args.steps
-    upd_s, sel_s, pred_s = (float(x) / 1e3 / args.steps for x in mx)
+    upd_s, sel_s, pred_s, main_s = (float(x) / 1e3 / args.steps for x in mx)
     if args.no_profile:
         upd_s = sel_s
+    if main_s <= 0.0:          # per-kernel split unavailable (NCCL-exchange path): gemm + epilogue together
+        main_s = upd_s
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,13 +312,16 @@ def run_ours(args):
         except Exception:
             pass
         tpeak = float(fp64.get("dmma_m8n8k4_tflops", 37.2)) * world
-        tach = float(tot[2]) / args.steps / upd_s / 1e12
-        roof = {"kernel": "k_grid_update (per-step [ny x r] x [r x nx] contraction on the fp64 tensor pipe "
-                          "+ posterior update + straddle score + arg-max)",
+        tach = float(tot[2]) / args.steps / main_s / 1e12
+        roof = {"kernel": "k_grid_gemm (per-step [ny x r] x [r x nx] contraction per z-slice on the fp64 tensor "
+                          "pipe, DMMA.8x8x4; stream-K over 148 persistent CTAs)",
+                "with_epilogue_kernel_tflops": float(tot[2]) / args.steps / upd_s / 1e12,
                 "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
                 "peak_source": ("fp64 DMMA.8x8x4 peak measured on this pool's B200 by scripts/fp64_peak.cu "
                                 "(profiles/r01_fp64_peak.json) x n_gpus; MEASURED_PEAKS.json has no fp64 figure"),
-                "traffic": None, "algorithmic_flops_per_step": float(tot[2]) / args.steps,
+                "traffic": ncu_traffic("r01_k_grid_gemm_ncu.csv"),
+                "traffic_note": "DRAM bytes read+written per launch from the committed ncu --set full capture (profiles/, launch at r~300): the operands come from L2, the kernel is not HBM-bound",
+                "algorithmic_flops_per_step": float(tot[2]) / args.steps,
                 "launches_per_step": acc["update_launches"] / args.steps}
     else:
         roof = None
@@ -312,7 +330,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * s_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
         "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / max(s_dev - sel_s, 1e-9) if grid_backend else N / pred_s,
-        "phase_ms": {"select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
+        "instrumented_ms_per_step": ms_inst / args.steps,
+        "phase_ms": {"note": "from the instrumented steps (per-launch CUDA events, plain launches)", "select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
                      "rank0_append_kernels": acc["append_ms"] / args.steps, "rank0_main_kernel": acc["main_ms"] / args.steps,
                      "rank0_epilogue_kernel": acc["epilogue_ms"] / args.steps},
         "n_selected": n_sel, "n_in_model": n_model,
@@ -325,7 +344,8 @@ def run_ours(args):
         "roofline": roof if roof else {"kernel": "k_update (candidate update + straddle score + arg-max)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs x n_gpus" if peaks else "fallback 6650 GB/s",
-                     "traffic": None,
+                     "traffic": ncu_traffic("r01_k_update_panel_ncu.csv"),
+                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/, 64^3 grid, r~505: algorithmic 8*U*(r+1) ~ 1.06 GB)",
                      "algorithmic_bytes_per_step": float(tot[0]) / args.steps,
                      "panel_bytes_touched_per_step": float(tot[1]) / args.steps,
                      "launches_per_step": acc["update_launches"] / args.steps,
@@ -337,6 +357,20 @@ def run_ours(args):
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first profiled launch in profiles/<name>."""
+    import csv
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        tot = 0.0
+        for row in csv.reader(open(os.path.join(ROOT, "profiles", name))):
+            if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(row[2]) * unit.get(row[1], 1.0)
+        return tot or None
+    except Exception:
+        return None
 
 
 def cpu_baseline(args, pts, tsdf, first):

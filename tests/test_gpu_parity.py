@@ -176,3 +176,47 @@ def test_errors_are_reported_not_fatal(G):
     with pytest.raises(G._lib.GpisError):
         eng.select_begin(1000)
     eng.close()
+
+
+def test_gpu_active_set_selector_mirror(G, tmp_path):
+    """GpuActiveSetSelector.SelectFromGrid / SelectChol semantics (beta schedule, predictive variance,
+    sign classification) against the same rule evaluated by the oracle's GP arithmetic."""
+    w = h = 18
+    rng = np.random.default_rng(4)
+    yy, xx = np.indices((h, w)).astype(np.float64)
+    tsdf = np.clip((np.hypot(xx - 8.6, yy - 9.3) - 5.2) / 2.0, -1, 1) + 1e-3 * rng.standard_normal((h, w))
+    csv = tmp_path / "t.csv"
+    np.savetxt(csv, tsdf, delimiter=",", fmt="%.17g")
+    sel = G.GpuActiveSetSelector()
+    K, sigma, beta, tol, first = 40, 6.0, 0.05, 0.01, 37
+    assert sel.SelectFromGrid(str(csv), K, sigma, beta, w, h, 1, 64, tol, first_index=first, out_dir=str(tmp_path / "out"))
+    ids = sel.last["ids"]
+    # oracle restatement of the same loop
+    pts = np.stack([xx.reshape(-1), yy.reshape(-1)], axis=1)
+    y = np.loadtxt(csv, delimiter=",").reshape(-1)
+    hyp = {"cov": np.array([0.5 * np.log(sigma), 0.0]), "mean": np.zeros(3), "lik": 0.5 * np.log(beta)}
+    gp = O.IncrementalGP(pts, hyp, K, False)
+    N = pts.shape[0]
+    active = np.zeros(N, bool); hi_f = np.zeros(N, bool); lo_f = np.zeros(N, bool)
+    order, pending = [first], first
+    active[first] = True
+    for it in range(K - 1):
+        gp.append(pts[pending], y[pending], None, beta)
+        unc = ~active & ~hi_f & ~lo_f
+        if not unc.any():
+            break
+        s = np.sqrt(2.0 * np.log(N * np.pi ** 2 * (it + 1) ** 2 / (6.0 * tol)))
+        idx = np.flatnonzero(unc)
+        var = gp.var[idx] + beta
+        mu = gp.mu[idx]
+        hi, lo = mu + s * var, mu - s * var
+        amb = np.minimum(hi, -lo)
+        pending = int(idx[np.flatnonzero(amb == amb.max())[0]])
+        active[pending] = True
+        order.append(pending)
+        hi_f[idx[lo > 0]] = True
+        lo_f[idx[hi < 0]] = True
+    assert np.array_equal(ids, np.asarray(order))
+    a = np.loadtxt(tmp_path / "out" / "alpha.csv", delimiter=",")
+    assert np.max(np.abs(a - gp.alpha()[:len(a)])) < 1e-8 * np.max(np.abs(a))
+    assert sel.last["errors"].mean > 0
