@@ -67,7 +67,16 @@ def main():
               "err_rms": f64(te.rmsError), "err_std": f64(te.stdError),
               "shape_fullTsdf": f64(s["shapeParams"].fullTsdf)})
     np.savez_compressed(f"{OUT}/loofa.npz", **d)
-    # real 3-D SDF header + a 2-D csv (sdf_file.py:91-99,116-117 assert these)
+    # real 3-D SDF (header asserted in sdf_file.py:91-99) and a 50x50 2-D csv (:116-117)
+    with open(f"{REF}/data/test/sdf/Co_clean_dim_25.sdf") as f:
+        nx, ny, nz = [int(t) for t in f.readline().split()]
+        origin = np.array([float(t) for t in f.readline().split()])
+        res = float(f.readline())
+        vals = np.loadtxt(f)
+    csv2d = np.loadtxt(f"{REF}/data/test/sdf/medium_black_spring_clamp_optimized_poisson_texture_mapped_mesh_clean_0.csv", delimiter=",")
+    np.savez_compressed(f"{OUT}/sdf_co_clean_dim_25.npz", dims=np.array([nx, ny, nz]), origin=origin, resolution=res,
+                        values=vals.astype(np.float32), csv2d_shape=np.array(csv2d.shape),
+                        csv2d_checksum=np.array([csv2d.sum(), np.abs(csv2d).max()]))
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(f"{OUT}/{f}"))

@@ -158,3 +158,55 @@ def test_c2_size_two_backends_agree_and_match_cpu_prefix(G):
     m2, v2, _ = mp.engine.predict(q)
     assert np.max(np.abs(m1 - m2)) < 1e-9 and np.max(np.abs(v1 - v2)) < 1e-9
     assert np.max(np.abs(m1 - mu[::997])) < 1e-9 and np.max(np.abs(v1 - var[::997])) < 1e-9
+
+
+def test_real_sdf_fixture_through_the_grid_backend(G):
+    """The reference's own 25^3 SDF (data/test/sdf/Co_clean_dim_25.sdf): selection + posterior grid
+    on its lattice against the oracle, and the Gpis3D host class against the oracle's dense fit."""
+    from conftest import load_golden
+    from gpis_b200.sdf_io import Sdf3D, Gpis3D, select_from_sdf
+    from gpis_b200.synth import grid_points
+    g = load_golden("sdf_co_clean_dim_25")
+    dims = tuple(int(v) for v in g["dims"])
+    sdf = Sdf3D(g["values"].astype(np.float64).reshape(dims, order="F"), g["origin"], float(g["resolution"]))
+    K, trunc, ell = 120, 4.0 * sdf.resolution, 3.0
+    out = select_from_sdf(sdf, K, trunc=trunc, ell=ell, first_index=5000)
+    pts = grid_points(dims)
+    hyp = {"cov": np.array([np.log(ell), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
+    tr = {"activeSetSize": K, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental({"points": pts, "tsdf": sdf.tsdf(trunc), "normals": None, "noise": None},
+                                        tr, 5000, hyp=hyp, prune=False)
+    assert np.array_equal(out["ids"], ora["order"]) and out["n_in_model"] == ora["n_in_model"]
+    fm, fv, _ = O.predict_points(ora["gp"], pts)
+    assert np.max(np.abs(out["mean"].reshape(-1, order="F") - fm)) < 1e-8
+    assert np.max(np.abs(out["var"].reshape(-1, order="F") - fv)) < 1e-8
+    # Gpis3D(points, sdf_meas, dims, ...): dense fit on a random subset + predict_locations
+    rng = np.random.default_rng(0)
+    sub = rng.choice(pts.shape[0], 300, replace=False)
+    gp3 = Gpis3D(pts[sub], sdf.tsdf(trunc)[sub], (6, 5, 4), meas_variance=0.05, kernel_hyps=[1.0, ell])
+    ref = O.create_gpis(pts[sub], sdf.tsdf(trunc)[sub], None, None, hyp)
+    q = gp3.grid_pts_
+    m_ref, _, Kx = O.gp_mean(ref, q, False)
+    assert gp3.mean_sdf().shape == (6, 5, 4)
+    assert np.max(np.abs(gp3.mean_pred_[:, 0] - m_ref)) < 1e-8
+    assert np.max(np.abs(gp3.var_pred_[:, 0] - (O.gp_var_diag(ref, q, Kx, False) + 0.05))) < 1e-8
+
+
+def test_batch_of_independent_objects_matches_solo_runs(G):
+    """Config 5 in miniature: a batch of independent small objects over a pool of engines/streams."""
+    from gpis_b200.batch import select_batch, superellipsoid_tsdf
+    g, K, B = 16, 60, 12
+    tsdfs = [superellipsoid_tsdf(g, k) for k in range(B)]
+    cfg = dict(ell=2.5, noise=0.05, level=0.0, eps=1e-2, beta=10.0)
+    res = select_batch(tsdfs, (g, g, g), K, 3254 % g ** 3, n_workers=4, **cfg)
+    assert [r["object"] for r in res] == list(range(B))
+    for k in (0, 5, 11):
+        eng = G.GpisEngine(3, g ** 3, K, **cfg)
+        eng.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdfs[k])
+        eng.select(3254 % g ** 3, K)
+        ids, nm = eng.active()
+        mu, var = eng.candidate_posterior()
+        assert np.array_equal(ids, res[k]["ids"]) and nm == res[k]["n_in_model"]
+        assert np.array_equal(mu, res[k]["mean"]) and np.array_equal(var, res[k]["var"])   # bit-identical
+    # objects differ from each other
+    assert not np.array_equal(res[0]["ids"], res[1]["ids"])
