@@ -52,6 +52,12 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        try:                      # building is not a fallback: the product is still the CUDA library
+            from . import build
+            build.build()
+        except Exception:
+            pass
+    if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -m gpis_b200.build` "
                           "(there is no CPU fallback for this path)")
     lib = C.CDLL(LIB_PATH)

@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -35,7 +36,8 @@ struct gpis_engine {
   bool have_candidates = false, have_noise = false, have_ids = false;
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
-  bool fused_solve = false;
+  bool fused_solve = false, onepass = false;
+  int solve1_ctas = 0;
   size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
   size_t w_bytes = 0, gws_bytes = 0, partials_cap = 0, state_cap = 0, grid_slots = 0;
@@ -91,6 +93,7 @@ struct Dispatch {
   void (*g_point)(EngineParams, int);
   void (*g_solve)(EngineParams);
   void (*g_solve_fused)(EngineParams);
+  void (*g_solve1)(EngineParams);
   void (*g_wrow)(EngineParams);
   void (*g_gemm)(EngineParams);
   void (*g_epi)(EngineParams);
@@ -99,7 +102,7 @@ struct Dispatch {
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -122,6 +125,13 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
       d.g_point<<<1, 1024, 0, s>>>(e->P, 1);
       e->launches++;
     } else {
+      if (e->onepass) {
+        d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
+        k_grid_wrow1<<<e->num_sms, GSOLVE_THREADS, 0, s>>>(e->P, e->solve1_ctas);
+        e->launches += 2;
+        CU(cudaGetLastError());
+        return GPIS_OK;
+      }
       if (e->fused_solve) {
         d.g_solve_fused<<<e->solve_ctas + 1, GSOLVE_THREADS, e->solve_smem, s>>>(e->P);
       } else {
@@ -171,11 +181,17 @@ gpis_status ensure_inverse(gpis_engine* e, cudaStream_t s) {
   if (rc != GPIS_OK) return rc;
   const int R = e->host_state.r;
   if (e->inverse_rows == R) return GPIS_OK;
-  const bool have_wt = e->backend == 2 && e->selecting;   // the grid backend maintains W' itself
+  const bool have_w = e->backend == 2 && e->selecting;    // the grid backend maintains W (and W' unless one-pass)
+  const bool have_wt = have_w && !e->onepass;
   if (!have_wt) CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
   if (R > 0) {
     const int blocks = (R * 32 + 255) / 256;
-    if (!have_wt) {
+    if (have_w && !have_wt) {
+      dim3 tg((R + 31) / 32, (R + 31) / 32);
+      k_transpose_lower<<<tg, dim3(32, 8), 0, s>>>(e->P.W, e->d_Wt, e->ldw, R);
+      CU(cudaGetLastError());
+      e->launches++;
+    } else if (!have_wt) {
       k_invert_factor<<<blocks, 256, 0, s>>>(e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
       CU(cudaGetLastError());
       e->launches++;
@@ -306,6 +322,13 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->solve_ctas = e->num_sms * 4;
     e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
+    e->onepass = (NB == 1) && P.R_cap <= GS1_RMAX && getenv("GPIS_TWO_PASS") == nullptr;
+    e->solve1_ctas = e->num_sms * 2;
+    if (e->onepass) {
+      CU(cudaFuncSetAttribute((const void*)disp.g_solve1, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(sizeof(double) * GS1_RMAX)));
+      CU(dalloc(e, &P.ypart, (size_t)e->solve1_ctas * GS1_RMAX));
+    }
     if (e->fused_solve)
       CU(cudaFuncSetAttribute((const void*)disp.g_solve_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)e->solve_smem));
@@ -611,7 +634,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       CU(cudaEventRecord(e->prof_events[4 * it + 3], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += e->backend == 2 ? (e->fused_solve ? 4 : 5) : 2;
+      e->launches += e->backend == 2 ? ((e->fused_solve || e->onepass) ? 4 : 5) : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;

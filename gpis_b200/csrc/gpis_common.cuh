@@ -94,6 +94,7 @@ struct EngineParams {
   double* Wt;              // its transpose (shared with the predict kernel)
   long long ldW;
   double* kvec;            // [MAXNB][R_cap] covariance of the new rows with the model rows
+  double* ypart;           // one-pass solve: per-CTA partial W' l vectors [solve CTAs][4096]
   double* gws;             // split-K workspace [NB][tiles][gws_segmax][128*128]
   int gws_segmax;
   int gemm_ctas;           // persistent grid of the update GEMM

@@ -316,6 +316,208 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
 }
 
 // ---------------------------------------------------------------------------------------
+// One-pass variant of K1/K2 for function-only models with R_cap <= 4096 (the headline configs):
+//   l = W kvec and Y = W' l need W only ONCE: a CTA takes rows s = cta, cta + G, ... in order;
+//   for each row it forms l[s] (block reduction) and immediately accumulates l[s] * W[s, :] into
+//   per-thread column accumulators while the row is still in registers (the next row is already
+//   in flight).  Each CTA leaves a partial Y; k_grid_wrow1 sums the partials in a fixed order, so
+//   every rank computes bit-identical rows of W.  Half the bytes of the two-pass form and no W'.
+// ---------------------------------------------------------------------------------------
+constexpr int GS1_CPT = 16;                        // columns per thread: R_cap <= 16 * 256
+constexpr int GS1_RMAX = GS1_CPT * GSOLVE_THREADS;
+
+template <int D>
+__global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams P) {
+  extern __shared__ double s_kv[];                   // [GS1_RMAX]
+  __shared__ double s_red[2][GSOLVE_THREADS / 32];
+  __shared__ int s_win;
+  DevState* st = P.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gen = st->iter;
+  if (!wait_records(P, st, gen)) return;
+  const double* recs = records_ptr(P, gen);
+  const int m = st->m;
+  if (tid == 0) {
+    int win = pick_winner(P, recs);
+    if (win >= 0 && m >= P.M_cap) win = -1;
+    s_win = win;
+  }
+  __syncthreads();
+  const int win = s_win;
+  const bool book = (blockIdx.x == gridDim.x - 1);
+  if (win < 0) {
+    if (book && tid == 0) st->done = 1;
+    return;
+  }
+  const double* pay = recs + (long long)win * P.pay_stride;
+  const long long* pl = reinterpret_cast<const long long*>(pay);
+  const int r0 = st->r;
+  double nx[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) nx[d] = pay[PAY_X + d];
+  if (book) {
+    if (tid == 0) {
+      if (win == P.rank) P.flags[grid_slot_of_local(P, pl[PAY_LOCAL])] |= F_ACTIVE;
+      P.sel_ids[m] = pl[PAY_ID];
+      st->n_sel = m + 1;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { st->nx[d] = nx[d]; P.AX[d][m] = nx[d]; }
+      st->nnoise = pay[PAY_NOISE];
+      st->r0 = r0;
+      double mf = P.mean_c;
+#pragma unroll
+      for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
+      st->gnew[0] = pay[PAY_TSDF] - mf;
+    }
+    for (int d = 0; d < D; ++d) {
+      const int len = P.gtlen[d];
+      for (int j = tid; j < len; j += blockDim.x) {
+        const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
+        double v = exp(-0.5 * diff * diff * P.inv_ell2);
+        if (d == 0) v *= P.sf2;
+        P.T[d][(long long)r0 * P.ldt[d] + j] = v;
+      }
+    }
+    return;
+  }
+#pragma unroll 4
+  for (int i = tid; i < GS1_RMAX; i += GSOLVE_THREADS) {
+    double k = 0.0;
+    if (i < m) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { const double df = P.AX[d][i] - nx[d]; d2 += df * df; }
+      k = P.sf2 * exp(-0.5 * d2 * P.inv_ell2);
+    }
+    s_kv[i] = k;
+  }
+  __syncthreads();
+  const int G = gridDim.x - 1;
+  double acc[GS1_CPT], wa[GS1_CPT], wb[GS1_CPT];
+#pragma unroll
+  for (int i = 0; i < GS1_CPT; ++i) acc[i] = 0.0;
+  auto load_row = [&](int row, double* w) {
+    const double* wrow = P.W + (long long)row * P.ldW + tid;
+#pragma unroll
+    for (int i = 0; i < GS1_CPT; ++i) w[i] = (tid + GSOLVE_THREADS * i <= row) ? ld_nc_f64(wrow + GSOLVE_THREADS * i) : 0.0;
+  };
+  int par = 0;
+  auto do_row = [&](int row, const double* w) {
+    double p = 0.0;
+#pragma unroll
+    for (int i = 0; i < GS1_CPT; ++i) p += w[i] * s_kv[tid + GSOLVE_THREADS * i];
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) s_red[par][warp] = p;
+    __syncthreads();
+    double ell = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < GSOLVE_THREADS / 32; ++w8) ell += s_red[par][w8];
+    par ^= 1;
+    if (tid == 0) P.L[(long long)r0 * P.R_cap + row] = ell;
+#pragma unroll
+    for (int i = 0; i < GS1_CPT; ++i) acc[i] += ell * w[i];
+  };
+  int s = blockIdx.x;
+  if (s < r0) load_row(s, wa);
+  while (s < r0) {
+    if (s + G < r0) load_row(s + G, wb);
+    do_row(s, wa);
+    s += G;
+    if (s >= r0) break;
+    if (s + G < r0) load_row(s + G, wa);
+    do_row(s, wb);
+    s += G;
+  }
+  if ((int)blockIdx.x < r0) {
+    double* yp = P.ypart + (long long)blockIdx.x * GS1_RMAX + tid;
+#pragma unroll
+    for (int i = 0; i < GS1_CPT; ++i)
+      if (tid + GSOLVE_THREADS * i < r0) yp[GSOLVE_THREADS * i] = acc[i];
+  }
+}
+
+// new row of W from the partial Y's; d, g_new, L's diagonal entry.  Four columns per warp,
+// eight lanes per column over the partials (fixed assignment + fixed shuffle tree).
+__global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow1(EngineParams P, int n_solve_ctas) {
+  DevState* st = P.st;
+  if (st->done) return;
+  __shared__ double s_gram[GSOLVE_THREADS / 32][2];
+  __shared__ double s_dinv;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r0 = st->r0;
+  const double* X = P.L + (long long)r0 * P.R_cap;
+  double p0 = 0.0, p1 = 0.0;
+  for (int s = tid; s < r0; s += GSOLVE_THREADS) { const double x = X[s]; p0 += x * x; p1 += x * P.g[s]; }
+  for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+  if (lane == 0) { s_gram[tid >> 5][0] = p0; s_gram[tid >> 5][1] = p1; }
+  __syncthreads();
+  if (tid == 0) {
+    double xx = 0.0, xg = 0.0;
+    for (int w = 0; w < GSOLVE_THREADS / 32; ++w) { xx += s_gram[w][0]; xg += s_gram[w][1]; }
+    double sdiag = P.sf2 + st->nnoise - xx;
+    bool ok = sdiag > 0.0;
+    if (!ok) sdiag = 1.0;
+    const double d = sqrt(sdiag), dinv = 1.0 / d;
+    s_dinv = dinv;
+    if (blockIdx.x == 0) {
+      const double gn = (st->gnew[0] - xg) / d;
+      P.g[r0] = gn;
+      P.L[(long long)r0 * P.R_cap + r0] = d;
+      P.W[(long long)r0 * P.ldW + r0] = dinv;
+      st->gnew[0] = gn;
+      st->r = r0 + 1;
+      st->m = st->m + 1;
+      if (!ok) { st->err = -5; st->done = 1; }
+    }
+  }
+  __syncthreads();
+  const double dinv = s_dinv;
+  const int nparts = min(n_solve_ctas, r0);
+  const int gw = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int sub = lane >> 2, cq = lane & 3;
+  for (int c0 = gw * 4; c0 < r0; c0 += nw * 4) {
+    const int c = c0 + cq;
+    double y = 0.0;
+    if (c < r0) {
+      const double* yp = P.ypart + c;
+      // every solve CTA < nparts wrote all r0 columns of its partial (zeros included): plain
+      // strided sum, five independent loads in flight per lane
+      int part = sub;
+      for (; part + 32 < nparts; part += 40) {
+        const double a0 = __ldcg(yp + (long long)part * GS1_RMAX);
+        const double a1 = __ldcg(yp + (long long)(part + 8) * GS1_RMAX);
+        const double a2 = __ldcg(yp + (long long)(part + 16) * GS1_RMAX);
+        const double a3 = __ldcg(yp + (long long)(part + 24) * GS1_RMAX);
+        const double a4 = __ldcg(yp + (long long)(part + 32) * GS1_RMAX);
+        y += a0; y += a1; y += a2; y += a3; y += a4;
+      }
+      for (; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
+    }
+    y += __shfl_xor_sync(0xffffffffu, y, 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 8);
+    y += __shfl_xor_sync(0xffffffffu, y, 16);
+    if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * dinv;
+  }
+}
+
+// W' from W (the grid backend's one-pass mode does not maintain it): 32 x 32 tiles
+__global__ void __launch_bounds__(256) k_transpose_lower(const double* __restrict__ W, double* Wt, long long ld, int R) {
+  __shared__ double t[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;      // Wt[bx + i][by + j] = W[by + j][bx + i]
+  if (bx > by + 31) return;                                   // strictly upper block of W: zero
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int row = by + i, col = bx + threadIdx.x;
+    t[i][threadIdx.x] = (row < R && col < R) ? W[(long long)row * ld + col] : 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int row = bx + i, col = by + threadIdx.x;
+    if (row < R && col < R) Wt[(long long)row * ld + col] = t[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K2: S = Q(new,new) - X'X = Lnn Lnn';  new rows of W = Lnn^-1 [-X'W | I]  (and of W');
 //     g_new = Lnn^-1 (y - m - X'g).  Every CTA recomputes the small Gram block.
 // ---------------------------------------------------------------------------------------

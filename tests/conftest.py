@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """Make sure the C-ABI library exists and is current (nvcc cross-compiles without a GPU)."""
+    try:
+        from gpis_b200 import build
+        build.build()
+    except Exception as e:  # the tests that need it will fail loudly
+        print("gpis_b200 build failed:", e)
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     return {k: z[k] for k in z.files}
