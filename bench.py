@@ -153,7 +153,7 @@ METRIC = "active-set pts selected/s (step = 4000-pt LSE selection + full posteri
 def workload_config(args):
     return {"workload": f"box TSDF {args.grid}^3 ({args.grid ** 3} candidates), SE ell={HYP_ELL} noise={NOISE}, "
                         f"{args.active}-pt straddle active set (beta={BETA}, eps={EPS}) + full {args.grid}^3 posterior grid",
-            "grid": args.grid, "active_set": args.active, "precision": "fp64", "backend": getattr(args, "backend", "grid"),
+            "grid": args.grid, "active_set": args.active, "precision": getattr(args, "precision", "fp64"), "backend": getattr(args, "backend", "grid"),
             "l2": ("per-step working set (W rows, axis tables, posterior arrays: > 300 MB over a step's kernels) exceeds L2; no explicit flush"
                    if getattr(args, "backend", "grid") == "grid" else "inputs larger than L2 (panel store >> 126 MB); no explicit flush")}
 
@@ -193,7 +193,10 @@ def run_ours(args):
     d_mean = torch.empty(n_loc, dtype=torch.float64, device=dev)
     d_var = torch.empty(n_loc, dtype=torch.float64, device=dev)
 
+    from gpis_b200 import _lib as glib
+    tf32 = args.precision == "tf32"
     eng = GpisEngine(D, n_loc, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA,
+                     precision=glib.PREC_TF32 if tf32 else glib.PREC_FP64,
                      rank=rank, world_size=world, total_candidates=N, id_base=lo, device=local_rank)
     sel = gdist.ShardedSelector(eng, rank, world, lo, hi)
     if world > 1 and args.exchange == "peer":
@@ -313,12 +316,18 @@ def run_ours(args):
             pass
         tpeak = float(fp64.get("dmma_m8n8k4_tflops", 37.2)) * world
         tach = float(tot[2]) / args.steps / main_s / 1e12
+        if args.precision == "tf32":
+            # tcgen05 kind::tf32 runs at half the bf16 rate; three MMAs per algorithmic product (3xTF32)
+            tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
+            tach = 3.0 * tach
         roof = {"kernel": "k_grid_gemm (per-step [ny x r] x [r x nx] contraction per z-slice on the fp64 tensor "
                           "pipe, DMMA.8x8x4; stream-K over 148 persistent CTAs)",
                 "with_epilogue_kernel_tflops": float(tot[2]) / args.steps / upd_s / 1e12,
                 "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
                 "peak_source": ("fp64 DMMA.8x8x4 peak measured on this pool's B200 by scripts/fp64_peak.cu "
-                                "(profiles/r01_fp64_peak.json) x n_gpus; MEASURED_PEAKS.json has no fp64 figure"),
+                                "(profiles/r01_fp64_peak.json) x n_gpus; MEASURED_PEAKS.json has no fp64 figure")
+                if args.precision == "fp64" else
+                "MEASURED_PEAKS.json bf16_tflops / 2 (tcgen05 kind::tf32 rate) x n_gpus; achieved counts the 3 executed MMAs per product",
                 "traffic": ncu_traffic("r01_k_grid_gemm_ncu.csv"),
                 "traffic_note": "DRAM bytes read+written per launch from the committed ncu --set full capture (profiles/, launch at r~300): the operands come from L2, the kernel is not HBM-bound",
                 "algorithmic_flops_per_step": float(tot[2]) / args.steps,
@@ -328,7 +337,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": n_sel / s_dev, "unit": "pts/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * s_dev, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "tf32x3 GEMM (fp32 accumulate), f64 factor/state",
+        "data": "synthetic", "config": workload_config(args),
         "select_pts_per_s": n_sel / sel_s, "grid_pts_per_s": N / max(s_dev - sel_s, 1e-9) if grid_backend else N / pred_s,
         "instrumented_ms_per_step": ms_inst / args.steps,
         "phase_ms": {"note": "from the instrumented steps (per-launch CUDA events, plain launches)", "select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
@@ -415,6 +425,8 @@ def main():
     ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32"],
+                    help="fp64 (default, exact-sequence mode) or tf32: update GEMM on tcgen05 with the 3xTF32 split")
     ap.add_argument("--backend", default="grid", choices=["grid", "panel"],
                     help="grid: lattice candidates, separable DMMA path (default); panel: arbitrary-point HBM path")
     args = ap.parse_args()

@@ -139,7 +139,7 @@ def detect_lattice(points):
 
 
 def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hyp=None, predict=True,
-                               backend="auto"):
+                               backend="auto", precision=_lib.PREC_FP64):
     """select_active_set_straddle.m:1-147 on the GPU engine.
 
     shapeParams: points (N,D), tsdf (N,), normals (N,D) or None/empty, noise (N,) or None/empty
@@ -157,7 +157,7 @@ def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hy
     K = int(trainingParams["activeSetSize"])
     first = _default_first(N) if first_index is None else int(first_index)
     eng = GpisEngine(D, N, K, use_gradients=use_grad, level=float(trainingParams["levelSet"]),
-                     eps=float(trainingParams["eps"]), beta=float(trainingParams["beta"]),
+                     eps=float(trainingParams["eps"]), beta=float(trainingParams["beta"]), precision=precision,
                      **_hyp_to_cfg(hyp, D))
     lat = detect_lattice(pts) if backend in ("auto", "grid") else None
     if backend == "grid" and lat is None:

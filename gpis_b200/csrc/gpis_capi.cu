@@ -12,6 +12,7 @@
 #include "../../include/gpis_b200.h"
 #include "gpis_common.cuh"
 #include "gpis_grid.cuh"
+#include "gpis_grid_tf32.cuh"
 #include "gpis_predict.cuh"
 #include "gpis_select.cuh"
 
@@ -96,13 +97,14 @@ struct Dispatch {
   void (*g_solve1)(EngineParams);
   void (*g_wrow)(EngineParams);
   void (*g_gemm)(EngineParams);
+  void (*g_gemm_tf32)(EngineParams);
   void (*g_epi)(EngineParams);
 };
 
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_epilogue<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -153,7 +155,8 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
 gpis_status launch_update(gpis_engine* e, cudaStream_t s, cudaEvent_t mid = nullptr) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2) {
-    d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
+    if (e->cfg.precision == GPIS_PREC_TF32) d.g_gemm_tf32<<<e->P.gemm_ctas, TF32_THREADS, TF32_SMEM, s>>>(e->P);
+    else d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
     if (mid) cudaEventRecord(mid, s);
     d.g_epi<<<GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s>>>(e->P);
     e->launches += 2;
@@ -232,7 +235,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
   if (cfg->dim < 1 || cfg->dim > MAXD || cfg->num_candidates < 0 || cfg->max_active < 1) return GPIS_ERR_INVALID;
   if (!(cfg->ell > 0.0) || !(cfg->sf2 > 0.0) || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
     return GPIS_ERR_INVALID;
-  if (cfg->precision != GPIS_PREC_FP64) return GPIS_ERR_INVALID;   // TF32 storage mode: not built yet
+  if (cfg->precision != GPIS_PREC_FP64 && cfg->precision != GPIS_PREC_TF32) return GPIS_ERR_INVALID;
   if (cfg->num_candidates > 0x7fffffffLL * TW / 2) return GPIS_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GPIS_ERR_NO_DEVICE; }
@@ -319,6 +322,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
     CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    CU(cudaFuncSetAttribute((const void*)disp.g_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF32_SMEM));
+    P.gemm_kc = cfg->precision == GPIS_PREC_TF32 ? TKC : GKC;
     e->solve_ctas = e->num_sms * 4;
     e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
@@ -372,6 +377,8 @@ gpis_status gpis_set_candidates(gpis_handle e, const double* pts, const double* 
   if (!e) return GPIS_ERR_INVALID;
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
+  if (e->cfg.precision == GPIS_PREC_TF32)
+    return fail(e, GPIS_ERR_INVALID, "GPIS_PREC_TF32 is implemented for lattice candidates (gpis_set_grid_candidates) only");
   if (N && (!pts || !tsdf)) return fail(e, GPIS_ERR_INVALID, "pts and tsdf are required");
   if (e->NB > 1 && N && !normals) return fail(e, GPIS_ERR_INVALID, "use_gradients needs normals");
   if (N) {
@@ -427,6 +434,7 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     const size_t bytes = sizeof(double) * (size_t)(e->rk_pad + GKC) * ld;
     if (bytes > e->table_bytes[d]) {
       CU(dalloc(e, &P.T[d], bytes / sizeof(double)));
+      if (e->cfg.precision == GPIS_PREC_TF32 && d < 2) CU(dalloc(e, &P.Tf[d], bytes / sizeof(double)));
       e->table_bytes[d] = bytes;
     }
     P.ldt[d] = ld;
@@ -494,6 +502,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
     CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
     for (int d = 0; d < MAXD; ++d) {
       CU(cudaMemsetAsync(e->P.T[d], 0, e->table_bytes[d], s));
+      if (e->P.Tf[d]) CU(cudaMemsetAsync(e->P.Tf[d], 0, e->table_bytes[d] / 2, s));
       if (d >= e->D) {    // unused axes: constant-one tables
         const long long rows = e->rk_pad + GKC;
         k_fill_ones_col0<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(e->P.T[d], e->P.ldt[d], rows);

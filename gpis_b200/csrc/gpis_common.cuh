@@ -90,6 +90,8 @@ struct EngineParams {
   double gorg[MAXD], gh[MAXD];   // x = gorg + gh * global index
   double* T[MAXD];         // [rows][ldt]: axis tables (axis 2 spans the GLOBAL z range)
   int ldt[MAXD];
+  float* Tf[MAXD];         // fp32 copies of the axis tables (TF32 mode), same leading dimensions
+  int gemm_kc;             // model rows per split-K chunk of the update GEMM (16 DMMA, 32 tcgen05)
   double* W;               // [rows][ldW] lower triangular L^-1
   double* Wt;              // its transpose (shared with the predict kernel)
   long long ldW;

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
       if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;     // [d_a f(x_rho), f(x_j)]
       if (d == 0) v *= P.sf2;
       P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
+      if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
     }
   }
   if (tid == 0) {
@@ -264,6 +265,8 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
           if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;
           if (d == 0) v *= P.sf2;
           P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
+          if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
+      if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
         }
       }
       return;
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams 
         double v = exp(-0.5 * diff * diff * P.inv_ell2);
         if (d == 0) v *= P.sf2;
         P.T[d][(long long)r0 * P.ldt[d] + j] = v;
+        if (P.Tf[d]) P.Tf[d][(long long)r0 * P.ldt[d] + j] = (float)v;
       }
     }
     return;
@@ -842,7 +846,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   __shared__ double s_sb, s_gn[NB];
   if (tid == 0) {                       // CTA-uniform: split-K segment count of this tile, sqrt(beta_t)
     const int r0 = st->r0;
-    const int C = (r0 + NB + GKC - 1) / GKC;
+    const int C = (r0 + NB + P.gemm_kc - 1) / P.gemm_kc;
     const long long U = (long long)T * C;
     const int G = (int)min((long long)P.gemm_ctas, U);
     const int g_first = unit_owner((long long)tile * C, U, G);
