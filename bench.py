@@ -277,6 +277,33 @@ def run_ours(args):
         acc = {k: v * args.steps for k, v in acc.items()}
     clocks = sampler.stop() if rank == 0 else None
     ids, n_model = eng.active()
+    # (4) optional: the same job in TF32 mode (update GEMM on tcgen05, 3xTF32), reported beside the
+    #     fp64 headline, never instead of it
+    tf32_extra = None
+    if grid_backend and not tf32 and not args.no_tf32:
+        ref_mean, ref_var = h_mean.clone(), h_var.clone()
+        eng2 = GpisEngine(D, n_loc, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA,
+                          precision=glib.PREC_TF32, rank=rank, world_size=world, total_candidates=N, id_base=lo,
+                          device=local_rank)
+        sel2 = gdist.ShardedSelector(eng2, rank, world, lo, hi)
+        if world > 1 and args.exchange == "peer":
+            sel2.enable_peer_exchange()
+        eng_fp64, sel_fp64 = eng, sel
+        eng, sel = eng2, sel2
+        step(True)
+        ms_tf32, _ = timed(False, args.steps)
+        step(True)
+        ids2, _ = eng2.active()
+        dv = torch.stack([(h_mean - ref_mean).abs().max(), ((h_var - ref_var).abs() / ref_var.abs().clamp_min(1e-2)).max()]).to(dev)
+        if world > 1:
+            dist.all_reduce(dv, op=dist.ReduceOp.MAX)
+        tf32_extra = {"ms_per_step": ms_tf32 / args.steps, "value": len(ids2) / (ms_tf32 / 1e3 / args.steps), "unit": "pts/s",
+                      "picks_identical_to_fp64": bool(np.array_equal(ids, ids2)),
+                      "max_abs_mean_diff_vs_fp64": float(dv[0]), "max_rel_var_diff_vs_fp64": float(dv[1]),
+                      "note": "GPIS_PREC_TF32: tcgen05 kind::tf32, 3xTF32 split, fp32 TMEM accumulators; factor and posterior state stay fp64"}
+        eng, sel = eng_fp64, sel_fp64
+        h_mean.copy_(ref_mean); h_var.copy_(ref_var)
+        eng2.close()
     # checksum of the posterior grid (sum of mean and of variance over all lattice points)
     cs = torch.stack([h_mean.sum(), h_var.sum()]).to(dev)
     if world > 1:
@@ -362,6 +389,8 @@ def run_ours(args):
                      "predict_tflops_fp64": (N * float(R) * R + 2.0 * N * R) / max(pred_s, 1e-9) / 1e12},
         "clocks": clocks,
     }
+    if tf32_extra is not None:
+        out["tf32_mode"] = tf32_extra
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, pts, tsdf, first)
     print(json.dumps(out))
@@ -422,6 +451,7 @@ def main():
     ap.add_argument("--ref-predict-points", type=int, default=16384)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode measurement")
     ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")

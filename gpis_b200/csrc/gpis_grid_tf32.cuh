@@ -32,6 +32,11 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// x rounded to nearest at 11 significant bits (a tf32 value): Veltkamp split with 2^13 + 1
+__device__ __forceinline__ float split_hi(float x) {
+  const float c = __fmul_rn(x, 8193.0f);
+  return __fsub_rn(c, __fsub_rn(c, x));
+}
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes
 __device__ __forceinline__ uint64_t umma_desc_sw128(unsigned saddr) {
   uint64_t d = 0;
@@ -194,10 +199,11 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
           float v0 = raw[(4 * j + 0) * GT + row], v1 = raw[(4 * j + 1) * GT + row];
           float v2 = raw[(4 * j + 2) * GT + row], v3 = raw[(4 * j + 3) * GT + row];
           if (is_a) { v0 *= cs[4 * j]; v1 *= cs[4 * j + 1]; v2 *= cs[4 * j + 2]; v3 *= cs[4 * j + 3]; }
-          // round-to-nearest split (cvt.rna): with it the TF32 mode reproduced all 4000 fp64 picks of
-          // the 128^3 bench; a truncating split (AND mask) was no faster and diverged
-          h.x = to_tf32(v0); h.y = to_tf32(v1); h.z = to_tf32(v2); h.w = to_tf32(v3);
-          l.x = to_tf32(v0 - h.x); l.y = to_tf32(v1 - h.y); l.z = to_tf32(v2 - h.z); l.w = to_tf32(v3 - h.w);
+          // round-to-nearest hi (Veltkamp split on the FMA pipe, 3 full-rate ops instead of the
+          // conversion unit's cvt.rna); lo = x - hi is exact in fp32 and the tensor core reads its
+          // top 11 bits.  A truncating hi (AND mask) loses a bit and changed the pick sequence.
+          h.x = split_hi(v0); h.y = split_hi(v1); h.z = split_hi(v2); h.w = split_hi(v3);
+          l.x = v0 - h.x; l.y = v1 - h.y; l.z = v2 - h.z; l.w = v3 - h.w;
           const unsigned off = sw128_chunk(row, j);
           *reinterpret_cast<float4*>(hi + off) = h;
           *reinterpret_cast<float4*>(lo + off) = l;
