@@ -233,3 +233,41 @@ def test_tf32_mode_tcgen05(G):
     assert np.max(np.abs(var - fv) / np.maximum(np.abs(fv), 1e-2)) < 1e-3
     print("tf32: first divergence from fp64 picks at", same, "of", len(m64["order"]),
           "max |dmu|", np.max(np.abs(mu - fm)), "max rel dvar", np.max(np.abs(var - fv) / np.maximum(np.abs(fv), 1e-2)))
+
+
+def test_tf32_mode_gradients_2d_and_odd_sizes(G):
+    """TF32 mode beyond the headline shape: gradient rows (NB = 4 passes), 2-D lattices, axes that
+    are not multiples of the tile (per-row bulk copies instead of one 16 KB copy), tiny models."""
+    shape, hyp = sphere(12, ell=2.5, with_normals=True)
+    tr = {"activeSetSize": 60, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    m, _, _ = G.select_active_set(shape, tr, first_index=500, hyp=hyp, backend="grid", predict=False,
+                                  precision=G._lib.PREC_TF32)
+    ids = m["order"][:m["n_in_model"]]
+    ref = O.create_gpis(shape["points"][ids], shape["tsdf"][ids], shape["normals"][ids], None, hyp)
+    fm, _, Kx = O.gp_mean(ref, shape["points"], True)
+    fv = O.gp_var_diag(ref, shape["points"], Kx, True)
+    mu, var = m.engine.candidate_posterior()
+    n = shape["points"].shape[0]
+    assert np.max(np.abs(mu - fm[:n])) < 1e-3
+    assert np.max(np.abs(var - fv) / np.maximum(np.abs(fv), 1e-2)) < 1e-3
+    rng = np.random.default_rng(7)
+    for dims in [(25, 25), (130, 3), (7, 5)]:
+        nx, ny = dims
+        ii = np.indices((ny, nx)).reshape(2, -1)[::-1].T.astype(np.float64) + 1.0
+        c = np.array([nx * 0.52, ny * 0.47])
+        tsdf = np.clip((np.linalg.norm(ii - c, axis=1) - min(dims) * 0.3) / 2.0, -1, 1) + 1e-3 * rng.standard_normal(ii.shape[0])
+        sh = {"points": ii, "tsdf": tsdf, "normals": None, "noise": None}
+        hy = {"cov": np.array([0.6, 0.0]), "mean": np.zeros(3), "lik": 0.5 * np.log(0.05)}
+        t2 = {"activeSetSize": min(30, ii.shape[0]), "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+        m2, _, _ = G.select_active_set(sh, t2, first_index=3, hyp=hy, backend="grid", predict=False,
+                                       precision=G._lib.PREC_TF32)
+        i2 = m2["order"][:m2["n_in_model"]]
+        r2 = O.create_gpis(ii[i2], tsdf[i2], None, None, hy)
+        f2, _, K2 = O.gp_mean(r2, ii, False)
+        v2 = O.gp_var_diag(r2, ii, K2, False)
+        mu2, var2 = m2.engine.candidate_posterior()
+        assert np.max(np.abs(mu2 - f2)) < 1e-3, dims
+        assert np.max(np.abs(var2 - v2) / np.maximum(np.abs(v2), 1e-2)) < 1e-3, dims
+    # the panel backend does not implement this mode and says so
+    with pytest.raises(G._lib.GpisError):
+        G.select_active_set(shape, tr, first_index=500, hyp=hyp, backend="panel", precision=G._lib.PREC_TF32)
