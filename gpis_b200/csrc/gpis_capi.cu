@@ -476,9 +476,12 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
 }
 
 namespace {
-__global__ void k_fill_ones_col0(double* T, int ld, long long rows) {
+__global__ void k_fill_ones_col0(double* T, float* Tf, int ld, long long rows) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (r < rows) T[r * ld] = 1.0;
+  if (r < rows) {
+    T[r * ld] = 1.0;
+    if (Tf) Tf[r * ld] = 1.0f;
+  }
 }
 }  // namespace
 
@@ -505,7 +508,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
       if (e->P.Tf[d]) CU(cudaMemsetAsync(e->P.Tf[d], 0, e->table_bytes[d] / 2, s));
       if (d >= e->D) {    // unused axes: constant-one tables
         const long long rows = e->rk_pad + GKC;
-        k_fill_ones_col0<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(e->P.T[d], e->P.ldt[d], rows);
+        k_fill_ones_col0<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(e->P.T[d], e->P.Tf[d], e->P.ldt[d], rows);
         e->launches++;
       }
     }

@@ -271,3 +271,27 @@ def test_tf32_mode_gradients_2d_and_odd_sizes(G):
     # the panel backend does not implement this mode and says so
     with pytest.raises(G._lib.GpisError):
         G.select_active_set(shape, tr, first_index=500, hyp=hyp, backend="panel", precision=G._lib.PREC_TF32)
+
+
+def test_one_dimensional_lattice_both_precisions(G):
+    rng = np.random.default_rng(9)
+    n = 300
+    x = np.arange(n, dtype=np.float64)[:, None] * 0.5
+    tsdf = np.clip(np.sin(x[:, 0] / 7.0) * 1.5, -1, 1) + 1e-3 * rng.standard_normal(n)
+    shape = {"points": x, "tsdf": tsdf, "normals": None, "noise": None}
+    hyp = {"cov": np.array([np.log(3.0), 0.0]), "mean": np.zeros(2), "lik": 0.5 * np.log(0.05)}
+    tr = {"activeSetSize": 40, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental(shape, tr, 17, hyp=hyp, prune=False)
+    m, _, _ = G.select_active_set(shape, tr, first_index=17, hyp=hyp, backend="grid", predict=False)
+    assert m["backend"] == "grid" and np.array_equal(m["order"], ora["order"])
+    fm, fv, _ = O.predict_points(ora["gp"], x)
+    mu, var = m.engine.candidate_posterior()
+    assert np.max(np.abs(mu - fm)) < 1e-8 and np.max(np.abs(var - fv)) < 1e-8
+    mt, _, _ = G.select_active_set(shape, tr, first_index=17, hyp=hyp, backend="grid", predict=False,
+                                   precision=G._lib.PREC_TF32)
+    it = mt["order"][:mt["n_in_model"]]
+    ref = O.create_gpis(x[it], tsdf[it], None, None, hyp)
+    f2, _, K2 = O.gp_mean(ref, x, False)
+    mu2, var2 = mt.engine.candidate_posterior()
+    assert np.max(np.abs(mu2 - f2)) < 1e-3
+    assert np.max(np.abs(var2 - O.gp_var_diag(ref, x, K2, False))) < 1e-3
