@@ -118,7 +118,7 @@ Dispatch get_dispatch(int D, bool grad) {
   }
 }
 
-constexpr size_t PRED_SMEM = (2 * PKC * PSB + 2 * PKC * PQ + 32 * PQ) * sizeof(double);
+constexpr size_t PRED_SMEM = (2 * PKC * PLDA + 2 * PKC * PLDB + 8 * PQ) * sizeof(double);
 
 gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int finalize_only) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);

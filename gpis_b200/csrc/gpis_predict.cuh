@@ -93,15 +93,24 @@ __device__ __forceinline__ double kstar(const PredictParams& P, int k, const dou
   return val;
 }
 
+// fp64 tensor pipe: D[256 rows x 32 queries] += Wt-tile' * K*-tile, DMMA.8x8x4; 8 warps, each a
+// 32 x 32 warp tile (4 x 4 DMMA tiles).  Shared rows are padded by 4 doubles so that the four
+// k-rows of a fragment load fall on disjoint bank groups.
+constexpr int PLDA = PSB + 4;
+constexpr int PLDB = PQ + 4;
+
+__device__ __forceinline__ void p_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 template <int NB, int D>
 __global__ void __launch_bounds__(PRED_THREADS, 2) k_predict_f64(PredictParams P) {
   extern __shared__ __align__(16) double smem[];
-  double* As = smem;                                  // [2][PKC][PSB]
-  double* Bs = smem + 2 * PKC * PSB;                  // [2][PKC][PQ]
-  double* Red = Bs + 2 * PKC * PQ;                    // [32][PQ] reductions
+  double* As = smem;                                  // [2][PKC][PLDA]
+  double* Bs = smem + 2 * PKC * PLDA;                 // [2][PKC][PLDB]
+  double* Red = Bs + 2 * PKC * PLDB;                  // [8][PQ] reductions
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rg = (warp >> 1) * 8 + (lane >> 2);       // row group 0..31 -> rows rg*8..+7
-  const int qg = (warp & 1) * 4 + (lane & 3);         // query group 0..7 -> queries qg*4..+3
   const long long q0 = (long long)blockIdx.x * PQ;
   const int R = P.R;
 
@@ -116,28 +125,30 @@ __global__ void __launch_bounds__(PRED_THREADS, 2) k_predict_f64(PredictParams P
   double mu_part = 0.0, nr_part[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) nr_part[d] = 0.0;
-  double vsq[4] = {0.0, 0.0, 0.0, 0.0};
+  double vsq[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) vsq[j][0] = vsq[j][1] = 0.0;
 
   const int n_sb = (R + PSB - 1) / PSB;
   for (int sb = 0; sb < n_sb; ++sb) {
     const bool last_sb = (sb == n_sb - 1);
     const int k_end = min(R, (sb + 1) * PSB);
     const int n_chunks = (k_end + PKC - 1) / PKC;
-    double acc[8][4];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     auto issue_A = [&](int c, int buf) {
       // tile rows k = c*PKC .. +15, columns sb*PSB .. +255 of Wt: 16 x 2 KB
       const double* src = P.Wt + (long long)(c * PKC) * P.ldw + (long long)sb * PSB;
-      double* dst = As + buf * PKC * PSB;
+      double* dst = As + buf * PKC * PLDA;
 #pragma unroll
       for (int i = 0; i < (PKC * PSB * 8 / 16) / PRED_THREADS; ++i) {
         const int e = tid + i * PRED_THREADS;        // 16-byte element
         const int kk = e / (PSB / 2), col2 = e % (PSB / 2);
-        cp_async16(dst + kk * PSB + col2 * 2, src + (long long)kk * P.ldw + col2 * 2);
+        cp_async16(dst + kk * PLDA + col2 * 2, src + (long long)kk * P.ldw + col2 * 2);
       }
       cp_async_commit();
     };
@@ -165,49 +176,62 @@ __global__ void __launch_bounds__(PRED_THREADS, 2) k_predict_f64(PredictParams P
     double bnext[2];
     issue_A(0, 0);
     gen_B(0, bnext);
-    Bs[(gk)*PQ + gq] = bnext[0];
-    Bs[(gk + 8) * PQ + gq] = bnext[1];
+    Bs[gk * PLDB + gq] = bnext[0];
+    Bs[(gk + 8) * PLDB + gq] = bnext[1];
     cp_async_wait_all();
     __syncthreads();
     for (int c = 0; c < n_chunks; ++c) {
       const int buf = c & 1;
       const bool more = c + 1 < n_chunks;
       if (more) { issue_A(c + 1, buf ^ 1); gen_B(c + 1, bnext); }
-      const double* Ab = As + buf * PKC * PSB + rg * 8;
-      const double* Bb = Bs + buf * PKC * PQ + qg * 4;
+      const double* Ab = As + buf * PKC * PLDA + warp * 32 + (lane >> 2);
+      const double* Bb = Bs + buf * PKC * PLDB + (lane >> 2);
 #pragma unroll
-      for (int kk = 0; kk < PKC; ++kk) {
-        double a[8], b[4];
-        const double2* ap = reinterpret_cast<const double2*>(Ab + kk * PSB);
-        const double2* bp = reinterpret_cast<const double2*>(Bb + kk * PQ);
+      for (int k4 = 0; k4 < PKC / 4; ++k4) {
+        const int kb = k4 * 4 + (lane & 3);
+        double af[4], bf[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const double2 t = ap[i]; a[2 * i] = t.x; a[2 * i + 1] = t.y; }
+        for (int i = 0; i < 4; ++i) af[i] = Ab[kb * PLDA + i * 8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { const double2 t = bp[i]; b[2 * i] = t.x; b[2 * i + 1] = t.y; }
+        for (int j = 0; j < 4; ++j) bf[j] = Bb[kb * PLDB + j * 8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+          for (int j = 0; j < 4; ++j) p_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
       if (more) {
-        Bs[(buf ^ 1) * PKC * PQ + gk * PQ + gq] = bnext[0];
-        Bs[(buf ^ 1) * PKC * PQ + (gk + 8) * PQ + gq] = bnext[1];
+        Bs[(buf ^ 1) * PKC * PLDB + gk * PLDB + gq] = bnext[0];
+        Bs[(buf ^ 1) * PKC * PLDB + (gk + 8) * PLDB + gq] = bnext[1];
         cp_async_wait_all();
       }
       __syncthreads();
     }
+    // |v|^2 over this super-block's rows: fragment element (i, j, e) is row i*8 + lane/4 of the
+    // warp's 32 rows, query j*8 + 2*(lane%4) + e
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vsq[j] += acc[i][j] * acc[i][j];
+      for (int i = 0; i < 4; ++i) {
+        vsq[j][0] += acc[i][j][0] * acc[i][j][0];
+        vsq[j][1] += acc[i][j][1] * acc[i][j][1];
+      }
   }
 
-  // reductions: |v|^2 over the 32 row groups; mean / gradient parts over the 8 generator rows
+  // reductions: |v|^2 over the 8 row lanes of a warp (fixed shuffle tree) and the 8 warps; mean /
+  // gradient parts over the 8 generator rows
 #pragma unroll
-  for (int j = 0; j < 4; ++j) Red[rg * PQ + qg * 4 + j] = vsq[j];
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = vsq[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((lane >> 2) == 0) Red[warp * PQ + j * 8 + 2 * (lane & 3) + e] = v;
+    }
   __syncthreads();
   double vs = 0.0;
-  if (tid < PQ) for (int i = 0; i < 32; ++i) vs += Red[i * PQ + tid];
+  if (tid < PQ) for (int i = 0; i < 8; ++i) vs += Red[i * PQ + tid];
   __syncthreads();
   Red[gk * PQ + gq] = mu_part;
   __syncthreads();
