@@ -37,7 +37,7 @@ struct gpis_engine {
   bool have_candidates = false, have_noise = false, have_ids = false;
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
-  bool fused_solve = false, onepass = false;
+  bool fused_solve = false, onepass = false, solve_ring = false;
   int solve1_ctas = 0;
   size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
@@ -95,6 +95,7 @@ struct Dispatch {
   void (*g_solve)(EngineParams);
   void (*g_solve_fused)(EngineParams);
   void (*g_solve1)(EngineParams);
+  void (*g_solve2)(EngineParams);
   void (*g_wrow)(EngineParams);
   void (*g_gemm)(EngineParams);
   void (*g_gemm_tf32)(EngineParams);
@@ -104,7 +105,7 @@ struct Dispatch {
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -128,7 +129,8 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
       e->launches++;
     } else {
       if (e->onepass) {
-        d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
+        if (e->solve_ring) d.g_solve2<<<e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s>>>(e->P);
+        else d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
         k_grid_wrow1<<<e->num_sms, GSOLVE_THREADS, 0, s>>>(e->P, e->solve1_ctas);
         e->launches += 2;
         CU(cudaGetLastError());
@@ -328,8 +330,10 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
     e->onepass = (NB == 1) && P.R_cap <= GS1_RMAX && getenv("GPIS_TWO_PASS") == nullptr;
-    e->solve1_ctas = e->num_sms * 2;
+    e->solve_ring = getenv("GPIS_SOLVE_REGS") == nullptr;       // rows of W through a bulk-copy smem ring
+    e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
     if (e->onepass) {
+      CU(cudaFuncSetAttribute((const void*)disp.g_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS2_SMEM));
       CU(cudaFuncSetAttribute((const void*)disp.g_solve1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(sizeof(double) * GS1_RMAX)));
       CU(dalloc(e, &P.ypart, (size_t)e->solve1_ctas * GS1_RMAX));

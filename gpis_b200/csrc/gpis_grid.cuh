@@ -116,6 +116,32 @@ __device__ __forceinline__ double ld_nc_f64(const double* p) {
 template <int N>
 __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ int pick_winner(const EngineParams& P, const double* recs) {
   int win = -1;
   double bs = 0.0;
@@ -441,6 +467,138 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams 
   }
 }
 
+// Same pass with the rows of W streamed through a shared-memory ring by bulk async copies (one
+// copy per row, GS2_STAGES rows in flight per CTA, one CTA per SM): no register staging, so the
+// depth of the prefetch no longer competes with the column accumulators.
+constexpr int GS2_STAGES = 5;
+constexpr size_t GS2_SMEM = sizeof(double) * GS1_RMAX * (1 + GS2_STAGES) + 8 * GS2_STAGES;
+
+template <int D>
+__global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams P) {
+  extern __shared__ __align__(16) double s_dyn[];
+  double* s_kv = s_dyn;                               // [GS1_RMAX]
+  double* ring = s_dyn + GS1_RMAX;                    // [GS2_STAGES][GS1_RMAX]
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)GS2_STAGES * GS1_RMAX);
+  __shared__ double s_red[2][GSOLVE_THREADS / 32];
+  __shared__ int s_win;
+  DevState* st = P.st;
+  if (st->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gen = st->iter;
+  if (!wait_records(P, st, gen)) return;
+  const double* recs = records_ptr(P, gen);
+  const int m = st->m;
+  if (tid == 0) {
+    int win = pick_winner(P, recs);
+    if (win >= 0 && m >= P.M_cap) win = -1;
+    s_win = win;
+  }
+  __syncthreads();
+  const int win = s_win;
+  const bool book = (blockIdx.x == gridDim.x - 1);
+  if (win < 0) {
+    if (book && tid == 0) st->done = 1;
+    return;
+  }
+  const double* pay = recs + (long long)win * P.pay_stride;
+  const long long* pl = reinterpret_cast<const long long*>(pay);
+  const int r0 = st->r;
+  double nx[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) nx[d] = pay[PAY_X + d];
+  if (book) {
+    if (tid == 0) {
+      if (win == P.rank) P.flags[grid_slot_of_local(P, pl[PAY_LOCAL])] |= F_ACTIVE;
+      P.sel_ids[m] = pl[PAY_ID];
+      st->n_sel = m + 1;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { st->nx[d] = nx[d]; P.AX[d][m] = nx[d]; }
+      st->nnoise = pay[PAY_NOISE];
+      st->r0 = r0;
+      double mf = P.mean_c;
+#pragma unroll
+      for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
+      st->gnew[0] = pay[PAY_TSDF] - mf;
+    }
+    for (int d = 0; d < D; ++d) {
+      const int len = P.gtlen[d];
+      for (int j = tid; j < len; j += blockDim.x) {
+        const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
+        double v = exp(-0.5 * diff * diff * P.inv_ell2);
+        if (d == 0) v *= P.sf2;
+        P.T[d][(long long)r0 * P.ldt[d] + j] = v;
+        if (P.Tf[d]) P.Tf[d][(long long)r0 * P.ldt[d] + j] = (float)v;
+      }
+    }
+    return;
+  }
+  const int G = gridDim.x - 1;
+  const int my_rows = (int)blockIdx.x < r0 ? (r0 - 1 - (int)blockIdx.x) / G + 1 : 0;   // rows blockIdx.x + i*G
+  if (tid == 0) {
+    for (int i = 0; i < GS2_STAGES; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int i) {          // thread 0: row i of this CTA into ring slot i % STAGES
+    const int row = (int)blockIdx.x + i * G;
+    const unsigned bytes = (unsigned)(((row + 2) >> 1) << 4);          // row + 1 doubles, rounded up to 16 B
+    unsigned long long* bar = &full[i % GS2_STAGES];
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_g2s(ring + (size_t)(i % GS2_STAGES) * GS1_RMAX, P.W + (long long)row * P.ldW, bytes, bar);
+  };
+  if (tid == 0)
+    for (int i = 0; i < GS2_STAGES && i < my_rows; ++i) issue(i);
+#pragma unroll 4
+  for (int i = tid; i < GS1_RMAX; i += GSOLVE_THREADS) {
+    double k = 0.0;
+    if (i < m) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { const double df = P.AX[d][i] - nx[d]; d2 += df * df; }
+      k = P.sf2 * exp(-0.5 * d2 * P.inv_ell2);
+    }
+    s_kv[i] = k;
+  }
+  __syncthreads();
+  double acc[GS1_CPT];
+#pragma unroll
+  for (int i = 0; i < GS1_CPT; ++i) acc[i] = 0.0;
+  int par = 0;
+  for (int i = 0; i < my_rows; ++i) {
+    const int row = (int)blockIdx.x + i * G;
+    const double* buf = ring + (size_t)(i % GS2_STAGES) * GS1_RMAX;
+    mbar_wait(&full[i % GS2_STAGES], (unsigned)((i / GS2_STAGES) & 1));
+    double w[GS1_CPT];
+    double p = 0.0;
+#pragma unroll
+    for (int c = 0; c < GS1_CPT; ++c) {
+      const int col = tid + GSOLVE_THREADS * c;
+      w[c] = col <= row ? buf[col] : 0.0;
+      p += w[c] * s_kv[col];
+    }
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if (lane == 0) s_red[par][warp] = p;
+    __syncthreads();                 // also: every thread has read this row's slot
+    double ell = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < GSOLVE_THREADS / 32; ++w8) ell += s_red[par][w8];
+    par ^= 1;
+    if (tid == 0) {
+      P.L[(long long)r0 * P.R_cap + row] = ell;
+      if (i + GS2_STAGES < my_rows) issue(i + GS2_STAGES);   // refill the slot just drained
+    }
+#pragma unroll
+    for (int c = 0; c < GS1_CPT; ++c) acc[c] += ell * w[c];
+  }
+  if ((int)blockIdx.x < r0) {
+    double* yp = P.ypart + (long long)blockIdx.x * GS1_RMAX + tid;
+#pragma unroll
+    for (int c = 0; c < GS1_CPT; ++c)
+      if (tid + GSOLVE_THREADS * c < r0) yp[GSOLVE_THREADS * c] = acc[c];
+  }
+}
+
 // new row of W from the partial Y's; d, g_new, L's diagonal entry.  Four columns per warp,
 // eight lanes per column over the partials (fixed assignment + fixed shuffle tree).
 __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow1(EngineParams P, int n_solve_ctas) {
@@ -684,32 +842,6 @@ constexpr int GEMM_CWARPS = 8;                       // consumer warps: 4 (jy) x
 constexpr int GEMM_THREADS = (GEMM_CWARPS + 1) * 32;   // + 1 producer warp
 constexpr size_t GEMM_SMEM = (size_t)GPIPE * GSTAGE_DOUBLES * sizeof(double) + 2 * GPIPE * sizeof(unsigned long long);
 constexpr int GTILE_ELEMS = GT * GT;
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // owner CTA of flattened unit u when U units are cut into G ranges [g*U/G, (g+1)*U/G)
 __device__ __forceinline__ int unit_owner(long long u, long long U, int G) {
