@@ -41,6 +41,7 @@ struct gpis_engine {
   int solve1_ctas = 0;
   size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
+  size_t bimg_floats = 0;
   size_t w_bytes = 0, gws_bytes = 0, partials_cap = 0, state_cap = 0, grid_slots = 0;
   bool selecting = false;
   int inverse_rows = -1;        // rows Wt/alpha are valid for
@@ -326,6 +327,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF32_SMEM));
     P.gemm_kc = cfg->precision == GPIS_PREC_TF32 ? TKC : GKC;
+    P.gemm_zgroup = cfg->precision == GPIS_PREC_TF32 ? TZ : 1;
     e->solve_ctas = e->num_sms * 4;
     e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
@@ -448,6 +450,14 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     CU(dalloc(e, &P.W, (size_t)e->rk_pad * e->ldw));
     e->w_bytes = sizeof(double) * (size_t)e->rk_pad * e->ldw;
   }
+  if (e->cfg.precision == GPIS_PREC_TF32) {
+    P.bimg_cmax = (int)((e->rk_pad + GKC + TKC - 1) / TKC);
+    const size_t need = (size_t)((P.glen[0] + GT - 1) / GT) * P.bimg_cmax * 2 * GT * TKC;
+    if (need > e->bimg_floats) {
+      CU(dalloc(e, &P.bimg, need));
+      e->bimg_floats = need;
+    }
+  }
   const int tiles = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT) * P.glen[2];
   e->grid_ctas = tiles;
   if ((size_t)GEPI_CTAS_PER_TILE * tiles > e->partials_cap) {
@@ -464,7 +474,11 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     e->state_cap = e->grid_slots;
   }
   P.gemm_ctas = e->num_sms;
-  P.gws_segmax = P.gemm_ctas / tiles + 2;
+  {
+    const int txy = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT);
+    const int groups = txy * ((P.glen[2] + P.gemm_zgroup - 1) / P.gemm_zgroup);
+    P.gws_segmax = P.gemm_ctas / groups + 2;
+  }
   {
     const size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
     if (need > e->gws_bytes) {
@@ -506,6 +520,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   }
   if (e->backend == 2) {
     CU(cudaMemsetAsync(e->P.W, 0, e->w_bytes, s));
+    if (e->P.bimg) CU(cudaMemsetAsync(e->P.bimg, 0, sizeof(float) * e->bimg_floats, s));
     CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
     for (int d = 0; d < MAXD; ++d) {
       CU(cudaMemsetAsync(e->P.T[d], 0, e->table_bytes[d], s));

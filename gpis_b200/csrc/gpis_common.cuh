@@ -91,6 +91,9 @@ struct EngineParams {
   double* T[MAXD];         // [rows][ldt]: axis tables (axis 2 spans the GLOBAL z range)
   int ldt[MAXD];
   float* Tf[MAXD];         // fp32 copies of the axis tables (TF32 mode), same leading dimensions
+  float* bimg;             // TF32 mode: hi/lo axis-0 table in the MMA's shared-memory image [x-tiles][bimg_cmax][2][128*32]
+  int bimg_cmax;
+  int gemm_zgroup;         // z-slices per work tile of the update GEMM (1 DMMA, 2 tcgen05)
   int gemm_kc;             // model rows per split-K chunk of the update GEMM (16 DMMA, 32 tcgen05)
   double* W;               // [rows][ldW] lower triangular L^-1
   double* Wt;              // its transpose (shared with the predict kernel)

@@ -155,6 +155,39 @@ __device__ __forceinline__ int pick_winner(const EngineParams& P, const double* 
   return win;
 }
 
+// Axis-table rows of the NB new model rows of the point at nx (whole block cooperates):
+//   T_d[row][j] = exp(-(x_j - p_d)^2 / (2 ell^2)), times (x_j - p_d)/ell^2 on the row's own axis for
+//   gradient rows ([d_a f(x_rho), f(x_j)]); sf2 is folded into axis 0.  TF32 mode also keeps fp32
+//   copies and, for axis 0, the hi/lo split already in the K-major SWIZZLE_128B image the tcgen05
+//   B operand is read from (one 2 x 16 KB image per (x-tile, 32-row chunk); it does not depend on
+//   the step or the z-slice, so it is written once per row and bulk-copied by every CTA).
+template <int NB, int D>
+__device__ __forceinline__ void grid_write_tables(const EngineParams& P, int r0, const double* nx) {
+  for (int d = 0; d < D; ++d) {
+    const int len = P.gtlen[d];
+    for (int e = threadIdx.x; e < len * NB; e += blockDim.x) {
+      const int a = e / len, j = e % len;
+      const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
+      double v = exp(-0.5 * diff * diff * P.inv_ell2);
+      if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;
+      if (d == 0) v *= P.sf2;
+      const long long row = r0 + a;
+      P.T[d][row * P.ldt[d] + j] = v;
+      if (P.Tf[d]) P.Tf[d][row * P.ldt[d] + j] = (float)v;
+      if (d == 0 && P.bimg) {
+        const float x = (float)v;
+        const float c = __fmul_rn(x, 8193.0f);
+        const float hi = __fsub_rn(c, __fsub_rn(c, x));           // Veltkamp: x rounded to a tf32
+        const int k = (int)(row & 31), n = j & (GT - 1);
+        float* img = P.bimg + (((long long)(j / GT) * P.bimg_cmax + (row >> 5)) * 2) * (GT * 32);
+        const unsigned off = (unsigned)((n >> 3) * 1024 + (n & 7) * 128 + (((k >> 2) ^ (n & 7)) << 4) + ((k & 3) << 2)) >> 2;
+        img[off] = hi;
+        img[GT * 32 + off] = x - hi;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // K0 (one CTA): winner, its covariance with the model rows (kvec), its axis-table rows.
 // ---------------------------------------------------------------------------------------
@@ -199,20 +232,7 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
 #pragma unroll
       for (int b = 0; b < NB; ++b) P.kvec[(long long)a * P.R_cap + i * NB + b] = c[a][b];
   }
-  // axis tables of the new rows: T_d[row][j] = exp(-(x_j - p_d)^2 / (2 ell^2)), times
-  // (x_j - p_d)/ell^2 on the row's own axis for gradient rows; sf2 is folded into axis 0.
-  for (int d = 0; d < D; ++d) {
-    const int len = P.gtlen[d];
-    for (int e = tid; e < len * NB; e += blockDim.x) {
-      const int a = e / len, j = e % len;
-      const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
-      double v = exp(-0.5 * diff * diff * P.inv_ell2);
-      if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;     // [d_a f(x_rho), f(x_j)]
-      if (d == 0) v *= P.sf2;
-      P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
-      if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
-    }
-  }
+  grid_write_tables<NB, D>(P, r0, nx);
   if (tid == 0) {
 #pragma unroll
     for (int d = 0; d < D; ++d) { st->nx[d] = nx[d]; P.AX[d][m] = nx[d]; }
@@ -282,19 +302,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
         st->gnew[0] = pay[PAY_TSDF] - mf;
         for (int a = 1; a < NB; ++a) st->gnew[a] = pay[PAY_NRM + a - 1] - P.mean_w[a - 1];
       }
-      for (int d = 0; d < D; ++d) {
-        const int len = P.gtlen[d];
-        for (int e = tid; e < len * NB; e += blockDim.x) {
-          const int a = e / len, j = e % len;
-          const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
-          double v = exp(-0.5 * diff * diff * P.inv_ell2);
-          if (a > 0 && a - 1 == d) v *= diff * P.inv_ell2;
-          if (d == 0) v *= P.sf2;
-          P.T[d][(long long)(r0 + a) * P.ldt[d] + j] = v;
-          if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
-      if (P.Tf[d]) P.Tf[d][(long long)(r0 + a) * P.ldt[d] + j] = (float)v;
-        }
-      }
+      grid_write_tables<NB, D>(P, r0, nx);
       return;
     }
     for (int i = tid; i < m; i += blockDim.x) {
@@ -399,16 +407,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams 
       for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
       st->gnew[0] = pay[PAY_TSDF] - mf;
     }
-    for (int d = 0; d < D; ++d) {
-      const int len = P.gtlen[d];
-      for (int j = tid; j < len; j += blockDim.x) {
-        const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
-        double v = exp(-0.5 * diff * diff * P.inv_ell2);
-        if (d == 0) v *= P.sf2;
-        P.T[d][(long long)r0 * P.ldt[d] + j] = v;
-        if (P.Tf[d]) P.Tf[d][(long long)r0 * P.ldt[d] + j] = (float)v;
-      }
-    }
+    grid_write_tables<1, D>(P, r0, nx);
     return;
   }
 #pragma unroll 4
@@ -520,16 +519,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams 
       for (int d = 0; d < D; ++d) mf += P.mean_w[d] * nx[d];
       st->gnew[0] = pay[PAY_TSDF] - mf;
     }
-    for (int d = 0; d < D; ++d) {
-      const int len = P.gtlen[d];
-      for (int j = tid; j < len; j += blockDim.x) {
-        const double diff = (P.gorg[d] + P.gh[d] * (double)j) - nx[d];
-        double v = exp(-0.5 * diff * diff * P.inv_ell2);
-        if (d == 0) v *= P.sf2;
-        P.T[d][(long long)r0 * P.ldt[d] + j] = v;
-        if (P.Tf[d]) P.Tf[d][(long long)r0 * P.ldt[d] + j] = (float)v;
-      }
-    }
+    grid_write_tables<1, D>(P, r0, nx);
     return;
   }
   const int G = gridDim.x - 1;
@@ -979,10 +969,13 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   if (tid == 0) {                       // CTA-uniform: split-K segment count of this tile, sqrt(beta_t)
     const int r0 = st->r0;
     const int C = (r0 + NB + P.gemm_kc - 1) / P.gemm_kc;
-    const long long U = (long long)T * C;
+    // the GEMM's work tile is a group of gemm_zgroup z-slices (1 for DMMA, 2 for tcgen05)
+    const int txy = tiles_x * tiles_y, zg = P.gemm_zgroup;
+    const int gtile = (tile / txy / zg) * txy + tile % txy;
+    const long long U = (long long)txy * ((P.glen[2] + zg - 1) / zg) * C;
     const int G = (int)min((long long)P.gemm_ctas, U);
-    const int g_first = unit_owner((long long)tile * C, U, G);
-    s_nseg = unit_owner((long long)(tile + 1) * C - 1, U, G) - g_first + 1;
+    const int g_first = unit_owner((long long)gtile * C, U, G);
+    s_nseg = unit_owner((long long)(gtile + 1) * C - 1, U, G) - g_first + 1;
     double beta = P.beta;
     if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
     else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
