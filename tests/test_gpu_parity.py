@@ -220,3 +220,54 @@ def test_gpu_active_set_selector_mirror(G, tmp_path):
     a = np.loadtxt(tmp_path / "out" / "alpha.csv", delimiter=",")
     assert np.max(np.abs(a - gp.alpha()[:len(a)])) < 1e-8 * np.max(np.abs(a))
     assert sel.last["errors"].mean > 0
+
+
+def test_engine_reuse_across_backends_and_calls(G):
+    """One handle, many calls: panel -> grid -> panel candidates, repeated selections, a dense fit in
+    between; every result must equal a fresh engine's (no stale state survives a re-set)."""
+    from gpis_b200.synth import sphere_tsdf
+    pts, tsdf = sphere_tsdf(12, trunc=3.0)
+    g, K = 12, 50
+    cfg = dict(ell=2.5, noise=0.05, level=0.0, eps=1e-2, beta=10.0)
+
+    def fresh(kind):
+        e = G.GpisEngine(3, g ** 3, K, **cfg)
+        if kind == "grid":
+            e.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdf)
+        else:
+            e.set_candidates(pts, tsdf)
+        e.select(321, K)
+        ids, nm = e.active()
+        q = pts[::37]
+        m, v, _ = e.predict(q)
+        return ids, nm, m, v
+
+    ref_ids, ref_nm, ref_m, ref_v = fresh("grid")
+    pid, pnm, pm, pv = fresh("panel")
+    assert np.array_equal(ref_ids, pid) and ref_nm == pnm
+    assert np.max(np.abs(ref_m - pm)) < 1e-9 and np.max(np.abs(ref_v - pv)) < 1e-9
+    eng = G.GpisEngine(3, g ** 3, K, **cfg)
+    q = pts[::37]
+    for kind in ["panel", "grid", "grid", "panel", "fit", "grid"]:
+        if kind == "fit":
+            eng.fit(pts[ref_ids[:ref_nm]], tsdf[ref_ids[:ref_nm]])
+            m, v, _ = eng.predict(q)
+            assert np.max(np.abs(m - ref_m)) < 1e-8 and np.max(np.abs(v - ref_v)) < 1e-8
+            continue
+        if kind == "grid":
+            eng.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdf)
+        else:
+            eng.set_candidates(pts, tsdf)
+        eng.select(321, K)
+        ids, nm = eng.active()
+        assert np.array_equal(ids, ref_ids) and nm == ref_nm, kind
+        m, v, _ = eng.predict(q)
+        assert np.max(np.abs(m - ref_m)) < 1e-9 and np.max(np.abs(v - ref_v)) < 1e-9, kind
+        amb, hi, lo, ac = eng.levelset()
+        assert ac.sum() == len(ids) and not (hi & lo & ~ac).all()
+    # argument errors are statuses
+    with pytest.raises(G._lib.GpisError):
+        eng.select(321, K + 5)
+    with pytest.raises(G._lib.GpisError):
+        eng.select(g ** 3 + 7, K)
+    eng.close()
