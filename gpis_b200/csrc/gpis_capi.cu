@@ -130,10 +130,14 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
       e->launches++;
     } else {
       if (e->onepass) {
-        if (e->solve_ring) d.g_solve2<<<e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s>>>(e->P);
-        else d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
-        k_grid_wrow1<<<e->num_sms, GSOLVE_THREADS, 0, s>>>(e->P, e->solve1_ctas);
-        e->launches += 2;
+        if (e->solve_ring) {      // solve + grid barrier + new row of W in ONE launch (one CTA per SM)
+          d.g_solve2<<<e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s>>>(e->P);
+          e->launches += 1;
+        } else {
+          d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
+          k_grid_wrow1<<<e->num_sms, GSOLVE_THREADS, 0, s>>>(e->P, e->solve1_ctas);
+          e->launches += 2;
+        }
         CU(cudaGetLastError());
         return GPIS_OK;
       }
@@ -665,7 +669,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       CU(cudaEventRecord(e->prof_events[4 * it + 3], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += e->backend == 2 ? ((e->fused_solve || e->onepass) ? 4 : 5) : 2;
+      e->launches += e->backend == 2 ? ((e->onepass && e->solve_ring) ? 3 : (e->fused_solve || e->onepass) ? 4 : 5) : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;

@@ -29,6 +29,7 @@ struct DevState {
   int n_live[2];
   unsigned int blocks_done;
   int n_scored;  // candidates scored (unclassified at the start) in the running iteration
+  unsigned int grid_bar;  // arrivals at the in-kernel grid barrier of the fused solve kernel (monotonic per selection)
   unsigned int epoch;  // selection counter: tags the peer-exchange flags of this selection
   long long pending_id;
   double nx[MAXD];          // point appended last

@@ -466,6 +466,67 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams 
   }
 }
 
+// new row of W from the partial Y's; d, g_new, L's diagonal entry.  Four columns per warp,
+// eight lanes per column over the partials (fixed assignment + fixed shuffle tree).
+__device__ __forceinline__ void grid_wrow1_body(const EngineParams& P, DevState* st, int r0, int n_solve_ctas) {
+  __shared__ double s_gram[GSOLVE_THREADS / 32][2];
+  __shared__ double s_dinv;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const double* X = P.L + (long long)r0 * P.R_cap;
+  double p0 = 0.0, p1 = 0.0;
+  for (int s = tid; s < r0; s += GSOLVE_THREADS) { const double x = X[s]; p0 += x * x; p1 += x * P.g[s]; }
+  for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+  if (lane == 0) { s_gram[tid >> 5][0] = p0; s_gram[tid >> 5][1] = p1; }
+  __syncthreads();
+  if (tid == 0) {
+    double xx = 0.0, xg = 0.0;
+    for (int w = 0; w < GSOLVE_THREADS / 32; ++w) { xx += s_gram[w][0]; xg += s_gram[w][1]; }
+    double sdiag = P.sf2 + st->nnoise - xx;
+    bool ok = sdiag > 0.0;
+    if (!ok) sdiag = 1.0;
+    const double d = sqrt(sdiag), dinv = 1.0 / d;
+    s_dinv = dinv;
+    if (blockIdx.x == 0) {
+      const double gn = (st->gnew[0] - xg) / d;
+      P.g[r0] = gn;
+      P.L[(long long)r0 * P.R_cap + r0] = d;
+      P.W[(long long)r0 * P.ldW + r0] = dinv;
+      st->gnew[0] = gn;
+      st->r = r0 + 1;
+      st->m = st->m + 1;
+      if (!ok) { st->err = -5; st->done = 1; }
+    }
+  }
+  __syncthreads();
+  const double dinv = s_dinv;
+  const int nparts = min(n_solve_ctas, r0);
+  const int gw = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int sub = lane >> 2, cq = lane & 3;
+  for (int c0 = gw * 4; c0 < r0; c0 += nw * 4) {
+    const int c = c0 + cq;
+    double y = 0.0;
+    if (c < r0) {
+      const double* yp = P.ypart + c;
+      // every solve CTA < nparts wrote all r0 columns of its partial (zeros included): plain
+      // strided sum, five independent loads in flight per lane
+      int part = sub;
+      for (; part + 32 < nparts; part += 40) {
+        const double a0 = __ldcg(yp + (long long)part * GS1_RMAX);
+        const double a1 = __ldcg(yp + (long long)(part + 8) * GS1_RMAX);
+        const double a2 = __ldcg(yp + (long long)(part + 16) * GS1_RMAX);
+        const double a3 = __ldcg(yp + (long long)(part + 24) * GS1_RMAX);
+        const double a4 = __ldcg(yp + (long long)(part + 32) * GS1_RMAX);
+        y += a0; y += a1; y += a2; y += a3; y += a4;
+      }
+      for (; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
+    }
+    y += __shfl_xor_sync(0xffffffffu, y, 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 8);
+    y += __shfl_xor_sync(0xffffffffu, y, 16);
+    if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * dinv;
+  }
+}
+
 // Same pass with the rows of W streamed through a shared-memory ring by bulk async copies (one
 // copy per row, GS2_STAGES rows in flight per CTA, one CTA per SM): no register staging, so the
 // depth of the prefetch no longer competes with the column accumulators.
@@ -520,10 +581,9 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams 
       st->gnew[0] = pay[PAY_TSDF] - mf;
     }
     grid_write_tables<1, D>(P, r0, nx);
-    return;
   }
   const int G = gridDim.x - 1;
-  const int my_rows = (int)blockIdx.x < r0 ? (r0 - 1 - (int)blockIdx.x) / G + 1 : 0;   // rows blockIdx.x + i*G
+  const int my_rows = (!book && (int)blockIdx.x < r0) ? (r0 - 1 - (int)blockIdx.x) / G + 1 : 0;   // rows blockIdx.x + i*G
   if (tid == 0) {
     for (int i = 0; i < GS2_STAGES; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -581,76 +641,40 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams 
 #pragma unroll
     for (int c = 0; c < GS1_CPT; ++c) acc[c] += ell * w[c];
   }
-  if ((int)blockIdx.x < r0) {
+  if (!book && (int)blockIdx.x < r0) {
     double* yp = P.ypart + (long long)blockIdx.x * GS1_RMAX + tid;
 #pragma unroll
     for (int c = 0; c < GS1_CPT; ++c)
       if (tid + GSOLVE_THREADS * c < r0) yp[GSOLVE_THREADS * c] = acc[c];
   }
+  // ---- grid barrier (one CTA per SM, all resident), then the former k_grid_wrow1 in the same launch:
+  //      the partial Y's and the new row of L are complete, every CTA finishes a slice of W's new row
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_bar_to;
+  if (tid == 0) {
+    s_bar_to = 0;
+    const unsigned target = (unsigned)(gen + 1) * gridDim.x;
+    atomicAdd(&st->grid_bar, 1u);
+    const long long t0 = clock64();
+    while (*(volatile unsigned*)&st->grid_bar < target) {
+      if (clock64() - t0 > 4000000000LL) { s_bar_to = 1; break; }
+      __nanosleep(64);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (s_bar_to) {
+    if (tid == 0) { st->err = -7; st->done = 1; }
+    return;
+  }
+  grid_wrow1_body(P, st, r0, G);
 }
 
-// new row of W from the partial Y's; d, g_new, L's diagonal entry.  Four columns per warp,
-// eight lanes per column over the partials (fixed assignment + fixed shuffle tree).
 __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_wrow1(EngineParams P, int n_solve_ctas) {
   DevState* st = P.st;
   if (st->done) return;
-  __shared__ double s_gram[GSOLVE_THREADS / 32][2];
-  __shared__ double s_dinv;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int r0 = st->r0;
-  const double* X = P.L + (long long)r0 * P.R_cap;
-  double p0 = 0.0, p1 = 0.0;
-  for (int s = tid; s < r0; s += GSOLVE_THREADS) { const double x = X[s]; p0 += x * x; p1 += x * P.g[s]; }
-  for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
-  if (lane == 0) { s_gram[tid >> 5][0] = p0; s_gram[tid >> 5][1] = p1; }
-  __syncthreads();
-  if (tid == 0) {
-    double xx = 0.0, xg = 0.0;
-    for (int w = 0; w < GSOLVE_THREADS / 32; ++w) { xx += s_gram[w][0]; xg += s_gram[w][1]; }
-    double sdiag = P.sf2 + st->nnoise - xx;
-    bool ok = sdiag > 0.0;
-    if (!ok) sdiag = 1.0;
-    const double d = sqrt(sdiag), dinv = 1.0 / d;
-    s_dinv = dinv;
-    if (blockIdx.x == 0) {
-      const double gn = (st->gnew[0] - xg) / d;
-      P.g[r0] = gn;
-      P.L[(long long)r0 * P.R_cap + r0] = d;
-      P.W[(long long)r0 * P.ldW + r0] = dinv;
-      st->gnew[0] = gn;
-      st->r = r0 + 1;
-      st->m = st->m + 1;
-      if (!ok) { st->err = -5; st->done = 1; }
-    }
-  }
-  __syncthreads();
-  const double dinv = s_dinv;
-  const int nparts = min(n_solve_ctas, r0);
-  const int gw = (blockIdx.x * blockDim.x + tid) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  const int sub = lane >> 2, cq = lane & 3;
-  for (int c0 = gw * 4; c0 < r0; c0 += nw * 4) {
-    const int c = c0 + cq;
-    double y = 0.0;
-    if (c < r0) {
-      const double* yp = P.ypart + c;
-      // every solve CTA < nparts wrote all r0 columns of its partial (zeros included): plain
-      // strided sum, five independent loads in flight per lane
-      int part = sub;
-      for (; part + 32 < nparts; part += 40) {
-        const double a0 = __ldcg(yp + (long long)part * GS1_RMAX);
-        const double a1 = __ldcg(yp + (long long)(part + 8) * GS1_RMAX);
-        const double a2 = __ldcg(yp + (long long)(part + 16) * GS1_RMAX);
-        const double a3 = __ldcg(yp + (long long)(part + 24) * GS1_RMAX);
-        const double a4 = __ldcg(yp + (long long)(part + 32) * GS1_RMAX);
-        y += a0; y += a1; y += a2; y += a3; y += a4;
-      }
-      for (; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
-    }
-    y += __shfl_xor_sync(0xffffffffu, y, 4);
-    y += __shfl_xor_sync(0xffffffffu, y, 8);
-    y += __shfl_xor_sync(0xffffffffu, y, 16);
-    if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * dinv;
-  }
+  grid_wrow1_body(P, st, st->r0, n_solve_ctas);
 }
 
 // W' from W (the grid backend's one-pass mode does not maintain it): 32 x 32 tiles

@@ -162,6 +162,7 @@ __global__ void k_begin(EngineParams P, long long first_local, unsigned epoch) {
     st->n_live[1] = 0;
     st->blocks_done = 0;
     st->n_scored = 0;
+    st->grid_bar = 0;
     st->pending_id = -1;
     st->epoch = epoch;
   }
