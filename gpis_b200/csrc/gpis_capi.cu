@@ -480,6 +480,11 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   P.gemm_ctas = e->num_sms;
   {
     const int txy = ((P.glen[0] + GT - 1) / GT) * ((P.glen[1] + GT - 1) / GT);
+    // TF32 GEMM: pair z-slices per work tile only while that still leaves about one work tile per
+    // two SMs; on a small shard (multi-GPU slabs) pairing would split each tile over twice as many
+    // CTAs and double the partials the epilogue has to sum
+    if (e->cfg.precision == GPIS_PREC_TF32)
+      P.gemm_zgroup = (txy * ((P.glen[2] + TZ - 1) / TZ) * 3 >= e->num_sms) ? TZ : 1;
     const int groups = txy * ((P.glen[2] + P.gemm_zgroup - 1) / P.gemm_zgroup);
     P.gws_segmax = P.gemm_ctas / groups + 2;
   }

@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
   const int nx = P.glen[0], ny = P.glen[1], nz = P.glen[2];
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT, txy = tiles_x * tiles_y;
   const int T = txy * nz;                                  // real 128x128 tiles (workspace index)
-  const int Tg = txy * ((nz + TZ - 1) / TZ);               // z-grouped tiles (work units)
+  const int zg = P.gemm_zgroup;                            // 1 or TZ slices per work tile (host's choice)
+  const int Tg = txy * ((nz + zg - 1) / zg);               // z-grouped tiles (work units)
   const int C = (r0 + NB + TKC - 1) / TKC;
   const long long U = (long long)Tg * C;
   const int G = (int)min((long long)gridDim.x, U), g = blockIdx.x;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
       const int klen = r0 + a + 1;
       for (long long u = u0; u < u1; ++u) {
         const int gt = (int)(u / C), c = (int)(u % C);
-        const int tz0 = (gt / txy) * TZ, ty = (gt / tiles_x) % tiles_y;
+        const int tz0 = (gt / txy) * zg, ty = (gt / tiles_x) % tiles_y;
         mbar_wait(&raw_empty[rs], rph ^ 1);
         float* rTy = reinterpret_cast<float*>(raws + (size_t)rs * T_RAW_BYTES);
         float* cs = rTy + TKC * GT;
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
         const double w = rho < klen ? wrow[rho] : 0.0;
 #pragma unroll
         for (int z = 0; z < TZ; ++z)
-          cs[z * TKC + lane] = (tz0 + z < nz) ? (float)(w * P.T[2][rho * P.ldt[2] + P.gz0 + tz0 + z]) : 0.0f;
+          cs[z * TKC + lane] = (z < zg && tz0 + z < nz) ? (float)(w * P.T[2][rho * P.ldt[2] + P.gz0 + tz0 + z]) : 0.0f;
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], TKC * GT * 4);
         __syncwarp();
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
         long long u = u0;
         while (u < u1) {
           const int gt = (int)(u / C);
-          const int nsl = min(TZ, nz - (gt / txy) * TZ);    // valid slices of this group
+          const int nsl = min(zg, nz - (gt / txy) * zg);    // valid slices of this group
           const long long uend = min(u1, (long long)(gt + 1) * C);
           mbar_wait(&acc_empty[cs_], cph ^ 1);             // epilogue has drained this accumulator stage
           tc_fence_after();
@@ -310,8 +311,8 @@ __global__ void __launch_bounds__(TF32_THREADS, 1) k_grid_gemm_tf32(EngineParams
         const int gt = (int)(u / C);
         u = min(u1, (long long)(gt + 1) * C);
         const int seg = g - unit_owner((long long)gt * C, U, G);
-        const int tz0 = (gt / txy) * TZ, tyx = gt % txy;
-        const int nsl = min(TZ, nz - tz0);
+        const int tz0 = (gt / txy) * zg, tyx = gt % txy;
+        const int nsl = min(zg, nz - tz0);
         mbar_wait(&acc_full[as], aph);
         tc_fence_after();
         for (int z = 0; z < nsl; ++z) {
