@@ -5,6 +5,7 @@ each of `n_workers` host threads owns one engine on its own CUDA stream and work
 share of the objects (the C ABI releases the GIL for the duration of a call, the greedy loop of
 each object is a captured CUDA graph).  With N GPUs every rank takes objects rank::N ("replicas
 only" -- DESIGN.md section 6)."""
+import os
 import threading
 
 import numpy as np
@@ -40,6 +41,12 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
     results = [None] * len(mine)
     errors = []
     n_workers = max(1, min(n_workers, len(mine)))
+    # Engines of a batch run concurrently on one device.  The single-engine fast path fuses two
+    # kernels behind an in-kernel grid barrier, which needs ALL its CTAs resident at once -- not
+    # guaranteed when several engines' kernels share the SMs -- so the batch uses the unfused
+    # kernels (read by gpis_create; see include/gpis_b200.h).
+    prev = os.environ.get("GPIS_SOLVE_REGS")
+    os.environ["GPIS_SOLVE_REGS"] = "1"
 
     def work(w):
         try:
@@ -65,6 +72,10 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
         t.start()
     for t in threads:
         t.join()
+    if prev is None:
+        os.environ.pop("GPIS_SOLVE_REGS", None)
+    else:
+        os.environ["GPIS_SOLVE_REGS"] = prev
     if errors:
         raise errors[0]
     return results

@@ -20,7 +20,11 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *     calls are asynchronous on it unless they return values through host pointers,
  *     in which case they synchronise the stream before returning;
- *   - there is no CPU fallback: without a CUDA device gpis_create fails.
+ *   - there is no CPU fallback: without a CUDA device gpis_create fails;
+ *   - a handle assumes it has the device to itself while gpis_select runs (its factor-append kernel
+ *     uses an in-kernel grid barrier: one CTA per SM, all resident).  To run several handles
+ *     concurrently on one device (gpis_b200/batch.py does), set the environment variable
+ *     GPIS_SOLVE_REGS=1 before gpis_create: the append then uses two plain kernels instead.
  */
 #ifndef GPIS_B200_H
 #define GPIS_B200_H
