@@ -60,3 +60,37 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no oracle", ""), f
+
+
+def _build_c_consumer(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_check")
+    src = os.path.join(ROOT, "tests", "c_abi", "abi_check.c")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe, src,
+                    "-ldl", "-lm"], check=True)
+    return exe
+
+
+def test_header_is_valid_c_and_a_c_caller_gets_no_device(lib, tmp_path):
+    """include/gpis_b200.h compiles as C99 (-Wall -Werror) and a plain-C caller that dlopens the
+    library gets GPIS_ERR_NO_DEVICE on a box without a GPU."""
+    import subprocess
+    import torch
+    from gpis_b200 import _lib
+    exe = _build_c_consumer(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked C test")
+    r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sizeof(gpis_config)=152" in r.stdout and "create status=-6" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_caller_runs_a_selection_through_the_abi(lib, tmp_path):
+    """The same C program on a GPU: lattice selection + posterior with host buffers, no Python in the loop."""
+    import subprocess
+    from gpis_b200 import _lib
+    exe = _build_c_consumer(tmp_path)
+    r = subprocess.run([exe, _lib.LIB_PATH, "gpu"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "selected=30 in_model=29 first=123" in r.stdout
