@@ -5,11 +5,11 @@ gpis_b200/libgpis_b200.so); this package is the Python host side that mirrors th
 reference's operator interface.  There is no CPU fallback."""
 from . import _lib
 from .api import (GpModel, create_gpis, create_sparse_gpis, default_hyp, evaluate_errors, gp_cov,
-                  gp_mean, predict_2d_grid, predict_grid, predict_points, select_active_set,
+                  gp_mean, predict_2d_grid, predict_grid, predict_points, sample_shapes, select_active_set,
                   select_active_set_straddle)
 from .engine import GpisEngine
 from .selector import GaussianProcessHyperparams, GpuActiveSetSelector, PredictionError
 
 __all__ = ["GpisEngine", "GpuActiveSetSelector", "GaussianProcessHyperparams", "PredictionError", "GpModel", "create_gpis", "create_sparse_gpis", "default_hyp", "evaluate_errors",
            "gp_cov", "gp_mean", "predict_2d_grid", "predict_grid", "predict_points", "select_active_set",
-           "select_active_set_straddle"]
+           "select_active_set_straddle", "sample_shapes"]

@@ -19,6 +19,7 @@ SYMBOLS = [
     "gpis_select_end", "gpis_exchange_buffers", "gpis_get_active", "gpis_get_factor", "gpis_fit",
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
+    "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing",
 ]
 
 
@@ -91,6 +92,9 @@ def load():
         "gpis_peer_export": [vp, vp],
         "gpis_peer_import": [vp, vp, C.c_int32],
         "gpis_get_history": [vp, vp, vp, vp, i32p],
+        "gpis_posterior_cov": [vp, dp, C.c_int64, C.c_int32, dp, dp, C.c_int64, vp],
+        "gpis_sample_shapes": [vp, dp, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double, dp, dp, dp, C.c_int64, vp],
+        "gpis_get_sampling_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

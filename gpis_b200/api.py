@@ -81,10 +81,39 @@ def gp_mean(gpModel, x, use_derivative):
     return np.concatenate([mu, np.asarray(nrm).reshape(-1, order="F")])
 
 
-def gp_cov(gpModel, x, Kxxp=None, use_derivative=True):
-    """Diagonal of gp_cov.m:1-21 over the function values (latent variance, :6)."""
+def gp_cov(gpModel, x, Kxxp=None, use_derivative=True, full=False):
+    """gp_cov.m:1-21.  full=False: the diagonal over the function values (latent variance, :6) --
+    all that select_active_set_straddle.m:95-96 and predict_2d_grid.m:15-16 keep.  full=True: the
+    whole symmetrised posterior covariance of [f; d1 f; ..] (dimension-major) as the reference
+    returns it (the consumer is sample_shapes.m:14)."""
+    if full:
+        return np.asarray(gpModel.engine.posterior_cov(x, use_derivative)[1])
     _, var, _ = gpModel.engine.predict(x)
     return np.asarray(var)
+
+
+def sample_shapes(gpModel, gridDim, numSamples, resolution=1, z=None, seed=None, jitter=1e-12, return_logpdf=False):
+    """mc_sampling/sample_shapes.m:1-33: draws of [tsdf; normals] over meshgrid(1:res:g, 1:res:g)
+    from the posterior, and their densities.  The reference draws with MATLAB's randn; here the
+    standard-normal draws are `z` [numSamples, 3 P] or come from torch's generator seeded with
+    `seed` (on the device).  Returns (shape_samples, pdfs) -- pdfs = exp(logpdf) overflows to inf
+    exactly as in the reference's stored constructionResults -- plus logpdf if asked."""
+    import torch
+    ax = np.arange(1, gridDim + 1, resolution, dtype=np.float64)
+    X, Y = np.meshgrid(ax, ax)                                                  # :10-11
+    pts = np.stack([X.reshape(-1, order="F"), Y.reshape(-1, order="F")], axis=1)
+    P = pts.shape[0]
+    if z is None:
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(0 if seed is None else int(seed))
+        z = torch.randn((int(numSamples), 3 * P), dtype=torch.float64, device="cuda", generator=gen)
+    samples, logpdf = gpModel.engine.sample_shapes(pts, z, use_derivative=True, jitter=jitter)
+    if torch.is_tensor(samples):
+        samples, logpdf = samples.cpu().numpy(), logpdf.cpu().numpy()
+    shapes = [{"tsdf": s[:P].copy(), "normals": s[P:].reshape(P, 2, order="F")} for s in samples]   # :25-29
+    with np.errstate(over="ignore"):
+        pdfs = np.exp(logpdf)
+    return (shapes, pdfs, logpdf) if return_logpdf else (shapes, pdfs)
 
 
 def predict_points(gpModel, x, want_normals=True):

@@ -14,6 +14,7 @@
 #include "gpis_grid.cuh"
 #include "gpis_grid_tf32.cuh"
 #include "gpis_predict.cuh"
+#include "gpis_sample.cuh"
 #include "gpis_select.cuh"
 
 using namespace gpis;
@@ -51,6 +52,8 @@ struct gpis_engine {
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double select_ms = 0.0, predict_ms = 0.0, update_ms = 0.0, append_ms = 0.0, main_ms = 0.0, epilogue_ms = 0.0;
+  double cov_ms = 0.0, chol_ms = 0.0, draw_ms = 0.0;   // last gpis_posterior_cov / gpis_sample_shapes
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;
   long long update_launches = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
@@ -356,6 +359,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->state_cap = Nn;
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));
+    CU(cudaEventCreate(&e->ev2));
+    CU(cudaEventCreate(&e->ev3));
     return GPIS_OK;
   };
   rc = body();
@@ -375,6 +380,8 @@ gpis_status gpis_destroy(gpis_handle e) {
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->ev3) cudaEventDestroy(e->ev3);
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->allocs) cudaFree(p);
@@ -858,6 +865,163 @@ gpis_status gpis_predict(gpis_handle e, const double* query, int64_t nq, double*
   if (ce != cudaSuccess) return fail(e, GPIS_ERR_CUDA, cudaGetErrorString(ce));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->predict_ms = ms;
+  return GPIS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// per-call device scratch, released on every return path
+struct Scratch {
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <class T>
+  cudaError_t get(T** out, size_t n) {
+    void* q = nullptr;
+    cudaError_t r = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+    if (r == cudaSuccess) { p.push_back(q); *out = static_cast<T*>(q); }
+    return r;
+  }
+};
+
+struct FullPosterior {
+  double* mean = nullptr;   // [nv]
+  double* S = nullptr;      // [npad][npad], zero outside the nv x nv corner
+  long long nq = 0, nv = 0, npad = 0;
+};
+
+// MEAN and COV (gp_mean.m, gp_cov.m in full) of the joint vector at nq query points, on the device.
+gpis_status posterior_full(gpis_engine* e, const double* query, int64_t nq, int deriv, cudaStream_t s, Scratch& sc,
+                           FullPosterior* out) {
+  gpis_status rc = ensure_inverse(e, s);
+  if (rc != GPIS_OK) return rc;
+  const int D = e->D, R = e->host_state.r;
+  const int nt = deriv ? D + 1 : 1;
+  const long long nv = (long long)nq * nt, npad = (nv + CHB - 1) / CHB * CHB;
+  if (nq > 65535 || npad > 1000000) return fail(e, GPIS_ERR_INVALID, "too many query points for a full covariance (nq <= 65535)");
+  double *dq = nullptr, *Ks = nullptr, *V = nullptr;
+  CU(sc.get(&dq, (size_t)nq * D));
+  CU(sc.get(&out->mean, (size_t)nv));
+  CU(sc.get(&out->S, (size_t)npad * npad));
+  if (R > 0) {
+    CU(sc.get(&Ks, (size_t)R * nv));
+    CU(sc.get(&V, (size_t)R * nv));
+  }
+  CU(cudaMemcpyAsync(dq, query, sizeof(double) * nq * D, cudaMemcpyDefault, s));
+  CU(cudaMemsetAsync(out->S, 0, sizeof(double) * npad * npad, s));
+  FullCovParams F;
+  memset(&F, 0, sizeof(F));
+  for (int d = 0; d < D; ++d) { F.AX[d] = e->P.AX[d]; F.q[d] = dq + (size_t)d * nq; }
+  F.nq = nq;
+  F.nt = nt;
+  F.R = R;
+  F.inv_ell2 = e->P.inv_ell2;
+  F.sf2 = e->P.sf2;
+  for (int d = 0; d < MAXD; ++d) F.mean_w[d] = e->P.mean_w[d];
+  F.mean_c = e->P.mean_c;
+  posterior_full_device(D, e->NB > 1, F, e->d_Wt, e->ldw, e->d_alpha, Ks, V, out->S, npad, out->mean, s, &e->launches);
+  CU(cudaGetLastError());
+  out->nq = nq;
+  out->nv = nv;
+  out->npad = npad;
+  return GPIS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+gpis_status gpis_posterior_cov(gpis_handle e, const double* query, int64_t nq, int32_t use_derivative, double* mean,
+                               double* cov, int64_t ldc, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (nq < 0 || (nq && !query)) return fail(e, GPIS_ERR_INVALID, "query is required");
+  if (nq == 0) return GPIS_OK;
+  const long long nv = (long long)nq * (use_derivative ? e->D + 1 : 1);
+  if (cov && ldc < nv) return fail(e, GPIS_ERR_INVALID, "ldc must be >= the number of values");
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  FullPosterior fp;
+  cudaEventRecord(e->ev0, s);
+  gpis_status rc = posterior_full(e, query, nq, use_derivative, s, sc, &fp);
+  if (rc != GPIS_OK) return rc;
+  cudaEventRecord(e->ev1, s);
+  if (mean) CU(cudaMemcpyAsync(mean, fp.mean, sizeof(double) * nv, cudaMemcpyDefault, s));
+  if (cov)
+    CU(cudaMemcpy2DAsync(cov, sizeof(double) * ldc, fp.S, sizeof(double) * fp.npad, sizeof(double) * nv, (size_t)nv,
+                         cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->cov_ms = ms;
+  return GPIS_OK;
+}
+
+gpis_status gpis_sample_shapes(gpis_handle e, const double* query, int64_t nq, int32_t use_derivative,
+                               int32_t num_samples, const double* z, double jitter, double* samples, double* logpdf,
+                               double* chol, int64_t ldt, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (nq <= 0 || !query) return fail(e, GPIS_ERR_INVALID, "query is required");
+  if (num_samples < 0 || (num_samples && (!z || !samples))) return fail(e, GPIS_ERR_INVALID, "z and samples are required");
+  if (!(jitter >= 0.0)) return fail(e, GPIS_ERR_INVALID, "jitter must be >= 0");
+  const long long nv = (long long)nq * (use_derivative ? e->D + 1 : 1);
+  if (chol && ldt < nv) return fail(e, GPIS_ERR_INVALID, "ldt must be >= the number of values");
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc;
+  FullPosterior fp;
+  cudaEventRecord(e->ev0, s);
+  gpis_status rc = posterior_full(e, query, nq, use_derivative, s, sc, &fp);
+  if (rc != GPIS_OK) return rc;
+  cudaEventRecord(e->ev1, s);
+  const long long npad = fp.npad;
+  const int ns = num_samples;
+  int* d_err = nullptr;
+  double *dz = nullptr, *dzt = nullptr, *dout = nullptr, *dlp = nullptr;
+  CU(sc.get(&d_err, 1));
+  CU(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+  if (ns > 0) {
+    CU(sc.get(&dz, (size_t)ns * nv));
+    CU(sc.get(&dzt, (size_t)ns * nv));
+    CU(sc.get(&dout, (size_t)ns * nv));
+    CU(sc.get(&dlp, (size_t)ns));
+    CU(cudaMemcpyAsync(dz, z, sizeof(double) * ns * nv, cudaMemcpyDefault, s));
+  }
+  chol_upper_device(fp.S, npad, nv, jitter, d_err, s, &e->launches);
+  CU(cudaGetLastError());
+  cudaEventRecord(e->ev2, s);
+  if (ns > 0) {
+    draw_device(dz, dzt, fp.mean, fp.S, npad, ns, nv, dout, dlp, s, &e->launches);
+    CU(cudaGetLastError());
+  }
+  cudaEventRecord(e->ev3, s);
+  int h_err = 0;
+  CU(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (h_err != 0) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "posterior covariance + jitter is not positive definite (pivot %d of %lld): raise jitter",
+             h_err, nv);
+    return fail(e, GPIS_ERR_NOT_PD, buf);
+  }
+  if (ns > 0) {
+    CU(cudaMemcpyAsync(samples, dout, sizeof(double) * ns * nv, cudaMemcpyDefault, s));
+    if (logpdf) CU(cudaMemcpyAsync(logpdf, dlp, sizeof(double) * ns, cudaMemcpyDefault, s));
+  }
+  if (chol)
+    CU(cudaMemcpy2DAsync(chol, sizeof(double) * ldt, fp.S, sizeof(double) * npad, sizeof(double) * nv, (size_t)nv,
+                         cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->cov_ms = ms;
+  if (cudaEventElapsedTime(&ms, e->ev1, e->ev2) == cudaSuccess) e->chol_ms = ms;
+  if (cudaEventElapsedTime(&ms, e->ev2, e->ev3) == cudaSuccess) e->draw_ms = ms;
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_sampling_timing(gpis_handle e, double* cov_ms, double* chol_ms, double* draw_ms) {
+  if (!e) return GPIS_ERR_INVALID;
+  if (cov_ms) *cov_ms = e->cov_ms;
+  if (chol_ms) *chol_ms = e->chol_ms;
+  if (draw_ms) *draw_ms = e->draw_ms;
   return GPIS_OK;
 }
 

@@ -1,6 +1,8 @@
 // Shared device/host definitions of the GPIS engine (sm_100a).
 #pragma once
+#ifndef GPIS_EMULATE   // tests/emu supplies the execution model on the CPU (test infrastructure only)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace gpis {

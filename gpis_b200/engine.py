@@ -212,6 +212,49 @@ class GpisEngine:
             nrm = nrm.t() if on_dev else nrm.T
         return mean, var, nrm
 
+    def posterior_cov(self, query, use_derivative=False, want_cov=True):
+        """gp_mean.m + the FULL gp_cov.m at the query points: (MEAN [nv], COV [nv, nv]); values are
+        dimension-major [f(all q); d1 f(all q); ..] like the reference's joint vector."""
+        q = _soa(query)
+        nq = q.shape[1]
+        nv = nq * (self.dim + 1 if use_derivative else 1)
+        on_dev = _is_torch(q) and q.is_cuda
+        if on_dev:
+            mean = torch.empty(nv, dtype=torch.float64, device=q.device)
+            cov = torch.empty((nv, nv), dtype=torch.float64, device=q.device) if want_cov else None
+        else:
+            mean, cov = np.empty(nv), (np.empty((nv, nv)) if want_cov else None)
+        self._ck(self.lib.gpis_posterior_cov(self.h, _ptr(q), nq, int(bool(use_derivative)), _ptr(mean), _ptr(cov),
+                                             nv, _stream()))
+        return mean, cov
+
+    def sample_shapes(self, query, z, use_derivative=False, jitter=1e-12, want_chol=False):
+        """sample_shapes.m:14-31 at the query points with the standard-normal draws z [S, nv] made
+        explicit: (samples [S, nv], logpdf [S][, T upper with T'T = COV + jitter I])."""
+        q = _soa(query)
+        nq = q.shape[1]
+        nv = nq * (self.dim + 1 if use_derivative else 1)
+        on_dev = _is_torch(z) and z.is_cuda
+        if on_dev:
+            z = z.to(torch.float64).contiguous().reshape(-1, nv)
+            ns = z.shape[0]
+            samples = torch.empty((ns, nv), dtype=torch.float64, device=z.device)
+            logpdf = torch.empty(ns, dtype=torch.float64, device=z.device)
+            chol = torch.empty((nv, nv), dtype=torch.float64, device=z.device) if want_chol else None
+        else:
+            z = np.ascontiguousarray(np.asarray(z, np.float64).reshape(-1, nv))
+            ns = z.shape[0]
+            samples, logpdf = np.empty((ns, nv)), np.empty(ns)
+            chol = np.empty((nv, nv)) if want_chol else None
+        self._ck(self.lib.gpis_sample_shapes(self.h, _ptr(q), nq, int(bool(use_derivative)), ns, _ptr(z),
+                                             float(jitter), _ptr(samples), _ptr(logpdf), _ptr(chol), nv, _stream()))
+        return (samples, logpdf, chol) if want_chol else (samples, logpdf)
+
+    def sampling_timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.lib.gpis_get_sampling_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"cov_ms": a.value, "chol_ms": b.value, "draw_ms": c.value}
+
     def levelset(self):
         amb = np.empty(self.N)
         hi, lo, ac = (np.empty(self.N, np.uint8) for _ in range(3))

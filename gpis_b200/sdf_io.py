@@ -110,13 +110,33 @@ class _GpisBase:
         self.mean_pred_, self.var_pred_ = self.predict_locations(self.grid_pts_)
 
     def predict_locations(self, points, full_cov=False):
-        """gpis.py:114-123: (means, vars) at the given points; diagonal only (full_cov is the
-        shape-sampling consumer, out of scope)."""
+        """gpis.py:114-123: (means, vars) at the given points; with full_cov the second output is
+        the whole predictive covariance (latent + meas_variance on the diagonal, as GPy returns)."""
         if full_cov:
-            raise NotImplementedError("full posterior covariance is outside the accelerated path")
+            m, c = self.engine.posterior_cov(points, use_derivative=False)
+            c = np.asarray(c)
+            c[np.diag_indices_from(c)] += self.var_
+            return np.asarray(m)[:, None], c
         m, v, _ = self.engine.predict(points)
         # GPy's predict returns the predictive variance of a noisy observation (latent + noise)
         return np.asarray(m)[:, None], (np.asarray(v) + self.var_)[:, None]
+
+    def sample_sdfs(self, num_samples=1, full_cov=True, z=None, seed=None, jitter=1e-8):
+        """gpis.py:98-112: draws of the SDF over the whole grid from the posterior, one array of
+        shape dims per sample (C order, like grid_pts_).  GPy's posterior_samples (not vendored,
+        version unpinned) is restated as the latent posterior + a diagonal `jitter`; the draws z
+        [num_samples, prod(dims)] may be given, else they come from torch's generator.  full_cov is
+        accepted and ignored, as in the reference (gpis.py:108 never reads it)."""
+        import torch
+        n = self.grid_pts_.shape[0]
+        if z is None:
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(0 if seed is None else int(seed))
+            z = torch.randn((int(num_samples), n), dtype=torch.float64, device="cuda", generator=gen)
+        samples, _ = self.engine.sample_shapes(self.grid_pts_, z, use_derivative=False, jitter=jitter)
+        if torch.is_tensor(samples):
+            samples = samples.cpu().numpy()
+        return [s.reshape(self.dims_) for s in samples]
 
     def mean_sdf(self):
         return self.mean_pred_.reshape(self.dims_)

@@ -165,6 +165,31 @@ gpis_status gpis_fit(gpis_handle h, const double* pts, const double* tsdf, const
 gpis_status gpis_predict(gpis_handle h, const double* query, int64_t nq, double* mean, double* var,
                          double* normals, void* stream);
 
+/* gp_mean.m:1-12 and gp_cov.m:1-21 IN FULL (the matrix, not its diagonal) at nq points, SoA query.
+ * Values are ordered like the reference's joint vector, dimension-major: value c = b*nq + q is
+ * f(x_q) for b = 0 and d_b f(x_q) for b = 1..D (se_cov_derivative.m block layout); nv = nq values
+ * when use_derivative == 0, nq*(D+1) otherwise.  mean[nv], cov[row*ldc + col] (ldc >= nv),
+ * symmetrised as gp_cov.m:19-20 does, latent (beta = 0 on K**, gp_cov.m:6).  Either output may be
+ * NULL.  nq <= 65535. */
+gpis_status gpis_posterior_cov(gpis_handle h, const double* query, int64_t nq, int32_t use_derivative,
+                               double* mean, double* cov, int64_t ldc, void* stream);
+
+/* mc_sampling/sample_shapes.m:10-31 (mvnrnd + mvnpdf on MEAN, COV + jitter I) and
+ * Gpis3D.sample_sdfs (src/grasp_selection/gpis.py:98-112) at nq points:
+ *   samples[s*nv + c] = MEAN[c] + sum_k z[s*nv + k] T[k][c],   T'T = COV + jitter I (T upper),
+ *   logpdf[s] = -|z_s|^2/2 - sum_k log T[k][k] - nv/2 log(2 pi)   (the reference's pdfs = exp(logpdf)).
+ * z holds the standard-normal draws, one sample per row ([num_samples][nv]); the caller supplies them
+ * so that runs are reproducible (MATLAB's randn stream is not).  The reference uses jitter = 1e-12
+ * (sample_shapes.m:20).  logpdf may be NULL; chol (NULL or [nv][ldt], ldt >= nv) receives T.
+ * num_samples may be 0 (factor only).  GPIS_ERR_NOT_PD when a pivot is not positive: raise jitter
+ * (mvnrnd falls back to an eigendecomposition there; this engine reports it instead). */
+gpis_status gpis_sample_shapes(gpis_handle h, const double* query, int64_t nq, int32_t use_derivative,
+                               int32_t num_samples, const double* z, double jitter, double* samples,
+                               double* logpdf, double* chol, int64_t ldt, void* stream);
+/* Device time (CUDA events on the call's stream), ms, of the last gpis_posterior_cov /
+ * gpis_sample_shapes: mean + covariance build, Cholesky, draws.  Any pointer may be NULL. */
+gpis_status gpis_get_sampling_timing(gpis_handle h, double* cov_ms, double* chol_ms, double* draw_ms);
+
 /* Level-set state of the candidates after selection: last ambiguity each candidate was
  * scored with, and the high / low masks (straddle.m:121-125; ClassificationBuffers). */
 gpis_status gpis_get_levelset(gpis_handle h, double* ambiguity, uint8_t* high, uint8_t* low,

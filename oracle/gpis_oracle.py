@@ -218,6 +218,46 @@ def evaluate_errors(predicted, true, K):
 
 
 # --------------------------------------------------------------------------
+# posterior shape sampling  (mc_sampling/sample_shapes.m)
+# --------------------------------------------------------------------------
+def sample_grid_points(grid_dim, resolution=1):
+    """sample_shapes.m:10-11: [X(:) Y(:)] of meshgrid(1:res:g, 1:res:g)."""
+    ax = np.arange(1, grid_dim + 1, resolution, dtype=np.float64)
+    X, Y = np.meshgrid(ax, ax)
+    return np.stack([X.reshape(-1, order="F"), Y.reshape(-1, order="F")], axis=1)
+
+
+def sample_from_posterior(mean, cov, z, jitter=1e-12):
+    """mvnrnd(MEAN, COV + 1e-12 I, n) and mvnpdf of the draws (sample_shapes.m:20,31) with the
+    standard-normal draws ``z`` [n x d] made explicit (MATLAB's randn stream is not
+    reproducible outside MATLAB).  mvnrnd (Statistics Toolbox, not vendored; restated from its
+    documented algorithm) forms T = cholcov(Sigma), T'T = Sigma, and returns z T + mu; mvnpdf
+    evaluates -(1/2)|X0 / T|^2 - sum(log diag T) - d/2 log(2 pi) with X0 = X - mu, i.e. |z|^2 for
+    a draw generated this way.  cholcov's eigen-decomposition fallback for matrices chol()
+    rejects is NOT restated: LinAlgError propagates.  Returns (samples [n x d], logpdf [n], T)."""
+    mean = np.asarray(mean, np.float64).reshape(-1)
+    z = np.atleast_2d(np.asarray(z, np.float64))
+    d = mean.shape[0]
+    T = sla.cholesky(np.asarray(cov, np.float64) + jitter * np.eye(d), lower=False)
+    samples = z @ T + mean[None, :]
+    logpdf = -0.5 * np.sum(z * z, axis=1) - np.sum(np.log(np.diag(T))) - 0.5 * d * np.log(2.0 * np.pi)
+    return samples, logpdf, T
+
+
+def sample_shapes(model, grid_dim, z, resolution=1, jitter=1e-12):
+    """matlab/mc_sampling/sample_shapes.m:1-33.  ``z`` [numSamples x 3 P] replaces randn.
+    Returns (list of {tsdf [P], normals [P x 2]}, logpdf [numSamples]); the reference's ``pdfs``
+    is exp(logpdf) (all +inf in every stored constructionResults)."""
+    pts = sample_grid_points(grid_dim, resolution)
+    P = pts.shape[0]
+    MEAN, _, Kxxp = gp_mean(model, pts, True)                            # :15
+    COV = gp_cov(model, pts, Kxxp, True)                                 # :14
+    samples, logpdf, _ = sample_from_posterior(MEAN, COV, z, jitter)     # :20
+    shapes = [{"tsdf": s[:P].copy(), "normals": s[P:].reshape(P, 2, order="F")} for s in samples]  # :25-29
+    return shapes, logpdf
+
+
+# --------------------------------------------------------------------------
 # selection  (select_active_set_straddle.m)
 # --------------------------------------------------------------------------
 def _argmax_lowest(score):

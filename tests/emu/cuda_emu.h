@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE ONLY -- a CPU emulation of the CUDA execution model, just enough of it to run the
+// kernels and launch sequences of gpis_b200/csrc/gpis_sample.cuh under g++ (-DGPIS_EMULATE) so that their
+// indexing and pointer arithmetic are checked where there is no GPU.  One OS thread per CUDA thread,
+// thread blocks one after another, __syncthreads() = a std::barrier, __shared__ = a function-static
+// array, mma.sync.m8n8k4.f64 = a warp-wide exchange through a staging box.  Nothing under gpis_b200/
+// uses this; the shipped library is compiled by nvcc without GPIS_EMULATE and has no CPU path.
+#pragma once
+#include <barrier>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __shared__ static
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+constexpr int cudaSuccess = 0;
+
+namespace emu {
+struct WarpBox {
+  std::barrier<> bar{32};
+  double a[32], b[32];
+};
+inline thread_local uint3 t_idx, b_idx;
+inline thread_local WarpBox* my_warp;
+inline thread_local int my_lane;
+inline dim3 g_dim, b_dim;
+inline std::barrier<>* cta_bar;
+
+template <class F>
+void launch(dim3 grid, dim3 block, F body) {
+  const unsigned nth = block.x * block.y * block.z;
+  g_dim = grid;
+  b_dim = block;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::barrier<> bar(nth);
+        cta_bar = &bar;
+        std::vector<std::unique_ptr<WarpBox>> warps;
+        for (unsigned w = 0; w < (nth + 31) / 32; ++w) warps.emplace_back(new WarpBox);
+        std::vector<std::thread> th;
+        th.reserve(nth);
+        for (unsigned t = 0; t < nth; ++t)
+          th.emplace_back([&, t]() {
+            t_idx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            b_idx = uint3{bx, by, bz};
+            my_warp = warps[t / 32].get();
+            my_lane = (int)(t % 32);
+            body();
+            bar.arrive_and_drop();          // a thread that returned no longer takes part in barriers
+          });
+        for (auto& x : th) x.join();
+      }
+}
+}  // namespace emu
+
+#define threadIdx emu::t_idx
+#define blockIdx emu::b_idx
+#define blockDim emu::b_dim
+#define gridDim emu::g_dim
+
+inline void __syncthreads() { emu::cta_bar->arrive_and_wait(); }
+inline int atomicCAS(int* p, int cmp, int val) { return __sync_val_compare_and_swap(p, cmp, val); }
+
+namespace gpis {
+// mma.sync.aligned.m8n8k4.row.col.f64: lane l supplies A[l/4][l%4] and B[l%4][l/4] and owns
+// D[l/4][2*(l%4) + {0,1}] (PTX ISA, "Matrix fragments for mma.m8n8k4 with .f64").
+inline void s_dmma(double& c0, double& c1, double a, double b) {
+  emu::WarpBox* w = emu::my_warp;
+  const int l = emu::my_lane;
+  w->a[l] = a;
+  w->b[l] = b;
+  w->bar.arrive_and_wait();
+  const int m = l >> 2, n = 2 * (l & 3);
+  for (int k = 0; k < 4; ++k) {
+    c0 = std::fma(w->a[m * 4 + k], w->b[n * 4 + k], c0);
+    c1 = std::fma(w->a[m * 4 + k], w->b[(n + 1) * 4 + k], c1);
+  }
+  w->bar.arrive_and_wait();
+}
+}  // namespace gpis

@@ -1,0 +1,142 @@
+"""The posterior-covariance / shape-sampling kernels and launch sequences of
+gpis_b200/csrc/gpis_sample.cuh, run on the CPU emulation of the CUDA execution model in tests/emu
+(g++ -DGPIS_EMULATE) and compared with the oracle's restatement of gp_mean.m, gp_cov.m and
+mc_sampling/sample_shapes.m.  This checks indexing and launch arithmetic where there is no GPU;
+tests/test_gpu_sampling.py is the same comparison through the C ABI on the device."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from conftest import ROOT, golden_model, load_golden
+from oracle import gpis_oracle as O
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_SO = os.path.join(ROOT, "build", "libemu_sample.so")
+EMU_DEPS = [os.path.join(EMU_DIR, "emu_sample.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_sample.cuh"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in EMU_DEPS):
+        subprocess.run(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
+                        "-I" + EMU_DIR, "-o", EMU_SO, EMU_DEPS[0]], check=True)
+    lib = C.CDLL(EMU_SO)
+    vp = C.c_void_p
+    lib.emu_sample_shapes.restype = C.c_int
+    lib.emu_sample_shapes.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_longlong, vp, vp, C.c_longlong,
+                                      C.c_int, C.c_double, C.c_double, vp, C.c_double, C.c_int, vp, C.c_double,
+                                      vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
+    return lib
+
+
+def run_emu(lib, gp, query, deriv, z, jitter):
+    """Feed the emulated device code what gpis_capi.cu feeds the real one: active points (SoA),
+    Wt[k][row] = (L^-1)[row][k] zero-padded, alpha, the query (SoA)."""
+    D, R, m = gp.D, gp.r, gp.m
+    ldw = (R + 255) // 256 * 256
+    W = sla.solve_triangular(gp.L[:R, :R], np.eye(R), lower=True) if R else np.zeros((0, 0))
+    Wt = np.zeros((max(R, 1), ldw))
+    Wt[:R, :R] = W.T
+    alpha = np.ascontiguousarray(gp.alpha()) if R else np.zeros(1)
+    AX = np.ascontiguousarray(gp.X[:max(m, 1)].T)
+    q = np.ascontiguousarray(np.asarray(query, np.float64).T)
+    nq = q.shape[1]
+    nv = nq * (D + 1 if deriv else 1)
+    z = np.ascontiguousarray(np.asarray(z, np.float64).reshape(-1, nv))
+    ns = z.shape[0]
+    mean, cov, chol = np.empty(nv), np.empty((nv, nv)), np.empty((nv, nv))
+    samples, logpdf = np.empty((ns, nv)), np.empty(ns)
+    mw = np.ascontiguousarray(gp.hm[:D])
+    launches = C.c_longlong()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.emu_sample_shapes(D, int(gp.use_grad), R, p(AX), AX.shape[1], p(Wt), ldw, p(alpha), p(q), nq, int(deriv),
+                               float(np.sqrt(gp.ell2)), gp.sf2, p(mw), float(gp.hm[D]), ns, p(z), jitter,
+                               p(mean), p(cov), p(chol), p(samples), p(logpdf), C.byref(launches))
+    return rc, mean, cov, chol, samples, logpdf, launches.value
+
+
+def incremental(hyp, X, y, dy, beta, use_grad):
+    gp = O.IncrementalGP(np.zeros((0, X.shape[1])), hyp, max(X.shape[0], 1), use_grad)
+    for i in range(X.shape[0]):
+        gp.append(X[i], y[i], dy[i] if use_grad else None, beta[i] if np.ndim(beta) else beta)
+    return gp
+
+
+def test_emulated_kernels_match_sample_shapes_on_the_loofa_model(emu):
+    """2-D model with gradient rows (the reference's stored loofa gpModel), derivative queries on the
+    sample_shapes.m grid at resolution 3: 81 points, 243 values -> four 64-blocks with padding."""
+    g = load_golden("loofa")
+    hyp, X, y, dy, beta = golden_model(g)
+    model = O.create_gpis(X, y, dy, beta, hyp)
+    gp = incremental(hyp, X, y, dy, beta, True)
+    pts = O.sample_grid_points(25, 3)
+    z = np.random.default_rng(3).standard_normal((3, 3 * len(pts)))
+    MEAN, _, Kxxp = O.gp_mean(model, pts, True)
+    COV = O.gp_cov(model, pts, Kxxp, True)
+    shapes, lp = O.sample_shapes(model, 25, z, resolution=3, jitter=1e-12)
+    rc, mean, cov, chol, samples, logpdf, launches = run_emu(emu, gp, pts, True, z, 1e-12)
+    assert rc == 0
+    assert np.max(np.abs(mean - MEAN)) < 1e-11
+    assert np.max(np.abs(cov - COV)) < 1e-12 and np.array_equal(cov, cov.T)
+    assert np.all(np.tril(chol, -1) == 0.0)
+    assert np.max(np.abs(chol.T @ chol - (COV + 1e-12 * np.eye(len(MEAN))))) < 1e-12
+    ref = np.stack([np.concatenate([s["tsdf"], s["normals"].reshape(-1, order="F")]) for s in shapes])
+    assert np.max(np.abs(samples - ref)) < 1e-7
+    assert np.max(np.abs(logpdf - lp)) < 1e-6 * np.max(np.abs(lp))
+    nblk = (len(MEAN) + 63) // 64
+    assert launches == 3 + 2 + 1 + 1 + nblk + 2 * (nblk - 1) + 1 + 4      # the count gpis_capi.cu reports
+
+
+def test_emulated_kernels_3d_function_only_and_empty_model(emu):
+    """3-D function-only model (Gpis3D.sample_sdfs shape): no derivative values, 5^3 = 125 points."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 4, (40, 3))
+    y = np.linalg.norm(X - 2.0, axis=1) - 1.5
+    hyp = {"cov": np.array([np.log(1.3), np.log(0.9)]), "mean": np.array([0.01, -0.02, 0.03, 0.2]), "lik": np.log(0.1)}
+    model = O.create_gpis(X, y, None, None, hyp)
+    gp = incremental(hyp, X, y, None, np.exp(2 * hyp["lik"]), False)
+    ax = np.arange(5.0)
+    pts = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    z = rng.standard_normal((2, 125))
+    MEAN, _, Kxxp = O.gp_mean(model, pts, False)
+    COV = O.gp_cov(model, pts, Kxxp, False)
+    ref, lp, T = O.sample_from_posterior(MEAN, COV, z, 1e-10)
+    rc, mean, cov, chol, samples, logpdf, _ = run_emu(emu, gp, pts, False, z, 1e-10)
+    assert rc == 0
+    assert np.max(np.abs(mean - MEAN)) < 1e-12 and np.max(np.abs(cov - COV)) < 1e-12
+    assert np.max(np.abs(samples - ref)) < 1e-8 and np.max(np.abs(logpdf - lp)) < 1e-6 * np.max(np.abs(lp))
+    # derivative queries against a function-only model (rows have no gradient kind)
+    pts2 = pts[::7]
+    rc, mean, cov, chol, _, _, _ = run_emu(emu, gp, pts2, True, np.zeros((0, 4 * len(pts2))), 1e-10)
+    assert rc == 0
+    Kss = O.se_cov_derivative(hyp["cov"], 0.0, pts2)
+    Ks = O.se_cov_derivative(hyp["cov"], 0.0, X, pts2)[:len(X)]           # function rows of the training block
+    Q = model["Q"]
+    S = Kss - Ks.T @ np.linalg.solve(Q, Ks)
+    assert np.max(np.abs(cov - (S + S.T) / 2)) < 1e-11
+    assert np.max(np.abs(chol.T @ chol - cov - 1e-10 * np.eye(len(cov)))) < 1e-12
+    # a model with no rows: prior mean and prior covariance
+    empty = O.IncrementalGP(np.zeros((0, 3)), hyp, 1, False)
+    rc, mean, cov, chol, _, _, _ = run_emu(emu, empty, pts2, False, np.zeros((0, len(pts2))), 1e-10)
+    assert rc == 0
+    assert np.allclose(mean, pts2 @ hyp["mean"][:3] + hyp["mean"][3], rtol=0, atol=1e-15)
+    assert np.max(np.abs(cov - O.cov_se_iso(hyp["cov"], pts2))) < 1e-15
+
+
+def test_emulated_cholesky_reports_a_bad_pivot(emu):
+    """Duplicate query points make COV exactly singular; without jitter the second copy's pivot is <= 0
+    (or rounds to a tiny positive number) and the status must carry its index instead of NaNs."""
+    hyp = {"cov": np.array([0.0, 0.0]), "mean": np.zeros(3), "lik": np.log(0.1)}
+    gp = O.IncrementalGP(np.zeros((0, 2)), hyp, 1, False)
+    pts = np.array([[0.0, 0.0], [1.0, 0.5], [0.0, 0.0], [2.0, 2.0]])
+    rc, *_ = run_emu(emu, gp, pts, False, np.zeros((0, 4)), 0.0)
+    assert rc == 3                                                            # 1-based index of the pivot
+    rc, _, cov, chol, *_ = run_emu(emu, gp, pts, False, np.zeros((0, 4)), 1e-9)
+    assert rc == 0 and np.max(np.abs(chol.T @ chol - cov - 1e-9 * np.eye(4))) < 1e-15
