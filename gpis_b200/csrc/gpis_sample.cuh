@@ -382,20 +382,37 @@ inline void posterior_full_device(int D, bool grad, const FullCovParams& F, cons
 
 // Blocked right-looking upper Cholesky of blockdiag(COV + jitter I, I) in place: T'T = COV + jitter I in
 // the upper triangle, zeros below.  *d_err (zeroed by the caller) receives the first bad pivot.
+// Two levels of blocking: 64-wide block rows (diagonal block in one CTA, block row by forward
+// substitution) update only the rest of their 256-wide outer block row; the trailing matrix is updated
+// once per outer block with K = 256, which divides its HBM traffic (the cost that bounds a K = 64 update)
+// by four.
+constexpr int CHO = 256;           // outer block
 inline void chol_upper_device(double* S, long long npad, long long nv, double jitter, int* d_err, cudaStream_t s,
                               long long* launches) {
   GPIS_LAUNCH(k_prepare_diag, dim3((unsigned)((npad + 255) / 256)), dim3(256), s, S, npad, (int)nv, (int)npad, jitter);
   *launches += 1;
-  for (long long o = 0; o < npad; o += CHB) {
-    GPIS_LAUNCH(k_chol_diag, dim3(1), dim3(256), s, S, npad, (int)o, d_err);
-    *launches += 1;
-    const long long rest = npad - o - CHB;
-    if (rest > 0) {
+  for (long long O = 0; O < npad; O += CHO) {
+    const long long oe = (O + CHO < npad) ? O + CHO : npad;
+    for (long long o = O; o < oe; o += CHB) {
+      GPIS_LAUNCH(k_chol_diag, dim3(1), dim3(256), s, S, npad, (int)o, d_err);
+      *launches += 1;
+      const long long rest = npad - o - CHB;
+      if (rest <= 0) continue;
       GPIS_LAUNCH(k_chol_panel, dim3((unsigned)((rest + 127) / 128)), dim3(128), s, S, npad, (int)o, (int)npad);
-      const double* pan = S + o * npad + o + CHB;
-      launch_gemm_tn(pan, npad, pan, npad, S + (o + CHB) * npad + o + CHB, npad, (int)rest, (int)rest, CHB, -1.0, 1.0,
-                     1, s);
-      *launches += 2;
+      *launches += 1;
+      const long long mi = oe - (o + CHB);         // rows of this outer block row still to be factored
+      if (mi > 0) {
+        const double* pan = S + o * npad + o + CHB;
+        launch_gemm_tn(pan, npad, pan, npad, S + (o + CHB) * npad + o + CHB, npad, (int)mi, (int)rest, CHB, -1.0, 1.0,
+                       1, s);
+        *launches += 1;
+      }
+    }
+    const long long rem = npad - oe;
+    if (rem > 0) {
+      const double* pan = S + O * npad + oe;       // rows O..oe of the factor, columns oe..npad
+      launch_gemm_tn(pan, npad, pan, npad, S + oe * npad + oe, npad, (int)rem, (int)rem, (int)(oe - O), -1.0, 1.0, 1, s);
+      *launches += 1;
     }
   }
   const unsigned t16 = (unsigned)((npad + 15) / 16);

@@ -41,3 +41,16 @@ extern "C" int emu_sample_shapes(int D, int grad, int R, const double* AX, int m
   }
   return 0;
 }
+
+// chol_upper_device alone on a given symmetric matrix A [n][n]: T (upper, T'T = A + jitter I) into T_out.
+extern "C" int emu_chol_upper(const double* A, long long n, double jitter, double* T_out, long long* launches) {
+  const long long npad = (n + CHB - 1) / CHB * CHB;
+  std::vector<double> S((size_t)npad * npad, 0.0);
+  for (long long i = 0; i < n; ++i) memcpy(S.data() + i * npad, A + i * n, sizeof(double) * n);
+  int err = 0;
+  *launches = 0;
+  chol_upper_device(S.data(), npad, n, jitter, &err, nullptr, launches);
+  if (err) return err;
+  for (long long i = 0; i < n; ++i) memcpy(T_out + i * n, S.data() + i * npad, sizeof(double) * n);
+  return 0;
+}

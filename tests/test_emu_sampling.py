@@ -33,6 +33,8 @@ def emu():
     lib.emu_sample_shapes.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.c_longlong, vp, vp, C.c_longlong,
                                       C.c_int, C.c_double, C.c_double, vp, C.c_double, C.c_int, vp, C.c_double,
                                       vp, vp, vp, vp, vp, C.POINTER(C.c_longlong)]
+    lib.emu_chol_upper.restype = C.c_int
+    lib.emu_chol_upper.argtypes = [vp, C.c_longlong, C.c_double, vp, C.POINTER(C.c_longlong)]
     return lib
 
 
@@ -60,6 +62,21 @@ def run_emu(lib, gp, query, deriv, z, jitter):
                                float(np.sqrt(gp.ell2)), gp.sf2, p(mw), float(gp.hm[D]), ns, p(z), jitter,
                                p(mean), p(cov), p(chol), p(samples), p(logpdf), C.byref(launches))
     return rc, mean, cov, chol, samples, logpdf, launches.value
+
+
+def chol_launches(nv, blk=64, outer=256):
+    """Launches of chol_upper_device: diagonal prep, per 64-block a diagonal kernel (+ block row
+    + update inside the 256-wide outer block), per outer block one trailing update, zeroing."""
+    npad = (nv + blk - 1) // blk * blk
+    n = 1
+    for O in range(0, npad, outer):
+        oe = min(O + outer, npad)
+        for o in range(O, oe, blk):
+            n += 1
+            if npad - o - blk > 0:
+                n += 1 + (1 if oe - o - blk > 0 else 0)
+        n += 1 if npad - oe > 0 else 0
+    return n + 1
 
 
 def incremental(hyp, X, y, dy, beta, use_grad):
@@ -90,8 +107,7 @@ def test_emulated_kernels_match_sample_shapes_on_the_loofa_model(emu):
     ref = np.stack([np.concatenate([s["tsdf"], s["normals"].reshape(-1, order="F")]) for s in shapes])
     assert np.max(np.abs(samples - ref)) < 1e-7
     assert np.max(np.abs(logpdf - lp)) < 1e-6 * np.max(np.abs(lp))
-    nblk = (len(MEAN) + 63) // 64
-    assert launches == 3 + 2 + 1 + 1 + nblk + 2 * (nblk - 1) + 1 + 4      # the count gpis_capi.cu reports
+    assert launches == 3 + 2 + 1 + chol_launches(len(MEAN)) + 4           # the count gpis_capi.cu reports
 
 
 def test_emulated_kernels_3d_function_only_and_empty_model(emu):
@@ -140,3 +156,21 @@ def test_emulated_cholesky_reports_a_bad_pivot(emu):
     assert rc == 3                                                            # 1-based index of the pivot
     rc, _, cov, chol, *_ = run_emu(emu, gp, pts, False, np.zeros((0, 4)), 1e-9)
     assert rc == 0 and np.max(np.abs(chol.T @ chol - cov - 1e-9 * np.eye(4))) < 1e-15
+
+
+def test_emulated_two_level_cholesky_across_outer_blocks(emu):
+    """330 values -> 384 padded: the first 256-wide outer block updates the trailing 128 x 128 with
+    K = 256, the second one is factored by 64-blocks; compared with LAPACK and by reconstruction."""
+    rng = np.random.default_rng(8)
+    n = 330
+    B = rng.standard_normal((n, 40))
+    A = B @ B.T / 40.0 + np.diag(rng.uniform(0.01, 0.1, n))
+    A = (A + A.T) / 2
+    T = np.empty((n, n))
+    launches = C.c_longlong()
+    rc = emu.emu_chol_upper(A.ctypes.data_as(C.c_void_p), n, 1e-9, T.ctypes.data_as(C.c_void_p), C.byref(launches))
+    assert rc == 0 and launches.value == chol_launches(n)
+    ref = sla.cholesky(A + 1e-9 * np.eye(n), lower=False)
+    assert np.all(np.tril(T, -1) == 0.0)
+    assert np.max(np.abs(T - ref)) < 1e-12
+    assert np.max(np.abs(T.T @ T - A - 1e-9 * np.eye(n))) < 1e-14
