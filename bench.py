@@ -304,6 +304,14 @@ def run_ours(args):
         eng, sel = eng_fp64, sel_fp64
         h_mean.copy_(ref_mean); h_var.copy_(ref_var)
         eng2.close()
+    # (5) optional, one GPU: posterior shape draws (mc_sampling/sample_shapes.m, Gpis3D.sample_sdfs) over a
+    #     coarse lattice from the model just selected -- reported beside the headline, never part of it
+    sampling_extra = None
+    if world == 1 and not args.no_sampling:
+        try:
+            sampling_extra = sampling_block(eng, g, dev)
+        except Exception as e:          # an extra must never cost the bench line
+            sampling_extra = {"error": repr(e)}
     # checksum of the posterior grid (sum of mean and of variance over all lattice points)
     cs = torch.stack([h_mean.sum(), h_var.sum()]).to(dev)
     if world > 1:
@@ -391,11 +399,51 @@ def run_ours(args):
     }
     if tf32_extra is not None:
         out["tf32_mode"] = tf32_extra
+    if sampling_extra is not None:
+        out["shape_sampling"] = sampling_extra
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, pts, tsdf, first)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sampling_block(eng, g, dev, per_axis=24, n_samples=8, jitter=1e-8):
+    """gpis_sample_shapes on a per_axis^3 sub-lattice of the g^3 grid from the engine's current model:
+    full posterior covariance (fp64 DMMA GEMMs), blocked Cholesky, draws.  Device times are CUDA
+    events inside the C ABI; e2e is the host-side call (device tensors in and out)."""
+    import torch
+    ax = (np.arange(per_axis) + 0.5) * (g / per_axis) - 0.5
+    q = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    qd = torch.as_tensor(q, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0)
+    z = torch.randn((n_samples, q.shape[0]), dtype=torch.float64, device=dev, generator=gen)
+    best = None
+    for _ in range(2):                       # first call warms up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        samples, logpdf = eng.sample_shapes(qd, z, jitter=jitter)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        best = dict(eng.sampling_timing(), e2e_ms=wall)
+    mu, var, _ = eng.predict(qd)
+    mean, _ = eng.posterior_cov(qd, want_cov=False)
+    _, n_model = eng.active()
+    R, nv = int(n_model), int(q.shape[0])
+    fp64_peak = 37.2
+    try:
+        fp64_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json"))).get("dmma_m8n8k4_tflops", 37.2))
+    except Exception:
+        pass
+    chol_tf = nv ** 3 / 3.0 / best["chol_ms"] * 1e-9
+    cov_tf = (2.0 * R * R * nv + 2.0 * nv * nv * R) / best["cov_ms"] * 1e-9
+    return {"workload": "%d posterior draws over a %d^3 sub-lattice (%d values) from the %d-point model of the selection" % (n_samples, per_axis, nv, R),
+            "cov_ms": best["cov_ms"], "chol_ms": best["chol_ms"], "draw_ms": best["draw_ms"], "e2e_ms": best["e2e_ms"],
+            "cov_tflops": cov_tf, "chol_tflops": chol_tf, "chol_frac_of_fp64_peak": chol_tf / fp64_peak,
+            "finite": bool(torch.isfinite(samples).all() and torch.isfinite(logpdf).all()),
+            "max_abs_mean_vs_predict": float((mean - mu).abs().max()), "jitter": jitter, "dtype": "f64",
+            "note": "gpis_sample_shapes: K**, K*, V = W K*, COV = K** - V'V, blocked upper Cholesky, MEAN + z T; fp64 DMMA GEMM k_gemm_tn_f64"}
 
 
 def ncu_traffic(name):
@@ -452,6 +500,7 @@ def main():
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode measurement")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the extra shape-sampling measurement")
     ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")

@@ -236,45 +236,74 @@ __global__ void __launch_bounds__(256) k_prepare_diag(double* S, long long ld, i
 constexpr int CHB = 64;            // Cholesky block
 constexpr int CHLD = CHB + 1;
 
-// Upper Cholesky (T'T = S) of the 64 x 64 diagonal block at offset o, in shared memory, written back to
-// the upper triangle.  A non-positive pivot records its (1-based) global index in *err.
+// Upper Cholesky (T'T = S) of the 64 x 64 diagonal block at offset o.  The block lives in registers:
+// thread (ti, tj) of a 16 x 16 arrangement owns the 4 x 4 sub-block at rows 4ti.., columns 4tj.. (threads
+// below the diagonal idle).  Per step k the owners of row k publish it through a double-buffered
+// shared row, everyone scales what it needs by 1/sqrt(pivot) and applies the rank-1 update to its own
+// registers: one barrier per step.  A non-positive pivot records its (1-based) global index in *err.
 __global__ void __launch_bounds__(256) k_chol_diag(double* S, long long ld, int o, int* err) {
-  __shared__ double T[CHB * CHLD];
-  const int tid = threadIdx.x;
-  for (int e = tid; e < CHB * CHB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    T[i * CHLD + j] = (j >= i) ? S[(long long)(o + i) * ld + o + j] : 0.0;
-  }
-  __syncthreads();
+  __shared__ double rowbuf[2][CHB];
+  const int tid = threadIdx.x, ti = tid >> 4, tj = tid & 15;
+  const bool mine = tj >= ti;
+  double a[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a[r][c] = mine ? S[(long long)(o + 4 * ti + r) * ld + o + 4 * tj + c] : 0.0;
   for (int k = 0; k < CHB; ++k) {
-    const double piv = T[k * CHLD + k];
+    const int kb = k >> 2, kr = k & 3;
+    double* rb = rowbuf[k & 1];
+    if (ti == kb && mine) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (r == kr) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rb[4 * tj + c] = a[r][c];
+        }
+    }
+    __syncthreads();
+    const double piv = rb[k];
     const double dg = sqrt(piv);
     const double inv = 1.0 / dg;
     if (!(piv > 0.0) && tid == 0) atomicCAS(err, 0, o + k + 1);
-    __syncthreads();                                   // everyone has read the pivot
-    for (int j = k + tid; j < CHB; j += 256) T[k * CHLD + j] = (j == k) ? dg : T[k * CHLD + j] * inv;
-    __syncthreads();
-    for (int e = tid; e < CHB * CHB; e += 256) {
-      const int i = e >> 6, j = e & 63;
-      if (i > k && j >= i) T[i * CHLD + j] -= T[k * CHLD + i] * T[k * CHLD + j];
-    }
-    __syncthreads();
+    if (!mine) continue;                                  // idle threads only keep the barrier count
+    double ri[4], cj[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ri[r] = rb[4 * ti + r] * inv;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cj[c] = rb[4 * tj + c] * inv;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * ti + r, j = 4 * tj + c;
+        if (i == k && j >= k) a[r][c] = (j == k) ? dg : cj[c];          // the finished row k of the factor
+        else if (i > k && j >= i) a[r][c] -= ri[r] * cj[c];
+      }
   }
-  for (int e = tid; e < CHB * CHB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    if (j >= i) S[(long long)(o + i) * ld + o + j] = T[i * CHLD + j];
+  if (mine) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (4 * tj + c >= 4 * ti + r) S[(long long)(o + 4 * ti + r) * ld + o + 4 * tj + c] = a[r][c];
   }
 }
 
 // Block row of the factor right of the diagonal block: T_jj' X = S[o:o+64, o+64:n], one thread per
-// column (forward substitution in registers, the diagonal block broadcast from shared memory).
+// column holding its 64 entries in registers.  Column-oriented forward substitution: once x[k] is final
+// (times the reciprocal pivot) it is eliminated from all later entries -- 63-k independent FMAs per step,
+// the diagonal block's row k broadcast from shared memory.
 __global__ void __launch_bounds__(128) k_chol_panel(double* S, long long ld, int o, int n) {
   __shared__ double T[CHB * CHLD];
+  __shared__ double rinv[CHB];
   const int tid = threadIdx.x;
   for (int e = tid; e < CHB * CHB; e += 128) {
     const int i = e >> 6, j = e & 63;
-    T[i * CHLD + j] = S[(long long)(o + i) * ld + o + j];     // only t <= k entries are read below
+    T[i * CHLD + j] = S[(long long)(o + i) * ld + o + j];     // only j >= i entries are read below
   }
+  __syncthreads();
+  if (tid < CHB) rinv[tid] = 1.0 / T[tid * CHLD + tid];
   __syncthreads();
   const long long m = (long long)o + CHB + blockIdx.x * 128LL + tid;
   if (m >= n) return;
@@ -283,10 +312,9 @@ __global__ void __launch_bounds__(128) k_chol_panel(double* S, long long ld, int
   for (int k = 0; k < CHB; ++k) x[k] = S[(long long)(o + k) * ld + m];
 #pragma unroll
   for (int k = 0; k < CHB; ++k) {
-    double s = x[k];
+    x[k] *= rinv[k];
 #pragma unroll
-    for (int t = 0; t < k; ++t) s -= T[t * CHLD + k] * x[t];
-    x[k] = s / T[k * CHLD + k];
+    for (int j = k + 1; j < CHB; ++j) x[j] -= T[k * CHLD + j] * x[k];
   }
 #pragma unroll
   for (int k = 0; k < CHB; ++k) S[(long long)(o + k) * ld + m] = x[k];

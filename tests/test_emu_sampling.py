@@ -87,10 +87,12 @@ def incremental(hyp, X, y, dy, beta, use_grad):
 
 
 def test_emulated_kernels_match_sample_shapes_on_the_loofa_model(emu):
-    """2-D model with gradient rows (the reference's stored loofa gpModel), derivative queries on the
+    """2-D model with gradient rows (a third of the reference's stored loofa gpModel), derivative queries on the
     sample_shapes.m grid at resolution 3: 81 points, 243 values -> four 64-blocks with padding."""
     g = load_golden("loofa")
     hyp, X, y, dy, beta = golden_model(g)
+    keep = np.arange(0, X.shape[0], 3)                      # 42 of the 126 points: the emulation is slow
+    X, y, dy, beta = X[keep], y[keep], dy[keep], beta[keep]
     model = O.create_gpis(X, y, dy, beta, hyp)
     gp = incremental(hyp, X, y, dy, beta, True)
     pts = O.sample_grid_points(25, 3)
