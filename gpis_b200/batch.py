@@ -31,16 +31,10 @@ def superellipsoid_tsdf(g, seed, trunc=3.0, jitter=1e-3):
     return np.clip(sd / trunc, -1, 1) + jitter * rng.standard_normal(idx.shape[0])
 
 
-def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep_posterior=True, sm_limit="auto",
-                 **cfg):
+def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep_posterior=True, **cfg):
     """tsdfs: sequence of per-object TSDF arrays on the same lattice `dims` (x fastest).
     Returns a list (one entry per object handled by this rank) of
-    dict(object, ids, n_in_model[, mean, var]).
-
-    n_workers engines run side by side, each on its own stream.  sm_limit sizes every launch of an
-    engine for that many SMs ("auto": the device's SMs shared out among the workers; None: the whole
-    device per launch) so that the small kernels of different objects really overlap instead of
-    queueing behind each other's device-wide grids (GPIS_SM_LIMIT, read by gpis_create)."""
+    dict(object, ids, n_in_model[, mean, var])."""
     D = len(dims)
     n = int(np.prod(dims))
     mine = list(range(rank, len(tsdfs), world))
@@ -53,13 +47,6 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
     # kernels (read by gpis_create; see include/gpis_b200.h).
     prev = os.environ.get("GPIS_SOLVE_REGS")
     os.environ["GPIS_SOLVE_REGS"] = "1"
-    prev_lim = os.environ.get("GPIS_SM_LIMIT")
-    if sm_limit == "auto":
-        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count \
-            if torch is not None and torch.cuda.is_available() else 0
-        sm_limit = max(4, sms // n_workers) if sms else None
-    if sm_limit is not None:
-        os.environ["GPIS_SM_LIMIT"] = str(int(sm_limit))
 
     def work(w):
         try:
@@ -89,11 +76,6 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
         os.environ.pop("GPIS_SOLVE_REGS", None)
     else:
         os.environ["GPIS_SOLVE_REGS"] = prev
-    if sm_limit is not None:
-        if prev_lim is None:
-            os.environ.pop("GPIS_SM_LIMIT", None)
-        else:
-            os.environ["GPIS_SM_LIMIT"] = prev_lim
     if errors:
         raise errors[0]
     return results

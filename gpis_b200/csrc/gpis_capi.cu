@@ -48,10 +48,7 @@ struct gpis_engine {
   int inverse_rows = -1;        // rows Wt/alpha are valid for
   int upd_grid = 0;
   size_t upd_smem = 0;
-  cudaGraphExec_t step_graph = nullptr;      // one (append, update) pair
-  cudaGraphExec_t step_graph_n = nullptr;    // GRAPH_UNROLL pairs: one graph launch per GRAPH_UNROLL selection steps
-  EngineParams graph_params;                 // the kernel arguments the graphs were captured with
-  bool unroll_failed = false;
+  cudaGraphExec_t step_graph = nullptr;
   cudaStream_t graph_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double select_ms = 0.0, predict_ms = 0.0, update_ms = 0.0, append_ms = 0.0, main_ms = 0.0, epilogue_ms = 0.0;
@@ -85,14 +82,6 @@ gpis_status fail(gpis_engine* e, gpis_status s, const std::string& msg) {
       return fail(e, _e == cudaErrorMemoryAllocation ? GPIS_ERR_NOMEM : GPIS_ERR_CUDA,   \
                   std::string(#call) + ": " + cudaGetErrorString(_e));                   \
   } while (0)
-
-constexpr int GRAPH_UNROLL = 8;
-
-void drop_graphs(gpis_engine* e) {
-  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
-  if (e->step_graph_n) { cudaGraphExecDestroy(e->step_graph_n); e->step_graph_n = nullptr; }
-  e->unroll_failed = false;
-}
 
 template <class T>
 cudaError_t dalloc(gpis_engine* e, T** p, size_t n) {
@@ -189,26 +178,6 @@ gpis_status launch_update(gpis_engine* e, cudaStream_t s, cudaEvent_t mid = null
   return GPIS_OK;
 }
 
-// Capture `pairs` (append, update) steps into an executable graph (on a private capturing stream).
-bool capture_steps(gpis_engine* e, int pairs, cudaGraphExec_t* out) {
-  cudaStream_t cs = nullptr;
-  cudaGraph_t g = nullptr;
-  *out = nullptr;
-  if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
-  bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-  if (ok) {
-    const long long l0 = e->launches;
-    for (int p = 0; p < pairs && ok; ++p) ok = launch_append(e, cs, 0, 0) == GPIS_OK && launch_update(e, cs) == GPIS_OK;
-    e->launches = l0;
-    ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && ok && g;
-    if (ok) ok = cudaGraphInstantiate(out, g, 0) == cudaSuccess;
-    if (g) cudaGraphDestroy(g);
-  }
-  cudaStreamDestroy(cs);
-  if (!ok) { cudaGetLastError(); *out = nullptr; }
-  return ok;
-}
-
 gpis_status read_state(gpis_engine* e, cudaStream_t s) {
   CU(cudaMemcpyAsync(&e->host_state, e->P.st, sizeof(DevState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -293,12 +262,6 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     CU(cudaGetDeviceProperties(&prop, e->device));
     if (prop.major < 10) return fail(e, GPIS_ERR_NO_DEVICE, "device is not sm_100 class");
     e->num_sms = prop.multiProcessorCount;
-    // GPIS_SM_LIMIT=k sizes every launch of this handle for k SMs instead of the whole device, so that
-    // several handles' kernels run side by side (gpis_b200/batch.py: many small independent objects)
-    if (const char* lim = getenv("GPIS_SM_LIMIT")) {
-      const int k = atoi(lim);
-      if (k >= 1 && k < e->num_sms) e->num_sms = k;
-    }
     EngineParams& P = e->P;
     memset(&P, 0, sizeof(P));
     const long long N = cfg->num_candidates;
@@ -414,7 +377,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
 
 gpis_status gpis_destroy(gpis_handle e) {
   if (!e) return GPIS_ERR_INVALID;
-  drop_graphs(e);
+  if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev2) cudaEventDestroy(e->ev2);
@@ -451,6 +414,7 @@ gpis_status gpis_set_candidates(gpis_handle e, const double* pts, const double* 
   e->backend = 1;
   e->have_candidates = true;
   e->selecting = false;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return GPIS_OK;
 }
 
@@ -541,6 +505,7 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   e->backend = 2;
   e->have_candidates = true;
   e->selecting = false;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return GPIS_OK;
 }
 
@@ -663,6 +628,7 @@ gpis_status gpis_peer_import(gpis_handle e, const void* handles, int32_t same_pr
   CU(cudaMemcpy(P.peer_xchg, xp.data(), sizeof(double*) * P.world, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(P.peer_xflag, fp.data(), sizeof(unsigned long long*) * P.world, cudaMemcpyHostToDevice));
   P.peer_mode = 1;
+  if (e->step_graph) { cudaGraphExecDestroy(e->step_graph); e->step_graph = nullptr; }
   return GPIS_OK;
 }
 
@@ -678,14 +644,22 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   gpis_status rc = gpis_select_begin(e, first_local, stream);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
-  if (e->step_graph && memcmp(&e->graph_params, &e->P, sizeof(EngineParams)) != 0) drop_graphs(e);
-  if (iters > 0 && !e->profiling) {
-    // one (append, update) pair, and -- lazily, a handle that only runs short selections never pays for
-    // it -- GRAPH_UNROLL pairs back to back: every argument is constant, all state is on the device (a
-    // step that finds the selection finished does nothing)
-    if (!e->step_graph && capture_steps(e, 1, &e->step_graph)) e->graph_params = e->P;
-    if (e->step_graph && !e->step_graph_n && !e->unroll_failed && iters >= GRAPH_UNROLL)
-      e->unroll_failed = !capture_steps(e, GRAPH_UNROLL, &e->step_graph_n);
+  if (iters > 0 && !e->step_graph && !e->profiling) {
+    // capture one (append, update) pair; every argument is constant, all state is on the device
+    cudaStream_t cs = nullptr;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const long long l0 = e->launches;
+      ok = launch_append(e, cs, 0, 0) == GPIS_OK && launch_update(e, cs) == GPIS_OK;
+      e->launches = l0;
+      ok = (cudaStreamEndCapture(cs, &g) == cudaSuccess) && ok && g;
+      if (ok) ok = cudaGraphInstantiate(&e->step_graph, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaStreamDestroy(cs);
+    if (!ok) { cudaGetLastError(); e->step_graph = nullptr; }
   }
   const bool prof = e->profiling;
   if (prof) {
@@ -695,14 +669,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       e->prof_events.push_back(ev);
     }
   }
-  const int per_pair = e->backend == 2 ? ((e->onepass && e->solve_ring) ? 3 : (e->fused_solve || e->onepass) ? 4 : 5) : 2;
-  int it = 0;
-  if (!prof && e->step_graph_n)
-    for (; it + GRAPH_UNROLL <= iters; it += GRAPH_UNROLL) {
-      CU(cudaGraphLaunch(e->step_graph_n, s));
-      e->launches += (long long)per_pair * GRAPH_UNROLL;
-    }
-  for (; it < iters; ++it) {
+  for (int it = 0; it < iters; ++it) {
     if (prof) {
       CU(cudaEventRecord(e->prof_events[4 * it], s));
       rc = launch_append(e, s, 0, 0);
@@ -714,7 +681,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       CU(cudaEventRecord(e->prof_events[4 * it + 3], s));
     } else if (e->step_graph) {
       CU(cudaGraphLaunch(e->step_graph, s));
-      e->launches += per_pair;
+      e->launches += e->backend == 2 ? ((e->onepass && e->solve_ring) ? 3 : (e->fused_solve || e->onepass) ? 4 : 5) : 2;
     } else {
       rc = launch_append(e, s, 0, 0);
       if (rc != GPIS_OK) return rc;

@@ -18,23 +18,21 @@ ap.add_argument("--objects", type=int, default=512)
 ap.add_argument("--grid", type=int, default=32)
 ap.add_argument("--active", type=int, default=256)
 ap.add_argument("--workers", type=int, nargs="*", default=[8])
-ap.add_argument("--sm-limit", default="auto", help='SMs each engine sizes its launches for: "auto", "none" or a number')
 a = ap.parse_args()
-lim = None if a.sm_limit == "none" else ("auto" if a.sm_limit == "auto" else int(a.sm_limit))
 g = a.grid
 tsdfs = [superellipsoid_tsdf(g, k) for k in range(a.objects)]
 cfg = dict(ell=2.5, noise=0.05, level=0.0, eps=1e-2, beta=10.0)
 ref = None
 for workers in a.workers:
-    select_batch(tsdfs[:workers], (g, g, g), a.active, 3254, n_workers=workers, keep_posterior=False, sm_limit=lim, **cfg)   # warm-up
+    select_batch(tsdfs[:workers], (g, g, g), a.active, 3254, n_workers=workers, keep_posterior=False, **cfg)   # warm-up
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = select_batch(tsdfs, (g, g, g), a.active, 3254, n_workers=workers, sm_limit=lim, **cfg)
+    res = select_batch(tsdfs, (g, g, g), a.active, 3254, n_workers=workers, **cfg)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     crc = zlib.crc32(np.concatenate([np.asarray(r["ids"], np.int64) for r in res]).tobytes())
     ref = crc if ref is None else ref
     print(json.dumps({"config": f"{a.objects} x {g}^3 objects, {a.active}-pt active set each", "workers": workers,
-                      "sm_limit": a.sm_limit, "seconds": dt, "objects_per_s": a.objects / dt,
+                      "seconds": dt, "objects_per_s": a.objects / dt,
                       "pts_selected_per_s": sum(len(r["ids"]) for r in res) / dt, "ids_crc32": crc,
                       "same_picks_as_first_setting": crc == ref}), flush=True)

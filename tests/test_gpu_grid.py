@@ -207,18 +207,7 @@ def test_batch_of_independent_objects_matches_solo_runs(G):
         ids, nm = eng.active()
         mu, var = eng.candidate_posterior()
         assert np.array_equal(ids, res[k]["ids"]) and nm == res[k]["n_in_model"]
-        # each batch engine sizes its launches for a share of the SMs (GPIS_SM_LIMIT): the split-K and
-        # W-row partial sums are grouped differently from the solo run's, so equal to rounding, not bitwise
-        assert np.max(np.abs(mu - res[k]["mean"])) < 1e-11 and np.max(np.abs(var - res[k]["var"])) < 1e-11
-    # the whole device per launch (sm_limit=None) reproduces the solo runs bit for bit
-    res_full = select_batch(tsdfs[:6], (g, g, g), K, 3254 % g ** 3, n_workers=2, sm_limit=None, **cfg)
-    eng = G.GpisEngine(3, g ** 3, K, **cfg)
-    eng.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdfs[5])
-    eng.select(3254 % g ** 3, K)
-    mu, var = eng.candidate_posterior()
-    assert np.array_equal(mu, res_full[5]["mean"]) and np.array_equal(var, res_full[5]["var"])
-    # a handle reused for several objects keeps its captured step graphs (same lattice, same buffers)
-    assert res_full[4]["object"] == 4 and np.array_equal(res_full[4]["ids"], res[4]["ids"])
+        assert np.array_equal(mu, res[k]["mean"]) and np.array_equal(var, res[k]["var"])   # bit-identical
     # objects differ from each other
     assert not np.array_equal(res[0]["ids"], res[1]["ids"])
 
