@@ -19,7 +19,7 @@ SYMBOLS = [
     "gpis_select_end", "gpis_exchange_buffers", "gpis_get_active", "gpis_get_factor", "gpis_fit",
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
-    "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing",
+    "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing", "gpis_batch_select",
 ]
 
 
@@ -95,6 +95,8 @@ def load():
         "gpis_posterior_cov": [vp, dp, C.c_int64, C.c_int32, dp, dp, C.c_int64, vp],
         "gpis_sample_shapes": [vp, dp, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double, dp, dp, dp, C.c_int64, vp],
         "gpis_get_sampling_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
+        "gpis_batch_select": [C.POINTER(GpisConfig), vp, vp, vp, C.c_int32, dp, C.c_int64, C.c_int32, vp, vp, vp,
+                              dp, dp, u8p, C.POINTER(C.c_double), vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

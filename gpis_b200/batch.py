@@ -4,13 +4,19 @@ Objects are independent, so there is no collective and nothing to shard inside a
 each of `n_workers` host threads owns one engine on its own CUDA stream and works through its
 share of the objects (the C ABI releases the GIL for the duration of a call, the greedy loop of
 each object is a captured CUDA graph).  With N GPUs every rank takes objects rank::N ("replicas
-only" -- DESIGN.md section 6)."""
+only" -- DESIGN.md section 6).
+
+`select_batch_fused` is the object-batched form for small lattices (<= 32 per axis, <= 256 points,
+function values, fixed beta): ONE launch in which every thread block runs the whole selection of an
+object (gpis_batch_select, gpis_b200/csrc/gpis_batch.cuh)."""
+import ctypes as C
 import os
 import threading
 
 import numpy as np
 
-from .engine import GpisEngine
+from . import _lib
+from .engine import GpisEngine, _ptr, _stream
 
 try:
     import torch
@@ -87,3 +93,53 @@ class _Null:
 
     def __exit__(self, *a):
         return False
+
+
+def select_batch_fused(tsdfs, dims, K, first_index, rank=0, world=1, keep_posterior=True, *, ell, sf2=1.0,
+                       mean_w=None, mean_c=0.0, noise=0.01, level=0.0, eps=1e-2, beta=10.0,
+                       variance_mode=_lib.VAR_LATENT, device=-1):
+    """Same inputs and result structure as `select_batch` (list of dict(object, ids, n_in_model[, mean,
+    var, flags])), through gpis_batch_select: one kernel launch for this rank's share of the objects.
+    `tsdfs` may be a sequence of per-object arrays or one (n_objects, N) array (NumPy or torch CUDA).
+    The result's "device_ms" (on every entry) is the CUDA-event time of that launch."""
+    lib = _lib.load()
+    D = len(dims)
+    n = int(np.prod(dims))
+    mine = list(range(rank, len(tsdfs), world))
+    if not mine:
+        return []
+    on_dev = torch is not None and isinstance(tsdfs, torch.Tensor) and tsdfs.is_cuda
+    if on_dev:
+        t = tsdfs[mine].to(torch.float64).contiguous().reshape(len(mine), n)
+    else:
+        t = np.ascontiguousarray(np.stack([np.asarray(tsdfs[k], np.float64).reshape(-1) for k in mine]))
+    B = len(mine)
+    cfg = _lib.GpisConfig()
+    cfg.struct_size = C.sizeof(_lib.GpisConfig)
+    cfg.dim, cfg.num_candidates, cfg.max_active = D, n, int(K)
+    cfg.precision, cfg.beta_mode, cfg.variance_mode = _lib.PREC_FP64, _lib.BETA_FIXED, int(variance_mode)
+    cfg.world_size, cfg.device = 1, int(device)
+    cfg.ell, cfg.sf2 = float(ell), float(sf2)
+    mw = np.zeros(3) if mean_w is None else np.asarray(mean_w, np.float64).reshape(-1)
+    for d in range(D):
+        cfg.mean_w[d] = float(mw[d])
+    cfg.mean_c, cfg.noise = float(mean_c), float(noise)
+    cfg.level, cfg.eps, cfg.beta = float(level), float(eps), float(beta)
+    dims_a = np.ascontiguousarray(np.asarray(dims, np.int32))
+    ids = np.empty((B, int(K)), np.int64)
+    n_sel, n_model = np.empty(B, np.int32), np.empty(B, np.int32)
+    mean = var = flags = None
+    if keep_posterior:
+        mean, var, flags = np.empty((B, n)), np.empty((B, n)), np.empty((B, n), np.uint8)
+    ms = C.c_double(0.0)
+    st = lib.gpis_batch_select(C.byref(cfg), _ptr(dims_a), None, None, B, _ptr(t), int(first_index), int(K),
+                               _ptr(ids), _ptr(n_sel), _ptr(n_model), _ptr(mean), _ptr(var), _ptr(flags),
+                               C.byref(ms), _stream())
+    _lib.check(lib, None, st)
+    out = []
+    for i, k in enumerate(mine):
+        r = {"object": k, "ids": ids[i, :n_sel[i]].copy(), "n_in_model": int(n_model[i]), "device_ms": ms.value}
+        if keep_posterior:
+            r["mean"], r["var"], r["flags"] = mean[i], var[i], flags[i]
+        out.append(r)
+    return out

@@ -14,6 +14,7 @@
 #include "gpis_grid.cuh"
 #include "gpis_grid_tf32.cuh"
 #include "gpis_predict.cuh"
+#include "gpis_batch.cuh"
 #include "gpis_sample.cuh"
 #include "gpis_select.cuh"
 
@@ -1015,6 +1016,106 @@ gpis_status gpis_sample_shapes(gpis_handle e, const double* query, int64_t nq, i
   if (cudaEventElapsedTime(&ms, e->ev1, e->ev2) == cudaSuccess) e->chol_ms = ms;
   if (cudaEventElapsedTime(&ms, e->ev2, e->ev3) == cudaSuccess) e->draw_ms = ms;
   return GPIS_OK;
+}
+
+gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin, const double* spacing,
+                              int32_t n_objects, const double* tsdf, int64_t first_index, int32_t K, int64_t* ids,
+                              int32_t* n_selected, int32_t* n_in_model, double* mean, double* var, uint8_t* flags,
+                              double* device_ms, void* stream) {
+  if (!cfg || cfg->struct_size != (int32_t)sizeof(gpis_config) || !dims || !tsdf || !ids || !n_selected)
+    return GPIS_ERR_INVALID;
+  const int D = cfg->dim;
+  if (D < 2 || D > 3 || cfg->use_gradients || cfg->precision != GPIS_PREC_FP64 || cfg->beta_mode != GPIS_BETA_FIXED ||
+      cfg->world_size > 1)
+    return GPIS_ERR_INVALID;            // function values, fp64, fixed beta, one rank (shard the OBJECTS across ranks)
+  BatchParams P;
+  memset(&P, 0, sizeof(P));
+  P.nx = dims[0];
+  P.ny = dims[1];
+  P.nz = D == 3 ? dims[2] : 1;
+  if (P.nx < 1 || P.ny < 1 || P.nz < 1 || P.nx > BAX || P.ny > BAX || P.nz > BAX) return GPIS_ERR_INVALID;
+  P.N = (long long)P.nx * P.ny * P.nz;
+  if (n_objects < 0 || K < 1 || K > BRMAX || first_index < 0 || first_index >= P.N) return GPIS_ERR_INVALID;
+  if (!(cfg->ell > 0.0) || !(cfg->sf2 > 0.0) || !(cfg->noise >= 0.0) || !(cfg->beta >= 0.0)) return GPIS_ERR_INVALID;
+  if (n_objects == 0) return GPIS_OK;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return GPIS_ERR_NO_DEVICE; }
+  gpis_engine* e = nullptr;             // the CU() macro records messages on a handle; there is none here
+  if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) return GPIS_ERR_NO_DEVICE;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n_blocks = n_objects < prop.multiProcessorCount ? n_objects : prop.multiProcessorCount;
+  const size_t BN = (size_t)n_objects * (size_t)P.N;
+  P.n_objects = n_objects;
+  P.K = K;
+  P.first = first_index;
+  for (int d = 0; d < 3; ++d) {
+    P.org[d] = (origin && d < D) ? origin[d] : 0.0;
+    P.h[d] = (spacing && d < D) ? spacing[d] : 1.0;
+    P.mean_w[d] = d < D ? cfg->mean_w[d] : 0.0;
+  }
+  P.inv_ell2 = 1.0 / (cfg->ell * cfg->ell);
+  P.sf2 = cfg->sf2;
+  P.noise = cfg->noise;
+  P.level = cfg->level;
+  P.eps = cfg->eps;
+  P.beta = cfg->beta;
+  P.variance_mode = cfg->variance_mode;
+  P.mean_c = cfg->mean_c;
+  Scratch sc;
+  double *d_tsdf = nullptr, *d_mu = nullptr, *d_var = nullptr;
+  unsigned char* d_flags = nullptr;
+  long long* d_ids = nullptr;
+  int* d_cnt = nullptr;                 // [3][n_objects]: n_sel, n_model, err
+  CU(sc.get(&d_tsdf, BN));
+  CU(sc.get(&d_mu, BN));
+  CU(sc.get(&d_var, BN));
+  CU(sc.get(&d_flags, BN));
+  CU(sc.get(&d_ids, (size_t)n_objects * K));
+  CU(sc.get(&d_cnt, (size_t)3 * n_objects));
+  CU(sc.get(&P.W, (size_t)n_blocks * BRMAX * BRMAX));
+  CU(sc.get(&P.Wt, (size_t)n_blocks * BRMAX * BRMAX));
+  CU(cudaMemcpyAsync(d_tsdf, tsdf, sizeof(double) * BN, cudaMemcpyDefault, s));
+  CU(cudaMemsetAsync(d_ids, 0xff, sizeof(long long) * (size_t)n_objects * K, s));        // -1: not selected
+  P.tsdf = d_tsdf;
+  P.mu = d_mu;
+  P.var = d_var;
+  P.flags = d_flags;
+  P.ids = d_ids;
+  P.n_sel = d_cnt;
+  P.n_model = d_cnt + n_objects;
+  P.err = d_cnt + 2 * (size_t)n_objects;
+  CU(cudaFuncSetAttribute((const void*)k_batch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  cudaEventRecord(e0, s);
+  launch_batch_select(P, n_blocks, s);
+  cudaError_t ce = cudaGetLastError();
+  cudaEventRecord(e1, s);
+  std::vector<int> h_cnt((size_t)3 * n_objects);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_cnt.data(), d_cnt, sizeof(int) * h_cnt.size(), cudaMemcpyDeviceToHost, s);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ids, d_ids, sizeof(long long) * (size_t)n_objects * K, cudaMemcpyDefault, s);
+  if (ce == cudaSuccess && mean) ce = cudaMemcpyAsync(mean, d_mu, sizeof(double) * BN, cudaMemcpyDefault, s);
+  if (ce == cudaSuccess && var) ce = cudaMemcpyAsync(var, d_var, sizeof(double) * BN, cudaMemcpyDefault, s);
+  if (ce == cudaSuccess && flags) ce = cudaMemcpyAsync(flags, d_flags, BN, cudaMemcpyDefault, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  float ms = 0.f;
+  if (ce == cudaSuccess && device_ms && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *device_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ce != cudaSuccess) return GPIS_ERR_CUDA;
+  bool not_pd = false;
+  for (int k = 0; k < n_objects; ++k) {
+    n_selected[k] = h_cnt[k];
+    if (n_in_model) n_in_model[k] = h_cnt[(size_t)n_objects + k];
+    not_pd = not_pd || h_cnt[2 * (size_t)n_objects + k] != 0;
+  }
+  return not_pd ? GPIS_ERR_NOT_PD : GPIS_OK;
 }
 
 gpis_status gpis_get_sampling_timing(gpis_handle e, double* cov_ms, double* chol_ms, double* draw_ms) {

@@ -15,12 +15,7 @@
 // (-DGPIS_EMULATE, test infrastructure only: the shipped library never defines it) and check the
 // indexing of every kernel and the pointer arithmetic of every launch without a GPU.
 #pragma once
-#ifdef GPIS_EMULATE
-#include "cuda_emu.h"
-#define GPIS_LAUNCH(kern, grid, block, stream, ...) emu::launch(grid, block, [&]() { kern(__VA_ARGS__); })
-#else
-#define GPIS_LAUNCH(kern, grid, block, stream, ...) kern<<<grid, block, 0, stream>>>(__VA_ARGS__)
-#endif
+#include "gpis_launch.cuh"
 #include "gpis_common.cuh"
 
 namespace gpis {

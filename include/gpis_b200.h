@@ -190,6 +190,24 @@ gpis_status gpis_sample_shapes(gpis_handle h, const double* query, int64_t nq, i
  * gpis_sample_shapes: mean + covariance build, Cholesky, draws.  Any pointer may be NULL. */
 gpis_status gpis_get_sampling_timing(gpis_handle h, double* cov_ms, double* chol_ms, double* draw_ms);
 
+/* A batch of INDEPENDENT small objects on the same lattice (BASELINE config 5: 512 x 32^3 object fits;
+ * the Dex-Net-style caller loops Gpis3D / select_active_set over objects): the whole greedy selection
+ * of an object (select_active_set_straddle.m:62-130) runs inside one thread block and one launch
+ * advances every object -- no handle, no per-step launches.  cfg supplies dim (2 or 3), ell, sf2,
+ * mean, noise, level, eps, beta, variance_mode, device; it must ask for function values only
+ * (use_gradients 0), fp64, GPIS_BETA_FIXED, world_size <= 1 (shard the objects across ranks).
+ * dims <= 32 per axis, K <= 256.  tsdf[k*N + j]: object k, lattice index j (x fastest).
+ * Outputs (host or device pointers): ids[k*K + i] picks in selection order (-1 beyond
+ * n_selected[k]), n_in_model[k] (NULL allowed), and -- each may be NULL -- the posterior mean /
+ * variance of every lattice point and the level-set flags (bit 0 active, bit 1 high, bit 2 low),
+ * [n_objects][N].  device_ms (NULL allowed): CUDA-event time of the launch.  Returns
+ * GPIS_ERR_NOT_PD if any object's factor lost positive definiteness (its counts tell where). */
+gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin,
+                              const double* spacing, int32_t n_objects, const double* tsdf,
+                              int64_t first_index, int32_t K, int64_t* ids, int32_t* n_selected,
+                              int32_t* n_in_model, double* mean, double* var, uint8_t* flags,
+                              double* device_ms, void* stream);
+
 /* Level-set state of the candidates after selection: last ambiguity each candidate was
  * scored with, and the high / low masks (straddle.m:121-125; ClassificationBuffers). */
 gpis_status gpis_get_levelset(gpis_handle h, double* ambiguity, uint8_t* high, uint8_t* low,

@@ -32,18 +32,22 @@ namespace emu {
 struct WarpBox {
   std::barrier<> bar{32};
   double a[32], b[32];
+  unsigned long long slot[32];
 };
 inline thread_local uint3 t_idx, b_idx;
 inline thread_local WarpBox* my_warp;
 inline thread_local int my_lane;
 inline dim3 g_dim, b_dim;
 inline std::barrier<>* cta_bar;
+inline unsigned char* dyn_smem;          // the block's dynamic shared memory (GPIS_DYN_SMEM)
 
 template <class F>
-void launch(dim3 grid, dim3 block, F body) {
+void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
   const unsigned nth = block.x * block.y * block.z;
   g_dim = grid;
   b_dim = block;
+  std::vector<unsigned char> smem(smem_bytes + 16);
+  dyn_smem = smem.data();
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
@@ -73,6 +77,25 @@ void launch(dim3 grid, dim3 block, F body) {
 #define gridDim emu::g_dim
 
 inline void __syncthreads() { emu::cta_bar->arrive_and_wait(); }
+inline void __threadfence_block() {}
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+// warp shuffle over all 32 lanes: every lane publishes its value, reads its partner's
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  emu::WarpBox* w = emu::my_warp;
+  const int l = emu::my_lane;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  w->slot[l] = bits;
+  w->bar.arrive_and_wait();
+  const unsigned long long other = w->slot[l ^ lane_mask];
+  w->bar.arrive_and_wait();
+  T out;
+  memcpy(&out, &other, sizeof(T));
+  return out;
+}
 inline int atomicCAS(int* p, int cmp, int val) { return __sync_val_compare_and_swap(p, cmp, val); }
 
 namespace gpis {

@@ -54,3 +54,28 @@ extern "C" int emu_chol_upper(const double* A, long long n, double jitter, doubl
   for (long long i = 0; i < n; ++i) memcpy(T_out + i * n, S.data() + i * npad, sizeof(double) * n);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// gpis_batch.cuh: the one-block-per-object whole-selection kernel, driven like gpis_batch_select does
+// ---------------------------------------------------------------------------------------------
+#include "../../gpis_b200/csrc/gpis_batch.cuh"
+
+extern "C" int emu_batch_select(const int* dims, const double* origin, const double* spacing, int n_objects,
+                                const double* tsdf, long long first, int K, double ell, double sf2, double noise,
+                                double level, double eps, double beta, int variance_mode, const double* mean_w,
+                                double mean_c, int n_blocks, long long* ids, int* n_sel, int* n_model, int* err,
+                                double* mu, double* var, unsigned char* flags) {
+  BatchParams P;
+  memset(&P, 0, sizeof(P));
+  P.nx = dims[0]; P.ny = dims[1]; P.nz = dims[2];
+  P.N = (long long)P.nx * P.ny * P.nz;
+  P.n_objects = n_objects; P.K = K; P.first = first;
+  for (int d = 0; d < 3; ++d) { P.org[d] = origin[d]; P.h[d] = spacing[d]; P.mean_w[d] = mean_w[d]; }
+  P.inv_ell2 = 1.0 / (ell * ell); P.sf2 = sf2; P.noise = noise; P.level = level; P.eps = eps; P.beta = beta;
+  P.variance_mode = variance_mode; P.mean_c = mean_c;
+  P.tsdf = tsdf; P.mu = mu; P.var = var; P.flags = flags; P.ids = ids; P.n_sel = n_sel; P.n_model = n_model; P.err = err;
+  std::vector<double> W((size_t)n_blocks * BRMAX * BRMAX, -7.0), Wt((size_t)n_blocks * BRMAX * BRMAX, -7.0);   // poisoned
+  P.W = W.data(); P.Wt = Wt.data();
+  launch_batch_select(P, n_blocks, nullptr);
+  return 0;
+}

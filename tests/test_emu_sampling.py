@@ -176,3 +176,84 @@ def test_emulated_two_level_cholesky_across_outer_blocks(emu):
     assert np.all(np.tril(T, -1) == 0.0)
     assert np.max(np.abs(T - ref)) < 1e-12
     assert np.max(np.abs(T.T @ T - A - 1e-9 * np.eye(n))) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------
+# gpis_batch.cuh: one thread block runs the whole selection of one object
+# ------------------------------------------------------------------------------------------------
+def run_emu_batch(lib, dims, tsdfs, first, K, hyp, train, n_blocks, variance_mode=0):
+    vp = C.c_void_p
+    lib.emu_batch_select.restype = C.c_int
+    lib.emu_batch_select.argtypes = [vp, vp, vp, C.c_int, vp, C.c_longlong, C.c_int] + [C.c_double] * 6 + \
+        [C.c_int, vp, C.c_double, C.c_int] + [vp] * 7
+    B, N = len(tsdfs), int(np.prod(dims))
+    d3 = np.ascontiguousarray(np.array(list(dims) + [1] * (3 - len(dims)), np.int32))
+    org, sp = np.zeros(3), np.ones(3)
+    t = np.ascontiguousarray(np.stack(tsdfs).astype(np.float64))
+    ids = np.full((B, K), -1, np.int64)
+    n_sel, n_model, err = (np.zeros(B, np.int32) for _ in range(3))
+    mu, var, flags = np.empty((B, N)), np.empty((B, N)), np.empty((B, N), np.uint8)
+    mw = np.zeros(3)
+    mw[:len(dims)] = hyp["mean"][:len(dims)]
+    p = lambda a: a.ctypes.data_as(vp)
+    rc = lib.emu_batch_select(p(d3), p(org), p(sp), B, p(t), first, K, float(np.exp(hyp["cov"][0])),
+                              float(np.exp(2 * hyp["cov"][1])), float(np.exp(2 * hyp["lik"])), train["levelSet"],
+                              train["eps"], train["beta"], variance_mode, p(mw), float(hyp["mean"][len(dims)]), n_blocks,
+                              p(ids), p(n_sel), p(n_model), p(err), p(mu), p(var), p(flags))
+    assert rc == 0
+    return ids, n_sel, n_model, err, mu, var, flags
+
+
+def lattice_points(dims):
+    idx = np.indices(tuple(dims)[::-1]).reshape(len(dims), -1)[::-1]
+    return np.ascontiguousarray(idx.T.astype(np.float64))
+
+
+@pytest.mark.parametrize("dims,K,n_blocks", [((10, 9, 7), 24, 2), ((13, 12), 30, 3)])
+def test_emulated_batch_kernel_matches_the_oracle_per_object(emu, dims, K, n_blocks):
+    """Three objects over two or three blocks (a block takes its objects one after another, reusing
+    its W workspace): picks, model size, posterior of EVERY lattice point and the level-set flags
+    against the incremental oracle; K - 1 points in the model (straddle.m:129-130)."""
+    rng = np.random.default_rng(7)
+    pts = lattice_points(dims)
+    D = len(dims)
+    hyp = {"cov": np.array([np.log(2.2), np.log(1.1)]), "mean": np.concatenate([0.01 * np.arange(1, D + 1), [0.05]]),
+           "lik": 0.5 * np.log(0.03)}
+    train = {"activeSetSize": K, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    tsdfs = []
+    for k in range(3):
+        c = np.array(dims) * rng.uniform(0.4, 0.6, D)
+        tsdfs.append(np.clip((np.linalg.norm(pts - c, axis=1) - 0.3 * min(dims) - 0.3 * k) / 2.0, -1, 1)
+                     + 1e-3 * rng.standard_normal(len(pts)))
+    first = 17
+    ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, tsdfs, first, K, hyp, train, n_blocks)
+    assert not err.any()
+    for k in range(3):
+        shape = {"points": pts, "tsdf": tsdfs[k], "normals": None, "noise": None}
+        ora = O.select_straddle_incremental(shape, train, first, hyp=hyp, prune=False)
+        assert n_sel[k] == len(ora["order"]) and np.array_equal(ids[k, :n_sel[k]], ora["order"]), k
+        assert n_model[k] == ora["n_in_model"]
+        fm, fv, _ = O.predict_points(ora["gp"], pts)
+        assert np.max(np.abs(mu[k] - fm)) < 1e-10 and np.max(np.abs(var[k] - fv)) < 1e-10
+        assert np.array_equal((flags[k] & 1) > 0, ora["active"])
+        assert np.array_equal((flags[k] & 2) > 0, ora["high"]) and np.array_equal((flags[k] & 4) > 0, ora["low"])
+    assert not np.array_equal(ids[0], ids[1])
+
+
+def test_emulated_batch_kernel_early_stop_and_k_one(emu):
+    """A flat TSDF far from the level set classifies everything after the first point: the selection stops
+    with the points picked so far; K = 1 selects the first point and fits nothing."""
+    dims = (6, 5, 4)
+    pts = lattice_points(dims)
+    hyp = {"cov": np.array([np.log(3.0), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.01)}
+    train = {"activeSetSize": 12, "beta": 1.0, "eps": 1e-2, "levelSet": 0.0}
+    tsdf = np.full(len(pts), 0.9) + 1e-4 * np.arange(len(pts))
+    shape = {"points": pts, "tsdf": tsdf, "normals": None, "noise": None}
+    ora = O.select_straddle_incremental(shape, train, 3, hyp=hyp, prune=False)
+    ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, [tsdf], 3, 12, hyp, train, 1)
+    assert len(ora["order"]) < 12                                  # the oracle stops early too
+    assert n_sel[0] == len(ora["order"]) and np.array_equal(ids[0, :n_sel[0]], ora["order"])
+    assert n_model[0] == ora["n_in_model"] and err[0] == 0
+    ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, [tsdf], 3, 1, hyp, train, 1)
+    assert n_sel[0] == 1 and ids[0, 0] == 3 and n_model[0] == 0
+    assert np.all(var[0] == 1.0) and flags[0, 3] == 1 and flags[0].sum() == 1
