@@ -50,6 +50,11 @@ __device__ __forceinline__ bool batch_better(double s, long long id, double bs, 
   return (s > bs) || (s == bs && id < bid);
 }
 
+// FAST selects the tuned forms of the three inner loops (vector shared-memory loads and w folded into the
+// Ty factor in the update; the state of eight lattice points loaded before any of them is processed; four
+// independent partial sums in the two triangular passes of the append).  Both forms are kept: the plain
+// one is the reference the tuned one is tested against (same picks; sums grouped differently).
+template <bool FAST>
 __global__ void __launch_bounds__(BT, 1) k_batch_select(BatchParams P) {
   GPIS_DYN_SMEM(double, sm);
   double* Tx = sm;                           // [BRMAX][BAX]
@@ -115,7 +120,20 @@ __global__ void __launch_bounds__(BT, 1) k_batch_select(BatchParams P) {
       // l = W k: thread s walks column entries Wt[c][s], c <= s (coalesced across s), ascending c
       double lv = 0.0;
       if (tid < r) {
-        for (int c = 0; c <= tid; ++c) lv += Wt[(long long)c * BRMAX + tid] * s_k[c];
+        if (FAST) {
+          double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+          int c = 0;
+          for (; c + 3 <= tid; c += 4) {
+            l0 += Wt[(long long)c * BRMAX + tid] * s_k[c];
+            l1 += Wt[(long long)(c + 1) * BRMAX + tid] * s_k[c + 1];
+            l2 += Wt[(long long)(c + 2) * BRMAX + tid] * s_k[c + 2];
+            l3 += Wt[(long long)(c + 3) * BRMAX + tid] * s_k[c + 3];
+          }
+          for (; c <= tid; ++c) l0 += Wt[(long long)c * BRMAX + tid] * s_k[c];
+          lv = (l0 + l1) + (l2 + l3);
+        } else {
+          for (int c = 0; c <= tid; ++c) lv += Wt[(long long)c * BRMAX + tid] * s_k[c];
+        }
         s_l[tid] = lv;
       }
       // |l|^2 and l.g: fixed shuffle tree per warp, then the 8 warp sums in order
@@ -145,7 +163,20 @@ __global__ void __launch_bounds__(BT, 1) k_batch_select(BatchParams P) {
         double wv;
         if (tid < r) {
           double y = 0.0;
-          for (int s = tid; s < r; ++s) y += s_l[s] * W[(long long)s * BRMAX + tid];
+          if (FAST) {
+            double y1 = 0.0, y2 = 0.0, y3 = 0.0;
+            int s = tid;
+            for (; s + 3 < r; s += 4) {
+              y += s_l[s] * W[(long long)s * BRMAX + tid];
+              y1 += s_l[s + 1] * W[(long long)(s + 1) * BRMAX + tid];
+              y2 += s_l[s + 2] * W[(long long)(s + 2) * BRMAX + tid];
+              y3 += s_l[s + 3] * W[(long long)(s + 3) * BRMAX + tid];
+            }
+            for (; s < r; ++s) y += s_l[s] * W[(long long)s * BRMAX + tid];
+            y = (y + y1) + (y2 + y3);
+          } else {
+            for (int s = tid; s < r; ++s) y += s_l[s] * W[(long long)s * BRMAX + tid];
+          }
           wv = -y / dd;
         } else {
           wv = 1.0 / dd;
@@ -178,53 +209,96 @@ __global__ void __launch_bounds__(BT, 1) k_batch_select(BatchParams P) {
         double acc[BZB][2][2];
 #pragma unroll
         for (int z = 0; z < BZB; ++z) acc[z][0][0] = acc[z][0][1] = acc[z][1][0] = acc[z][1][1] = 0.0;
-        for (int rho = 0; rho < r; ++rho) {
-          const double w = s_w[rho];
-          const double y0 = Ty[rho * BAX + ty2], y1 = Ty[rho * BAX + ty2 + 1];
-          const double x0 = Tx[rho * BAX + tx2], x1 = Tx[rho * BAX + tx2 + 1];
-          const double p00 = y0 * x0, p01 = y0 * x1, p10 = y1 * x0, p11 = y1 * x1;
-          const double* tz = Tz + rho * BAX + z0;
+        if (FAST) {
+          for (int rho = 0; rho < r; ++rho) {
+            const double w = s_w[rho];
+            const double2 yy = *reinterpret_cast<const double2*>(Ty + rho * BAX + ty2);
+            const double2 xx = *reinterpret_cast<const double2*>(Tx + rho * BAX + tx2);
+            const double y0 = w * yy.x, y1 = w * yy.y;
+            const double p00 = y0 * xx.x, p01 = y0 * xx.y, p10 = y1 * xx.x, p11 = y1 * xx.y;
+            const double2* tz2 = reinterpret_cast<const double2*>(Tz + rho * BAX + z0);
 #pragma unroll
-          for (int z = 0; z < BZB; ++z) {
-            const double cz = w * tz[z];
-            acc[z][0][0] += cz * p00;
-            acc[z][0][1] += cz * p01;
-            acc[z][1][0] += cz * p10;
-            acc[z][1][1] += cz * p11;
-          }
-        }
-#pragma unroll
-        for (int z = 0; z < BZB; ++z) {
-          const int jz = z0 + z;
-          if (jz >= nz) continue;
-#pragma unroll
-          for (int a = 0; a < 2; ++a) {
-            const int jy = ty2 + a;
-            if (jy >= ny) continue;
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const int jx = tx2 + b;
-              if (jx >= nx) continue;
-              const long long j = (long long)jx + (long long)nx * (jy + (long long)ny * jz);
-              const double v = acc[z][a][b];
-              const double m1 = __dadd_rn(mu[j], __dmul_rn(v, gnew));
-              const double v1 = __dadd_rn(var[j], -__dmul_rn(v, v));
-              mu[j] = m1;
-              var[j] = v1;
-              unsigned char f = flags[j];
-              if (f & (F_ACTIVE | F_HIGH | F_LOW)) continue;
-              double ve = v1;
-              if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise);
-              const double wd = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
-              const double hi = __dadd_rn(m1, wd), lo = __dadd_rn(m1, -wd);
-              const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-              unsigned char f1 = f;
-              if (__dadd_rn(lo, P.eps) > P.level) f1 |= F_HIGH;      // :122-125
-              if (__dadd_rn(hi, -P.eps) < P.level) f1 |= F_LOW;
-              if (f1 != f) flags[j] = f1;
-              if (sc == sc && (best_j < 0 || batch_better(sc, j, best_s, best_j))) { best_s = sc; best_j = j; }
+            for (int zq = 0; zq < BZB / 2; ++zq) {
+              const double2 t = tz2[zq];
+              acc[2 * zq][0][0] += t.x * p00;
+              acc[2 * zq][0][1] += t.x * p01;
+              acc[2 * zq][1][0] += t.x * p10;
+              acc[2 * zq][1][1] += t.x * p11;
+              acc[2 * zq + 1][0][0] += t.y * p00;
+              acc[2 * zq + 1][0][1] += t.y * p01;
+              acc[2 * zq + 1][1][0] += t.y * p10;
+              acc[2 * zq + 1][1][1] += t.y * p11;
             }
           }
+        } else {
+          for (int rho = 0; rho < r; ++rho) {
+            const double w = s_w[rho];
+            const double y0 = Ty[rho * BAX + ty2], y1 = Ty[rho * BAX + ty2 + 1];
+            const double x0 = Tx[rho * BAX + tx2], x1 = Tx[rho * BAX + tx2 + 1];
+            const double p00 = y0 * x0, p01 = y0 * x1, p10 = y1 * x0, p11 = y1 * x1;
+            const double* tz = Tz + rho * BAX + z0;
+#pragma unroll
+            for (int z = 0; z < BZB; ++z) {
+              const double cz = w * tz[z];
+              acc[z][0][0] += cz * p00;
+              acc[z][0][1] += cz * p01;
+              acc[z][1][0] += cz * p10;
+              acc[z][1][1] += cz * p11;
+            }
+          }
+        }
+        // posterior update, straddle score, classification of the thread's 2 x 2 x 8 lattice points, two
+        // z-slices (eight points) at a time; FAST loads the state of all eight before touching any
+        constexpr int ZP = 2;
+#pragma unroll
+        for (int zb = 0; zb < BZB; zb += ZP) {
+          double m0[ZP][2][2], v0[ZP][2][2];
+          unsigned char f0[ZP][2][2];
+          bool ok[ZP][2][2];
+#pragma unroll
+          for (int zz = 0; zz < ZP; ++zz)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int jz = z0 + zb + zz, jy = ty2 + a, jx = tx2 + b;
+                ok[zz][a][b] = jz < nz && jy < ny && jx < nx;
+                if (FAST && ok[zz][a][b]) {
+                  const long long j = (long long)jx + (long long)nx * (jy + (long long)ny * jz);
+                  m0[zz][a][b] = mu[j];
+                  v0[zz][a][b] = var[j];
+                  f0[zz][a][b] = flags[j];
+                }
+              }
+#pragma unroll
+          for (int zz = 0; zz < ZP; ++zz)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                if (!ok[zz][a][b]) continue;
+                const int jz = z0 + zb + zz, jy = ty2 + a, jx = tx2 + b;
+                const long long j = (long long)jx + (long long)nx * (jy + (long long)ny * jz);
+                const double v = acc[zb + zz][a][b];
+                const double mold = FAST ? m0[zz][a][b] : mu[j];
+                const double vold = FAST ? v0[zz][a][b] : var[j];
+                const double m1 = __dadd_rn(mold, __dmul_rn(v, gnew));
+                const double v1 = __dadd_rn(vold, -__dmul_rn(v, v));
+                mu[j] = m1;
+                var[j] = v1;
+                const unsigned char f = FAST ? f0[zz][a][b] : flags[j];
+                if (f & (F_ACTIVE | F_HIGH | F_LOW)) continue;
+                double ve = v1;
+                if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise);
+                const double wd = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
+                const double hi = __dadd_rn(m1, wd), lo = __dadd_rn(m1, -wd);
+                const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
+                unsigned char f1 = f;
+                if (__dadd_rn(lo, P.eps) > P.level) f1 |= F_HIGH;      // :122-125
+                if (__dadd_rn(hi, -P.eps) < P.level) f1 |= F_LOW;
+                if (f1 != f) flags[j] = f1;
+                if (sc == sc && (best_j < 0 || batch_better(sc, j, best_s, best_j))) { best_s = sc; best_j = j; }
+              }
         }
       }
       for (int o = 16; o > 0; o >>= 1) {
@@ -260,8 +334,11 @@ __global__ void __launch_bounds__(BT, 1) k_batch_select(BatchParams P) {
   }
 }
 
-inline void launch_batch_select(const BatchParams& P, int n_blocks, cudaStream_t s) {
-  GPIS_LAUNCH_SMEM(k_batch_select, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
+inline void launch_batch_select(const BatchParams& P, int n_blocks, bool fast, cudaStream_t s) {
+  auto k0 = k_batch_select<false>;
+  auto k1 = k_batch_select<true>;
+  if (fast) GPIS_LAUNCH_SMEM(k1, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
+  else GPIS_LAUNCH_SMEM(k0, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
 }
 
 }  // namespace gpis

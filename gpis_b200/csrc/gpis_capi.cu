@@ -1089,12 +1089,16 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
   P.n_sel = d_cnt;
   P.n_model = d_cnt + n_objects;
   P.err = d_cnt + 2 * (size_t)n_objects;
-  CU(cudaFuncSetAttribute((const void*)k_batch_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+  // GPIS_BATCH_KERNEL=tuned selects the tuned inner loops (gpis_batch.cuh); the plain form is the default
+  const char* variant = getenv("GPIS_BATCH_KERNEL");
+  const bool fast = variant && strcmp(variant, "tuned") == 0;
+  CU(cudaFuncSetAttribute((const void*)k_batch_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+  CU(cudaFuncSetAttribute((const void*)k_batch_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
   cudaEventRecord(e0, s);
-  launch_batch_select(P, n_blocks, s);
+  launch_batch_select(P, n_blocks, fast, s);
   cudaError_t ce = cudaGetLastError();
   cudaEventRecord(e1, s);
   std::vector<int> h_cnt((size_t)3 * n_objects);

@@ -63,7 +63,7 @@ extern "C" int emu_chol_upper(const double* A, long long n, double jitter, doubl
 extern "C" int emu_batch_select(const int* dims, const double* origin, const double* spacing, int n_objects,
                                 const double* tsdf, long long first, int K, double ell, double sf2, double noise,
                                 double level, double eps, double beta, int variance_mode, const double* mean_w,
-                                double mean_c, int n_blocks, long long* ids, int* n_sel, int* n_model, int* err,
+                                double mean_c, int n_blocks, int fast, long long* ids, int* n_sel, int* n_model, int* err,
                                 double* mu, double* var, unsigned char* flags) {
   BatchParams P;
   memset(&P, 0, sizeof(P));
@@ -76,6 +76,6 @@ extern "C" int emu_batch_select(const int* dims, const double* origin, const dou
   P.tsdf = tsdf; P.mu = mu; P.var = var; P.flags = flags; P.ids = ids; P.n_sel = n_sel; P.n_model = n_model; P.err = err;
   std::vector<double> W((size_t)n_blocks * BRMAX * BRMAX, -7.0), Wt((size_t)n_blocks * BRMAX * BRMAX, -7.0);   // poisoned
   P.W = W.data(); P.Wt = Wt.data();
-  launch_batch_select(P, n_blocks, nullptr);
+  launch_batch_select(P, n_blocks, fast != 0, nullptr);
   return 0;
 }

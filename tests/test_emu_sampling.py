@@ -18,7 +18,9 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(ROOT, "build", "libemu_sample.so")
 EMU_DEPS = [os.path.join(EMU_DIR, "emu_sample.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_sample.cuh"),
-            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh")]
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch.cuh"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_launch.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -181,11 +183,11 @@ def test_emulated_two_level_cholesky_across_outer_blocks(emu):
 # ------------------------------------------------------------------------------------------------
 # gpis_batch.cuh: one thread block runs the whole selection of one object
 # ------------------------------------------------------------------------------------------------
-def run_emu_batch(lib, dims, tsdfs, first, K, hyp, train, n_blocks, variance_mode=0):
+def run_emu_batch(lib, dims, tsdfs, first, K, hyp, train, n_blocks, variance_mode=0, fast=0):
     vp = C.c_void_p
     lib.emu_batch_select.restype = C.c_int
     lib.emu_batch_select.argtypes = [vp, vp, vp, C.c_int, vp, C.c_longlong, C.c_int] + [C.c_double] * 6 + \
-        [C.c_int, vp, C.c_double, C.c_int] + [vp] * 7
+        [C.c_int, vp, C.c_double, C.c_int, C.c_int] + [vp] * 7
     B, N = len(tsdfs), int(np.prod(dims))
     d3 = np.ascontiguousarray(np.array(list(dims) + [1] * (3 - len(dims)), np.int32))
     org, sp = np.zeros(3), np.ones(3)
@@ -198,7 +200,7 @@ def run_emu_batch(lib, dims, tsdfs, first, K, hyp, train, n_blocks, variance_mod
     p = lambda a: a.ctypes.data_as(vp)
     rc = lib.emu_batch_select(p(d3), p(org), p(sp), B, p(t), first, K, float(np.exp(hyp["cov"][0])),
                               float(np.exp(2 * hyp["cov"][1])), float(np.exp(2 * hyp["lik"])), train["levelSet"],
-                              train["eps"], train["beta"], variance_mode, p(mw), float(hyp["mean"][len(dims)]), n_blocks,
+                              train["eps"], train["beta"], variance_mode, p(mw), float(hyp["mean"][len(dims)]), n_blocks, int(fast),
                               p(ids), p(n_sel), p(n_model), p(err), p(mu), p(var), p(flags))
     assert rc == 0
     return ids, n_sel, n_model, err, mu, var, flags
@@ -209,8 +211,9 @@ def lattice_points(dims):
     return np.ascontiguousarray(idx.T.astype(np.float64))
 
 
+@pytest.mark.parametrize("fast", [0, 1])
 @pytest.mark.parametrize("dims,K,n_blocks", [((10, 9, 7), 24, 2), ((13, 12), 30, 3), ((6, 5, 19), 14, 1)])
-def test_emulated_batch_kernel_matches_the_oracle_per_object(emu, dims, K, n_blocks):
+def test_emulated_batch_kernel_matches_the_oracle_per_object(emu, dims, K, n_blocks, fast):
     """Three objects over two or three blocks (a block takes its objects one after another, reusing
     its W workspace): picks, model size, posterior of EVERY lattice point and the level-set flags
     against the incremental oracle; K - 1 points in the model (straddle.m:129-130)."""
@@ -226,7 +229,7 @@ def test_emulated_batch_kernel_matches_the_oracle_per_object(emu, dims, K, n_blo
         tsdfs.append(np.clip((np.linalg.norm(pts - c, axis=1) - 0.3 * min(dims) - 0.3 * k) / 2.0, -1, 1)
                      + 1e-3 * rng.standard_normal(len(pts)))
     first = 17
-    ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, tsdfs, first, K, hyp, train, n_blocks)
+    ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, tsdfs, first, K, hyp, train, n_blocks, fast=fast)
     assert not err.any()
     for k in range(3):
         shape = {"points": pts, "tsdf": tsdfs[k], "normals": None, "noise": None}

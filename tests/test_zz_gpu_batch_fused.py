@@ -30,8 +30,15 @@ def test_arguments_are_validated_before_the_device_is_touched():
         assert ei.value.status == _lib.ERR_NO_DEVICE
 
 
+@pytest.fixture(params=["plain", "tuned"])
+def variant(request, monkeypatch):
+    """Both forms of the kernel's inner loops (GPIS_BATCH_KERNEL, read at every gpis_batch_select)."""
+    monkeypatch.setenv("GPIS_BATCH_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.gpu
-def test_fused_batch_matches_solo_engines_and_oracle():
+def test_fused_batch_matches_solo_engines_and_oracle(variant):
     import gpis_b200
     from gpis_b200.batch import select_batch_fused, superellipsoid_tsdf
     g, K, B = 16, 60, 7
@@ -62,7 +69,7 @@ def test_fused_batch_matches_solo_engines_and_oracle():
 
 
 @pytest.mark.gpu
-def test_fused_batch_more_objects_than_sms_2d_and_device_input():
+def test_fused_batch_more_objects_than_sms_2d_and_device_input(variant):
     """200 small objects (> 148 blocks: blocks take several objects in turn, reusing their workspace),
     a 2-D lattice with odd sizes, and a torch CUDA tensor as input."""
     import torch
