@@ -1095,9 +1095,13 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
   const bool fast = !(variant && strcmp(variant, "plain") == 0);
   CU(cudaFuncSetAttribute((const void*)k_batch_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  CU(cudaEventCreate(&e0));
-  CU(cudaEventCreate(&e1));
+  struct EventPair {                    // released on every return path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CU(cudaEventCreate(&ev.a));
+  CU(cudaEventCreate(&ev.b));
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   cudaEventRecord(e0, s);
   launch_batch_select(P, n_blocks, fast, s);
   cudaError_t ce = cudaGetLastError();
@@ -1111,8 +1115,6 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   float ms = 0.f;
   if (ce == cudaSuccess && device_ms && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *device_ms = ms;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (ce != cudaSuccess) return GPIS_ERR_CUDA;
   bool not_pd = false;
   for (int k = 0; k < n_objects; ++k) {

@@ -67,6 +67,12 @@ def main():
               "err_rms": f64(te.rmsError), "err_std": f64(te.stdError),
               "shape_fullTsdf": f64(s["shapeParams"].fullTsdf)})
     np.savez_compressed(f"{OUT}/loofa.npz", **d)
+    # what the reference stored about its posterior shape sampling of this model
+    # (create_experiment_object.m:23-26,38-39): the densities of the 1000 draws (every one +inf) and the
+    # wall-clock times of the dense fit and of sample_shapes
+    cr = c["constructionResults"]
+    np.savez_compressed(f"{OUT}/loofa_sampling.npz", pdfs=f64(cr.pdfs), samplingTime=f64(cr.samplingTime),
+                        constructionTime=f64(cr.constructionTime))
     # real 3-D SDF (header asserted in sdf_file.py:91-99) and a 50x50 2-D csv (:116-117)
     with open(f"{REF}/data/test/sdf/Co_clean_dim_25.sdf") as f:
         nx, ny, nz = [int(t) for t in f.readline().split()]
