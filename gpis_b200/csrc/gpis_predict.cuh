@@ -9,6 +9,7 @@
 // never stored; the reference materialises it and runs cublasStrsm on it
 // (gpu_active_set_selector.cpp:858-871).
 #pragma once
+#include "gpis_launch.cuh"
 #include "gpis_common.cuh"
 
 namespace gpis {
@@ -64,12 +65,14 @@ __global__ void __launch_bounds__(256) k_alpha(const double* __restrict__ Wt, lo
   if (lane == 0) alpha[k] = p;
 }
 
+#ifndef GPIS_EMULATE   // tests/emu supplies synchronous stand-ins (test infrastructure only)
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+#endif
 
 // Covariance of model row k (point i = k / NB, kind a = k % NB, at X_i) with f(x_q), plus what
 // the mean's gradient needs.  diff = x_q - X_i.
@@ -99,14 +102,16 @@ __device__ __forceinline__ double kstar(const PredictParams& P, int k, const dou
 constexpr int PLDA = PSB + 4;
 constexpr int PLDB = PQ + 4;
 
+#ifndef GPIS_EMULATE
 __device__ __forceinline__ void p_dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+#endif
 
 template <int NB, int D>
 __global__ void __launch_bounds__(PRED_THREADS, 2) k_predict_f64(PredictParams P) {
-  extern __shared__ __align__(16) double smem[];
+  GPIS_DYN_SMEM(double, smem);
   double* As = smem;                                  // [2][PKC][PLDA]
   double* Bs = smem + 2 * PKC * PLDA;                 // [2][PKC][PLDB]
   double* Red = Bs + 2 * PKC * PLDB;                  // [8][PQ] reductions

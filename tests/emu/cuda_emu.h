@@ -77,7 +77,12 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
 #define blockDim emu::b_dim
 #define gridDim emu::g_dim
 
+using std::max;
+using std::min;
 inline void __syncthreads() { emu::cta_bar->arrive_and_wait(); }
+inline void __syncwarp() { emu::my_warp->bar.arrive_and_wait(); }
+template <class T>
+inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence_block() {}
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
@@ -100,6 +105,11 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
 inline int atomicCAS(int* p, int cmp, int val) { return __sync_val_compare_and_swap(p, cmp, val); }
 
 namespace gpis {
+// cp.async stand-ins: the copy happens at once, commit / wait are no-ops (a superset of the allowed
+// behaviours: a missing wait cannot be detected here)
+inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 // mma.sync.aligned.m8n8k4.row.col.f64: lane l supplies A[l/4][l%4] and B[l%4][l/4] and owns
 // D[l/4][2*(l%4) + {0,1}] (PTX ISA, "Matrix fragments for mma.m8n8k4 with .f64").
 inline void s_dmma(double& c0, double& c1, double a, double b) {
@@ -115,4 +125,5 @@ inline void s_dmma(double& c0, double& c1, double a, double b) {
   }
   w->bar.arrive_and_wait();
 }
+inline void p_dmma(double& c0, double& c1, double a, double b) { s_dmma(c0, c1, a, b); }
 }  // namespace gpis

@@ -79,3 +79,53 @@ extern "C" int emu_batch_select(const int* dims, const double* origin, const dou
   launch_batch_select(P, n_blocks, fast != 0, nullptr);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// gpis_predict.cuh: W' = L^-T by columns, alpha = W' g, fused covariance-tile + triangular GEMM +
+// column-norm prediction kernel -- launched as ensure_inverse / gpis_predict in gpis_capi.cu do
+// ---------------------------------------------------------------------------------------------
+#include "../../gpis_b200/csrc/gpis_predict.cuh"
+
+template <int NB, int D>
+static void emu_predict_launch(const PredictParams& Q, long long nq) {
+  const size_t smem = (2 * PKC * PLDA + 2 * PKC * PLDB + 8 * PQ) * sizeof(double);      // PRED_SMEM of gpis_capi.cu
+  auto k = k_predict_f64<NB, D>;
+  GPIS_LAUNCH_SMEM(k, dim3((unsigned)((nq + PQ - 1) / PQ)), dim3(PRED_THREADS), smem, nullptr, Q);
+}
+
+extern "C" int emu_predict(int D, int grad, int R, int m, const double* AX, const double* L, int ldl, const double* g,
+                           const double* query, long long nq, double ell, double sf2, const double* mean_w,
+                           double mean_c, int want_nrm, double* mean, double* var, double* nrm, double* alpha_out) {
+  const long long ldw = ((long long)R + PSB - 1) / PSB * PSB, rk_pad = ((long long)R + PKC - 1) / PKC * PKC;
+  std::vector<double> Wt((size_t)ldw * rk_pad, 0.0), alpha(R > 0 ? R : 1, 0.0);
+  if (R > 0) {
+    const int blocks = (R * 32 + 255) / 256;
+    GPIS_LAUNCH(k_invert_factor, dim3((unsigned)blocks), dim3(256), nullptr, L, ldl, R, Wt.data(), ldw);
+    GPIS_LAUNCH(k_alpha, dim3((unsigned)blocks), dim3(256), nullptr, Wt.data(), ldw, g, R, alpha.data());
+  }
+  PredictParams Q;
+  memset(&Q, 0, sizeof(Q));
+  Q.Wt = Wt.data();
+  Q.ldw = ldw;
+  Q.alpha = alpha.data();
+  for (int d = 0; d < D; ++d) { Q.AX[d] = AX + (size_t)d * m; Q.q[d] = query + (size_t)d * nq; }
+  Q.nq = nq;
+  Q.mean = mean;
+  Q.var = var;
+  for (int d = 0; d < D; ++d) Q.nrm[d] = want_nrm ? nrm + (size_t)d * nq : nullptr;
+  Q.R = R;
+  Q.inv_ell2 = 1.0 / (ell * ell);
+  Q.sf2 = sf2;
+  for (int d = 0; d < D; ++d) Q.mean_w[d] = mean_w[d];
+  Q.mean_c = mean_c;
+  switch (D * 2 + (grad ? 1 : 0)) {
+    case 2: emu_predict_launch<1, 1>(Q, nq); break;
+    case 3: emu_predict_launch<2, 1>(Q, nq); break;
+    case 4: emu_predict_launch<1, 2>(Q, nq); break;
+    case 5: emu_predict_launch<3, 2>(Q, nq); break;
+    case 6: emu_predict_launch<1, 3>(Q, nq); break;
+    default: emu_predict_launch<4, 3>(Q, nq); break;
+  }
+  if (alpha_out) memcpy(alpha_out, alpha.data(), sizeof(double) * R);
+  return 0;
+}

@@ -9,7 +9,7 @@
 #include <string>
 
 static void small_model(int m, std::vector<double>& ax, std::vector<double>& Wt, long long ldw, std::vector<double>& alpha,
-                        double ell, double noise) {
+                        double ell, double noise, std::vector<double>* L_out = nullptr) {
   std::mt19937 rng(5);
   std::uniform_real_distribution<double> u(0.0, 6.0);
   ax.assign(2 * m, 0.0);
@@ -31,6 +31,7 @@ static void small_model(int m, std::vector<double>& ax, std::vector<double>& Wt,
     }
   alpha.assign(m, 0.0);
   for (int i = 0; i < m; ++i) alpha[i] = 0.1 * std::sin(1.0 + i);
+  if (L_out) *L_out = L;
 }
 
 // Detector self-test: a kernel with a barrier missing between a shared write and the other threads' reads.
@@ -99,6 +100,19 @@ int main(int argc, char** argv) {
                      n_sel.data(), n_model.data(), err.data(), mu.data(), var.data(), flags.data());
     std::printf("batch fast=%d n_sel=%d,%d picks %lld %lld %lld\n", fast, n_sel[0], n_sel[1], ids[1], ids[2], ids[K + 1]);
     if (err[0] || err[1]) return 1;
+  }
+  // 4. dense prediction: factor inverse by columns (warp-synchronous), alpha, the double-buffered fused
+  //    prediction kernel; 40 rows (partial k-chunk), 45 queries (two query tiles, one partial)
+  {
+    const int m = 40, nq = 45;
+    std::vector<double> ax, Wt, alpha, L, g(m), q(2 * nq), mean(nq), var(nq), nrm(2 * nq);
+    small_model(m, ax, Wt, 256, alpha, 1.7, 0.05, &L);
+    for (int i = 0; i < m; ++i) g[i] = 0.3 * std::cos(0.7 * i);
+    for (int i = 0; i < nq; ++i) { q[i] = 0.13 * i; q[nq + i] = 5.9 - 0.12 * i; }
+    const double mw[3] = {0.01, -0.02, 0.0};
+    emu_predict(2, 0, m, m, ax.data(), L.data(), m, g.data(), q.data(), nq, 1.7, 1.0, mw, 0.1, 1, mean.data(), var.data(),
+                nrm.data(), nullptr);
+    std::printf("predict mean0=%.6f var0=%.6f\n", mean[0], var[0]);
   }
   std::printf("race_check done\n");
   return 0;

@@ -20,7 +20,8 @@ EMU_DEPS = [os.path.join(EMU_DIR, "emu_sample.cpp"), os.path.join(EMU_DIR, "cuda
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_sample.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch.cuh"),
-            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_launch.cuh")]
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_launch.cuh"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_predict.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -260,3 +261,58 @@ def test_emulated_batch_kernel_early_stop_and_k_one(emu):
     ids, n_sel, n_model, err, mu, var, flags = run_emu_batch(emu, dims, [tsdf], 3, 1, hyp, train, 1)
     assert n_sel[0] == 1 and ids[0, 0] == 3 and n_model[0] == 0
     assert np.all(var[0] == 1.0) and flags[0, 3] == 1 and flags[0].sum() == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# gpis_predict.cuh: factor inverse by columns, alpha, fused dense prediction (gp_mean / diag gp_cov)
+# ------------------------------------------------------------------------------------------------
+def run_emu_predict(lib, gp, query, want_nrm):
+    vp = C.c_void_p
+    lib.emu_predict.restype = C.c_int
+    lib.emu_predict.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, C.c_longlong, C.c_double,
+                                C.c_double, vp, C.c_double, C.c_int, vp, vp, vp, vp]
+    D, R, m = gp.D, gp.r, gp.m
+    L = np.ascontiguousarray(gp.L[:max(R, 1), :max(R, 1)])
+    g = np.ascontiguousarray(gp.g[:max(R, 1)])
+    AX = np.ascontiguousarray(gp.X[:max(m, 1)].T)
+    q = np.ascontiguousarray(np.asarray(query, np.float64).T)
+    nq = q.shape[1]
+    mean, var, nrm, alpha = np.empty(nq), np.empty(nq), np.empty((D, nq)), np.empty(max(R, 1))
+    mw = np.ascontiguousarray(gp.hm[:D])
+    p = lambda a: a.ctypes.data_as(vp)
+    rc = lib.emu_predict(D, int(gp.use_grad), R, AX.shape[1], p(AX), p(L), L.shape[1], p(g), p(q), nq,
+                         float(np.sqrt(gp.ell2)), gp.sf2, p(mw), float(gp.hm[D]), int(want_nrm), p(mean), p(var), p(nrm),
+                         p(alpha))
+    assert rc == 0
+    return mean, var, nrm.T, alpha[:R]
+
+
+def test_emulated_predict_kernel_matches_the_stored_predgrid(emu):
+    """The reference's stored loofa gpModel (126 points with normals = 378 rows: two super-blocks of the
+    triangular GEMM) predicted at 40 points of its stored predGrid: TSDF, normals and variance against the
+    reference's own numbers, alpha against the stored gpModel.alpha."""
+    g = load_golden("loofa")
+    hyp, X, y, dy, beta = golden_model(g)
+    gp = incremental(hyp, X, y, dy, beta, True)
+    sel = np.arange(3, 625, 16)[:40]
+    mean, var, nrm, alpha = run_emu_predict(emu, gp, g["pred_points"][sel], True)
+    assert np.max(np.abs(mean - g["pred_tsdf"][sel])) < 1e-10
+    assert np.max(np.abs(var - g["pred_noise"][sel])) < 1e-10
+    assert np.max(np.abs(nrm - g["pred_normals"][sel])) < 1e-10
+    m, D = X.shape
+    a = alpha.reshape(m, D + 1)                                   # point-major -> the reference's dimension-major
+    a_dm = np.concatenate([a[:, 0]] + [a[:, 1 + d] for d in range(D)])
+    assert np.max(np.abs(a_dm - g["model_alpha"])) / np.max(np.abs(g["model_alpha"])) < 1e-9
+
+
+def test_emulated_predict_kernel_3d_function_only_ragged(emu):
+    """3-D, function values only, 45 rows (a partial k-chunk) and 37 queries (a partial query tile)."""
+    rng = np.random.default_rng(9)
+    X = rng.uniform(0, 5, (45, 3))
+    y = np.linalg.norm(X - 2.4, axis=1) - 1.5
+    hyp = {"cov": np.array([np.log(1.6), np.log(1.2)]), "mean": np.array([0.02, 0.0, -0.01, 0.1]), "lik": 0.5 * np.log(0.02)}
+    gp = incremental(hyp, X, y, None, np.exp(2 * hyp["lik"]), False)
+    q = rng.uniform(0, 5, (37, 3))
+    mean, var, nrm, _ = run_emu_predict(emu, gp, q, True)
+    fm, fv, fn = O.predict_points(gp, q, want_normals=True)
+    assert np.max(np.abs(mean - fm)) < 1e-11 and np.max(np.abs(var - fv)) < 1e-11 and np.max(np.abs(nrm - fn)) < 1e-11
