@@ -5,6 +5,7 @@
 // rule, se_cov_derivative.m for the covariance blocks; the reference GPU path
 // (gpu_active_set_selector.cpp:499-560) refactorises and re-solves everything each step.
 #pragma once
+#include "gpis_launch.cuh"
 #include "gpis_common.cuh"
 
 namespace gpis {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
 // ---------------------------------------------------------------------------------------
 template <int NB, int D>
 __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(EngineParams P) {
-  extern __shared__ double s_ell[];                 // [NB][ell_chunk]
+  GPIS_DYN_SMEM_F64(s_ell);                         // [NB][ell_chunk]
   __shared__ double s_red[UPD_WARPS][NB][TW];
   __shared__ BlockBest s_best[2];
   __shared__ int s_flag, s_cnt;

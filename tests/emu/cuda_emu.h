@@ -86,6 +86,30 @@ inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence_block() {}
 inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+// warp collectives over all 32 lanes: every lane publishes its value, then reads what it needs
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  emu::WarpBox* w = emu::my_warp;
+  unsigned long long bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  w->slot[emu::my_lane] = bits;
+  w->bar.arrive_and_wait();
+  const unsigned long long other = w->slot[src_lane & 31];
+  w->bar.arrive_and_wait();
+  T out;
+  memcpy(&out, &other, sizeof(T));
+  return out;
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+  emu::WarpBox* w = emu::my_warp;
+  w->slot[emu::my_lane] = pred ? 1ull : 0ull;
+  w->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m |= (unsigned)(w->slot[l] & 1ull) << l;
+  w->bar.arrive_and_wait();
+  return m;
+}
 // warp shuffle over all 32 lanes: every lane publishes its value, reads its partner's
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
@@ -103,6 +127,15 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   return out;
 }
 inline int atomicCAS(int* p, int cmp, int val) { return __sync_val_compare_and_swap(p, cmp, val); }
+inline int atomicAdd(int* p, int v) { return __sync_fetch_and_add(p, v); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __sync_fetch_and_add(p, v); }
+inline int atomicOr(int* p, int v) { return __sync_fetch_and_or(p, v); }
+inline void __threadfence() { __sync_synchronize(); }
+inline void __threadfence_system() { __sync_synchronize(); }
+inline long long clock64() { return 0; }
+inline void __nanosleep(unsigned) {}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 
 namespace gpis {
 // cp.async stand-ins: the copy happens at once, commit / wait are no-ops (a superset of the allowed

@@ -129,3 +129,96 @@ extern "C" int emu_predict(int D, int grad, int R, int m, const double* AX, cons
   if (alpha_out) memcpy(alpha_out, alpha.data(), sizeof(double) * R);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// gpis_select.cuh: the panel backend's selection loop (arbitrary candidate points, factor panels in
+// memory) -- buffers and launches as gpis_create / gpis_set_candidates / gpis_select set them up
+// ---------------------------------------------------------------------------------------------
+#include "../../gpis_b200/csrc/gpis_select.cuh"
+
+template <int NB, int D>
+static void emu_panel_steps(const EngineParams& P, int K, int n_ctas, size_t upd_smem) {
+  auto ka = k_append<NB, D>;
+  auto ku = k_update<NB, D>;
+  for (int it = 0; it < K - 1; ++it) {
+    GPIS_LAUNCH(ka, dim3(1), dim3(APP_THREADS), nullptr, P, 0, 0);
+    GPIS_LAUNCH_SMEM(ku, dim3((unsigned)n_ctas), dim3(UPD_THREADS), upd_smem, nullptr, P);
+  }
+  GPIS_LAUNCH(ka, dim3(1), dim3(APP_THREADS), nullptr, P, 0, 1);      // gpis_select_end: record the last pick
+}
+
+extern "C" int emu_panel_select(int D, int grad, long long N, const double* pts, const double* tsdf,
+                                const double* normals, const double* noise, int K, long long first, double ell,
+                                double sf2, const double* mean_w, double mean_c, double noise_scalar, double level,
+                                double eps, double beta, int n_ctas, long long* ids, int* n_sel, int* n_model, int* err,
+                                double* mu, double* var, unsigned char* flags, double* L_out, double* g_out) {
+  const int NB = grad ? D + 1 : 1;
+  EngineParams P;
+  memset(&P, 0, sizeof(P));
+  P.N = N;
+  P.N_total = N;
+  P.n_tiles = (int)((N + TW - 1) / TW);
+  P.M_cap = K;
+  P.R_cap = K * NB;
+  P.tile_stride = (long long)P.R_cap * TW;
+  P.world = 1;
+  P.inv_ell2 = 1.0 / (ell * ell);
+  P.sf2 = sf2;
+  P.level = level;
+  P.eps = eps;
+  P.beta = beta;
+  P.noise_scalar = noise_scalar;
+  for (int d = 0; d < D; ++d) P.mean_w[d] = mean_w[d];
+  P.mean_c = mean_c;
+  P.pay_stride = PAY_HDR + P.R_cap;
+  std::vector<double> V((size_t)P.n_tiles * P.tile_stride, 0.0), amb(N), L((size_t)P.R_cap * P.R_cap, 0.0), g(P.R_cap, 0.0),
+      ax((size_t)MAXD * P.M_cap, 0.0), pay(P.pay_stride, 0.0);
+  std::vector<int> live0(P.n_tiles + 1), live1(P.n_tiles + 1), hist(3 * ((size_t)P.M_cap + 1), 0);
+  std::vector<long long> sel(P.M_cap + 1, -1);
+  std::vector<BlockBest> partials(n_ctas);
+  DevState st;
+  memset(&st, 0, sizeof(st));
+  for (int d = 0; d < D; ++d) {
+    P.cx[d] = pts + (size_t)d * N;
+    P.nrm[d] = normals ? normals + (size_t)d * N : nullptr;
+    P.AX[d] = ax.data() + (size_t)d * P.M_cap;
+  }
+  P.tsdf = tsdf;
+  P.noise = noise;
+  P.V = V.data();
+  P.mu = mu;
+  P.var = var;
+  P.amb = amb.data();
+  P.flags = flags;
+  P.live[0] = live0.data();
+  P.live[1] = live1.data();
+  P.L = L.data();
+  P.g = g.data();
+  P.sel_ids = sel.data();
+  P.st = &st;
+  P.hist = hist.data();
+  P.partials = partials.data();
+  P.pay_send = pay.data();
+  P.pay_recv = pay.data();
+  const size_t max_ell = (size_t)96 * 1024 / (sizeof(double) * NB);
+  P.ell_chunk = (int)std::min<size_t>((size_t)P.R_cap, max_ell);
+  const size_t upd_smem = sizeof(double) * NB * (size_t)P.ell_chunk;
+  const long long n = std::max<long long>(P.N, P.n_tiles);
+  GPIS_LAUNCH(k_init_candidates, dim3((unsigned)((n + 255) / 256)), dim3(256), nullptr, P);
+  GPIS_LAUNCH(k_begin, dim3(1), dim3(32), nullptr, P, first, 1u);
+  switch (D * 2 + (grad ? 1 : 0)) {
+    case 2: emu_panel_steps<1, 1>(P, K, n_ctas, upd_smem); break;
+    case 3: emu_panel_steps<2, 1>(P, K, n_ctas, upd_smem); break;
+    case 4: emu_panel_steps<1, 2>(P, K, n_ctas, upd_smem); break;
+    case 5: emu_panel_steps<3, 2>(P, K, n_ctas, upd_smem); break;
+    case 6: emu_panel_steps<1, 3>(P, K, n_ctas, upd_smem); break;
+    default: emu_panel_steps<4, 3>(P, K, n_ctas, upd_smem); break;
+  }
+  *n_sel = st.n_sel;
+  *n_model = st.m;
+  *err = st.err;
+  for (int i = 0; i < st.n_sel; ++i) ids[i] = sel[i];
+  if (L_out) memcpy(L_out, L.data(), sizeof(double) * L.size());
+  if (g_out) memcpy(g_out, g.data(), sizeof(double) * g.size());
+  return 0;
+}

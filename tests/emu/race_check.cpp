@@ -114,6 +114,32 @@ int main(int argc, char** argv) {
                 nrm.data(), nullptr);
     std::printf("predict mean0=%.6f var0=%.6f\n", mean[0], var[0]);
   }
+  // 5. panel backend: k_init_candidates, k_begin, (k_append, k_update) x 7, final k_append; 2-D points with
+  //    gradient observations (3 rows per point: blocked forward substitution), 150 candidates in 3 tiles
+  {
+    const long long N = 150;
+    const int K = 8;
+    std::vector<double> pts(2 * N), tsdf(N), nrm(2 * N), mu(N), var(N), L((size_t)K * 3 * K * 3), g(K * 3);
+    std::vector<unsigned char> flags(N);
+    std::vector<long long> ids(K + 1);
+    for (long long j = 0; j < N; ++j) {
+      const double x = 0.37 * (double)(j % 15) + 0.01 * std::sin(3.1 * j), y = 0.41 * (double)(j / 15) + 0.01 * std::cos(1.7 * j);
+      const double rr = std::sqrt((x - 2.6) * (x - 2.6) + (y - 2.0) * (y - 2.0));
+      pts[j] = x;
+      pts[N + j] = y;
+      double sd = (rr - 1.4) / 1.2;
+      sd = sd > 1 ? 1 : (sd < -1 ? -1 : sd);
+      tsdf[j] = sd + 1e-3 * std::sin(12.9898 * (double)j);
+      nrm[j] = rr > 1e-9 ? (x - 2.6) / rr / 1.2 : 0.0;
+      nrm[N + j] = rr > 1e-9 ? (y - 2.0) / rr / 1.2 : 0.0;
+    }
+    const double mw[3] = {0, 0, 0};
+    int n_sel = 0, n_model = 0, err = 0;
+    emu_panel_select(2, 1, N, pts.data(), tsdf.data(), nrm.data(), nullptr, K, 17, 1.8, 1.0, mw, 0.0, 0.01, 0.0, 1e-2, 10.0, 2,
+                     ids.data(), &n_sel, &n_model, &err, mu.data(), var.data(), flags.data(), L.data(), g.data());
+    std::printf("panel n_sel=%d n_model=%d err=%d pick1=%lld\n", n_sel, n_model, err, ids[1]);
+    if (err) return 1;
+  }
   std::printf("race_check done\n");
   return 0;
 }

@@ -21,7 +21,8 @@ EMU_DEPS = [os.path.join(EMU_DIR, "emu_sample.cpp"), os.path.join(EMU_DIR, "cuda
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_launch.cuh"),
-            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_predict.cuh")]
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_predict.cuh"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_select.cuh")]
 
 
 @pytest.fixture(scope="module")
@@ -316,3 +317,75 @@ def test_emulated_predict_kernel_3d_function_only_ragged(emu):
     mean, var, nrm, _ = run_emu_predict(emu, gp, q, True)
     fm, fv, fn = O.predict_points(gp, q, want_normals=True)
     assert np.max(np.abs(mean - fm)) < 1e-11 and np.max(np.abs(var - fv)) < 1e-11 and np.max(np.abs(nrm - fn)) < 1e-11
+
+
+# ------------------------------------------------------------------------------------------------
+# gpis_select.cuh: the panel backend's selection loop (arbitrary points, gradient observations)
+# ------------------------------------------------------------------------------------------------
+def run_emu_panel(lib, shape, train, first, hyp, n_ctas=3):
+    vp = C.c_void_p
+    lib.emu_panel_select.restype = C.c_int
+    lib.emu_panel_select.argtypes = [C.c_int, C.c_int, C.c_longlong, vp, vp, vp, vp, C.c_int, C.c_longlong] + \
+        [C.c_double] * 2 + [vp] + [C.c_double] * 5 + [C.c_int] + [vp] * 9
+    pts = np.asarray(shape["points"], np.float64)
+    N, D = pts.shape
+    use_grad = shape.get("normals") is not None and np.size(shape["normals"]) > 0
+    use_noise = shape.get("noise") is not None and np.size(shape["noise"]) > 0
+    K = int(train["activeSetSize"])
+    nb = D + 1 if use_grad else 1
+    P = np.ascontiguousarray(pts.T)
+    t = np.ascontiguousarray(np.asarray(shape["tsdf"], np.float64).reshape(-1))
+    nr = np.ascontiguousarray(np.asarray(shape["normals"], np.float64).reshape(N, D).T) if use_grad else None
+    nz = np.ascontiguousarray(np.asarray(shape["noise"], np.float64).reshape(-1)) if use_noise else None
+    ids = np.full(K + 1, -1, np.int64)
+    n_sel, n_model, err = C.c_int(), C.c_int(), C.c_int()
+    mu, var, flags = np.empty(N), np.empty(N), np.empty(N, np.uint8)
+    L, g = np.empty((K * nb, K * nb)), np.empty(K * nb)
+    mw = np.ascontiguousarray(np.asarray(hyp["mean"], np.float64)[:D])
+    p = lambda a: a.ctypes.data_as(vp) if a is not None else None
+    rc = lib.emu_panel_select(D, int(use_grad), N, p(P), p(t), p(nr), p(nz), K, int(first), float(np.exp(hyp["cov"][0])),
+                              float(np.exp(2 * hyp["cov"][1])), p(mw), float(hyp["mean"][D]), float(np.exp(2 * hyp["lik"])),
+                              float(train["levelSet"]), float(train["eps"]), float(train["beta"]), n_ctas, p(ids),
+                              C.byref(n_sel), C.byref(n_model), C.byref(err), p(mu), p(var), p(flags), p(L), p(g))
+    assert rc == 0
+    return ids[:n_sel.value], n_model.value, err.value, mu, var, flags, L, g
+
+
+def test_emulated_panel_backend_on_the_reference_tape_shape(emu):
+    """BASELINE config 1 in kind: the reference's stored 2-D `tape` shape (508 candidates, normals,
+    per-point noise) through k_append / k_update -- first 30 picks, factor, g, level-set masks and the
+    posterior of the unclassified candidates against the incremental oracle."""
+    g = load_golden("results_tape")
+    shape = {"points": g["shape_points"], "tsdf": g["shape_tsdf"], "normals": g["shape_normals"], "noise": g["shape_noise"]}
+    train = {"activeSetSize": 30, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    hyp = O.default_hyp(2)
+    ora = O.select_straddle_incremental(shape, train, 17, hyp=hyp)
+    ids, n_model, err, mu, var, flags, L, gv = run_emu_panel(emu, shape, train, 17, hyp)
+    assert err == 0 and np.array_equal(ids, ora["order"]) and n_model == ora["n_in_model"] == 29
+    r = ora["gp"].r
+    assert np.max(np.abs(L[:r, :r] - ora["gp"].L[:r, :r])) < 1e-11 and np.max(np.abs(gv[:r] - ora["gp"].g[:r])) < 1e-11
+    assert np.array_equal((flags & 1) > 0, ora["active"])
+    assert np.array_equal((flags & 2) > 0, ora["high"]) and np.array_equal((flags & 4) > 0, ora["low"])
+    live = (flags == 0)
+    fm, fv, _ = O.predict_points(ora["gp"], shape["points"][live])
+    assert live.sum() > 50 and np.max(np.abs(mu[live] - fm)) < 1e-10 and np.max(np.abs(var[live] - fv)) < 1e-10
+
+
+def test_emulated_panel_backend_3d_function_only_with_dead_tiles(emu):
+    """3-D points in random order (not a lattice), function values only, several CTAs; candidates far from
+    the level set classify early, so whole 64-candidate tiles drop out of the live list."""
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(0, 9, (700, 3))
+    pts = pts[np.argsort(np.linalg.norm(pts - 4.5, axis=1))]            # tiles of similar radius
+    tsdf = np.clip((np.linalg.norm(pts - 4.5, axis=1) - 2.5) / 1.5, -1, 1) + 1e-3 * rng.standard_normal(700)
+    shape = {"points": pts, "tsdf": tsdf, "normals": None, "noise": None}
+    hyp = {"cov": np.array([np.log(1.5), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.02)}
+    train = {"activeSetSize": 45, "beta": 4.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental(shape, train, 123, hyp=hyp)
+    ids, n_model, err, mu, var, flags, L, gv = run_emu_panel(emu, shape, train, 123, hyp, n_ctas=4)
+    assert err == 0 and np.array_equal(ids, ora["order"]) and n_model == ora["n_in_model"]
+    assert np.array_equal((flags & 2) > 0, ora["high"]) and np.array_equal((flags & 4) > 0, ora["low"])
+    live = (flags == 0)
+    fm, fv, _ = O.predict_points(ora["gp"], pts[live])
+    assert np.max(np.abs(mu[live] - fm)) < 1e-10 and np.max(np.abs(var[live] - fv)) < 1e-10
+    assert ((flags & 6) > 0).sum() > 128                                # enough classified to retire tiles
