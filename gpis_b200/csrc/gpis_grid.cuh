@@ -10,6 +10,7 @@
 // V is never stored: the per-step HBM traffic drops from 8*N*r bytes (panel backend) to the
 // posterior arrays (~42 bytes per candidate), and the step becomes compute-bound.
 #pragma once
+#include "gpis_launch.cuh"
 #include "gpis_common.cuh"
 #include "gpis_select.cuh"
 
@@ -24,10 +25,12 @@ constexpr int GSOLVE_THREADS = 256;
 constexpr int GSU = 16;         // independent 256-byte row segments in flight per warp in the W passes
 
 
+#ifndef GPIS_EMULATE   // tests/emu supplies stand-ins for the inline-PTX helpers (test infrastructure only)
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+#endif
 // Internal layout of the per-candidate state (mu, var, ambiguity, flags) in the grid backend:
 // tile-major, and inside a 128x128 tile the order of the update GEMM's accumulator fragments,
 // so that the epilogue streams it with fully coalesced 16-byte accesses.
@@ -98,6 +101,8 @@ __global__ void k_grid_export(EngineParams P, double* mu, double* var, double* a
   if (flags) flags[jl] = P.flags[slot];
 }
 
+#define GPIS_ISSUE_FENCE() asm volatile("" ::: "memory")
+#ifndef GPIS_EMULATE
 __device__ __forceinline__ void g_cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -111,7 +116,6 @@ __device__ __forceinline__ double ld_nc_f64(const double* p) {
   asm volatile("ld.global.nc.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
   return v;
 }
-#define GPIS_ISSUE_FENCE() asm volatile("" ::: "memory")
 
 template <int N>
 __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
@@ -141,6 +145,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// after mbarrier.init, before the barriers are used by the async proxy
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+#endif
 
 __device__ __forceinline__ int pick_winner(const EngineParams& P, const double* recs) {
   int win = -1;
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
 // ---------------------------------------------------------------------------------------
 template <int NB, int D, bool FUSED>
 __global__ void __launch_bounds__(GSOLVE_THREADS) k_grid_solve(EngineParams P) {
-  extern __shared__ double s_kv[];                   // FUSED: [NB][R_cap]
+  GPIS_DYN_SMEM_F64(s_kv);                           // FUSED: [NB][R_cap]
   DevState* st = P.st;
   if (st->done) return;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -365,7 +375,7 @@ constexpr int GS1_RMAX = GS1_CPT * GSOLVE_THREADS;
 
 template <int D>
 __global__ void __launch_bounds__(GSOLVE_THREADS, 2) k_grid_solve1(EngineParams P) {
-  extern __shared__ double s_kv[];                   // [GS1_RMAX]
+  GPIS_DYN_SMEM_F64(s_kv);                           // [GS1_RMAX]
   __shared__ double s_red[2][GSOLVE_THREADS / 32];
   __shared__ int s_win;
   DevState* st = P.st;
@@ -535,7 +545,7 @@ constexpr size_t GS2_SMEM = sizeof(double) * GS1_RMAX * (1 + GS2_STAGES) + 8 * G
 
 template <int D>
 __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams P) {
-  extern __shared__ __align__(16) double s_dyn[];
+  GPIS_DYN_SMEM_F64A(s_dyn);
   double* s_kv = s_dyn;                               // [GS1_RMAX]
   double* ring = s_dyn + GS1_RMAX;                    // [GS2_STAGES][GS1_RMAX]
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)GS2_STAGES * GS1_RMAX);
@@ -586,8 +596,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams 
   const int my_rows = (!book && (int)blockIdx.x < r0) ? (r0 - 1 - (int)blockIdx.x) / G + 1 : 0;   // rows blockIdx.x + i*G
   if (tid == 0) {
     for (int i = 0; i < GS2_STAGES; ++i) mbar_init(&full[i], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_init_fence();
   }
   __syncthreads();
   auto issue = [&](int i) {          // thread 0: row i of this CTA into ring slot i % STAGES
@@ -864,7 +873,7 @@ __device__ __forceinline__ int unit_owner(long long u, long long U, int G) {
 
 template <int NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
-  extern __shared__ __align__(16) double g_smem[];
+  GPIS_DYN_SMEM_F64A(g_smem);
   const DevState* st = P.st;
   if (st->done) return;
   unsigned long long* full = reinterpret_cast<unsigned long long*>(g_smem + (size_t)GPIPE * GSTAGE_DOUBLES);
@@ -872,8 +881,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int i = 0; i < GPIPE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], GEMM_CWARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    mbar_init_fence();
   }
   __syncthreads();
   const int r0 = st->r0;
