@@ -1,5 +1,9 @@
 // C ABI of the GPIS engine (include/gpis_b200.h): host-side orchestration only.
+#ifdef GPIS_EMULATE   // tests/emu: this file compiled by g++ against a CPU emulation of the CUDA runtime and
+#include "cuda_rt_emu.h"   // execution model -- test infrastructure only, the shipped library never defines it
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -12,7 +16,16 @@
 #include "../../include/gpis_b200.h"
 #include "gpis_common.cuh"
 #include "gpis_grid.cuh"
+#ifndef GPIS_EMULATE
 #include "gpis_grid_tf32.cuh"
+#else   // tcgen05 / TMEM are not emulated: GPIS_PREC_TF32 is rejected by gpis_create in that build
+namespace gpis {
+constexpr int TF32_THREADS = 32, TKC = 32, TZ = 2;
+constexpr size_t TF32_SMEM = 0;
+template <int NB>
+void k_grid_gemm_tf32(EngineParams) {}
+}  // namespace gpis
+#endif
 #include "gpis_predict.cuh"
 #include "gpis_batch.cuh"
 #include "gpis_sample.cuh"
@@ -130,33 +143,33 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2 && !external) {
     if (finalize_only) {
-      d.g_point<<<1, 1024, 0, s>>>(e->P, 1);
+      GPIS_LAUNCH_SMEM(d.g_point, 1, 1024, 0, s, e->P, 1);
       e->launches++;
     } else {
       if (e->onepass) {
         if (e->solve_ring) {      // solve + grid barrier + new row of W in ONE launch (one CTA per SM)
-          d.g_solve2<<<e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s>>>(e->P);
+          GPIS_LAUNCH_SMEM(d.g_solve2, e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s, e->P);
           e->launches += 1;
         } else {
-          d.g_solve1<<<e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s>>>(e->P);
-          k_grid_wrow1<<<e->num_sms, GSOLVE_THREADS, 0, s>>>(e->P, e->solve1_ctas);
+          GPIS_LAUNCH_SMEM(d.g_solve1, e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s, e->P);
+          GPIS_LAUNCH_SMEM(k_grid_wrow1, e->num_sms, GSOLVE_THREADS, 0, s, e->P, e->solve1_ctas);
           e->launches += 2;
         }
         CU(cudaGetLastError());
         return GPIS_OK;
       }
       if (e->fused_solve) {
-        d.g_solve_fused<<<e->solve_ctas + 1, GSOLVE_THREADS, e->solve_smem, s>>>(e->P);
+        GPIS_LAUNCH_SMEM(d.g_solve_fused, e->solve_ctas + 1, GSOLVE_THREADS, e->solve_smem, s, e->P);
       } else {
-        d.g_point<<<1, 1024, 0, s>>>(e->P, 0);
-        d.g_solve<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+        GPIS_LAUNCH_SMEM(d.g_point, 1, 1024, 0, s, e->P, 0);
+        GPIS_LAUNCH_SMEM(d.g_solve, e->solve_ctas, GSOLVE_THREADS, 0, s, e->P);
         e->launches++;
       }
-      d.g_wrow<<<e->solve_ctas, GSOLVE_THREADS, 0, s>>>(e->P);
+      GPIS_LAUNCH_SMEM(d.g_wrow, e->solve_ctas, GSOLVE_THREADS, 0, s, e->P);
       e->launches += 2;
     }
   } else {
-    d.append<<<1, APP_THREADS, 0, s>>>(e->P, external, finalize_only);
+    GPIS_LAUNCH_SMEM(d.append, 1, APP_THREADS, 0, s, e->P, external, finalize_only);
     e->launches++;
   }
   CU(cudaGetLastError());
@@ -166,13 +179,13 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
 gpis_status launch_update(gpis_engine* e, cudaStream_t s, cudaEvent_t mid = nullptr) {
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2) {
-    if (e->cfg.precision == GPIS_PREC_TF32) d.g_gemm_tf32<<<e->P.gemm_ctas, TF32_THREADS, TF32_SMEM, s>>>(e->P);
-    else d.g_gemm<<<e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s>>>(e->P);
+    if (e->cfg.precision == GPIS_PREC_TF32) GPIS_LAUNCH_SMEM(d.g_gemm_tf32, e->P.gemm_ctas, TF32_THREADS, TF32_SMEM, s, e->P);
+    else GPIS_LAUNCH_SMEM(d.g_gemm, e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s, e->P);
     if (mid) cudaEventRecord(mid, s);
-    d.g_epi<<<GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s>>>(e->P);
+    GPIS_LAUNCH_SMEM(d.g_epi, GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s, e->P);
     e->launches += 2;
   } else {
-    d.update<<<e->upd_grid, UPD_THREADS, e->upd_smem, s>>>(e->P);
+    GPIS_LAUNCH_SMEM(d.update, e->upd_grid, UPD_THREADS, e->upd_smem, s, e->P);
     e->launches++;
   }
   CU(cudaGetLastError());
@@ -202,15 +215,15 @@ gpis_status ensure_inverse(gpis_engine* e, cudaStream_t s) {
     const int blocks = (R * 32 + 255) / 256;
     if (have_w && !have_wt) {
       dim3 tg((R + 31) / 32, (R + 31) / 32);
-      k_transpose_lower<<<tg, dim3(32, 8), 0, s>>>(e->P.W, e->d_Wt, e->ldw, R);
+      GPIS_LAUNCH_SMEM(k_transpose_lower, tg, dim3(32, 8), 0, s, e->P.W, e->d_Wt, e->ldw, R);
       CU(cudaGetLastError());
       e->launches++;
     } else if (!have_wt) {
-      k_invert_factor<<<blocks, 256, 0, s>>>(e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
+      GPIS_LAUNCH_SMEM(k_invert_factor, blocks, 256, 0, s, e->P.L, e->P.R_cap, R, e->d_Wt, e->ldw);
       CU(cudaGetLastError());
       e->launches++;
     }
-    k_alpha<<<blocks, 256, 0, s>>>(e->d_Wt, e->ldw, e->P.g, R, e->d_alpha);
+    GPIS_LAUNCH_SMEM(k_alpha, blocks, 256, 0, s, e->d_Wt, e->ldw, e->P.g, R, e->d_alpha);
     CU(cudaGetLastError());
     e->launches += 1;
   }
@@ -247,6 +260,9 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
   if (!(cfg->ell > 0.0) || !(cfg->sf2 > 0.0) || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
     return GPIS_ERR_INVALID;
   if (cfg->precision != GPIS_PREC_FP64 && cfg->precision != GPIS_PREC_TF32) return GPIS_ERR_INVALID;
+#ifdef GPIS_EMULATE
+  if (cfg->precision == GPIS_PREC_TF32) return GPIS_ERR_INVALID;      // tcgen05 is not emulated
+#endif
   if (cfg->num_candidates > 0x7fffffffLL * TW / 2) return GPIS_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GPIS_ERR_NO_DEVICE; }
@@ -341,6 +357,9 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
     e->onepass = (NB == 1) && P.R_cap <= GS1_RMAX && getenv("GPIS_TWO_PASS") == nullptr;
     e->solve_ring = getenv("GPIS_SOLVE_REGS") == nullptr;       // rows of W through a bulk-copy smem ring
+#ifdef GPIS_EMULATE
+    e->solve_ring = false;      // the ring form ends in an in-kernel grid barrier; emulated blocks run one after another
+#endif
     e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
     if (e->onepass) {
       CU(cudaFuncSetAttribute((const void*)disp.g_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS2_SMEM));
@@ -527,11 +546,11 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = std::max<long long>(e->P.N, e->P.n_tiles);
   if (e->backend == 2) {
-    k_grid_init_state<<<(unsigned)((e->grid_slots + 255) / 256), 256, 0, s>>>(e->P, (long long)e->grid_slots);
+    GPIS_LAUNCH_SMEM(k_grid_init_state, (unsigned)((e->grid_slots + 255) / 256), 256, 0, s, e->P, (long long)e->grid_slots);
     CU(cudaGetLastError());
     e->launches++;
   } else if (n > 0) {
-    k_init_candidates<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(e->P);
+    GPIS_LAUNCH_SMEM(k_init_candidates, (unsigned)((n + 255) / 256), 256, 0, s, e->P);
     CU(cudaGetLastError());
     e->launches++;
   }
@@ -544,12 +563,12 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
       if (e->P.Tf[d]) CU(cudaMemsetAsync(e->P.Tf[d], 0, e->table_bytes[d] / 2, s));
       if (d >= e->D) {    // unused axes: constant-one tables
         const long long rows = e->rk_pad + GKC;
-        k_fill_ones_col0<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(e->P.T[d], e->P.Tf[d], e->P.ldt[d], rows);
+        GPIS_LAUNCH_SMEM(k_fill_ones_col0, (unsigned)((rows + 255) / 256), 256, 0, s, e->P.T[d], e->P.Tf[d], e->P.ldt[d], rows);
         e->launches++;
       }
     }
   }
-  k_begin<<<1, 32, 0, s>>>(e->P, first_local < 0 ? -1 : first_local, ++e->epoch);
+  GPIS_LAUNCH_SMEM(k_begin, 1, 32, 0, s, e->P, first_local < 0 ? -1 : first_local, ++e->epoch);
   CU(cudaGetLastError());
   e->launches++;
   e->selecting = true;
@@ -765,7 +784,7 @@ gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const
   {
     EngineParams q = e->P;
     q.peer_mode = 0;
-    k_begin<<<1, 32, 0, s>>>(q, -1, ++e->epoch);
+    GPIS_LAUNCH_SMEM(k_begin, 1, 32, 0, s, q, -1, ++e->epoch);
   }
   CU(cudaGetLastError());
   e->launches++;
@@ -851,7 +870,7 @@ gpis_status gpis_predict(gpis_handle e, const double* query, int64_t nq, double*
   Q.mean_c = e->P.mean_c;
   Dispatch disp = get_dispatch(D, e->NB > 1);
   cudaEventRecord(e->ev0, s);
-  disp.predict<<<(unsigned)((nq + PQ - 1) / PQ), PRED_THREADS, PRED_SMEM, s>>>(Q);
+  GPIS_LAUNCH_SMEM(disp.predict, (unsigned)((nq + PQ - 1) / PQ), PRED_THREADS, PRED_SMEM, s, Q);
   cudaError_t ce = cudaGetLastError();
   e->launches++;
   cudaEventRecord(e->ev1, s);
@@ -1159,7 +1178,7 @@ gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, u
   const double* amb_src = e->P.amb;
   const unsigned char* flag_src = e->P.flags;
   if (ce == cudaSuccess && e->backend == 2) {     // state is stored in tile/fragment order: export it
-    k_grid_export<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P, nullptr, nullptr, tmp_amb, tmp + 3 * N);
+    GPIS_LAUNCH_SMEM(k_grid_export, (unsigned)((N + 255) / 256), 256, 0, s, e->P, nullptr, nullptr, tmp_amb, tmp + 3 * N);
     e->launches++;
     amb_src = tmp_amb;
     flag_src = tmp + 3 * N;
@@ -1167,7 +1186,7 @@ gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, u
   }
   if (ce == cudaSuccess && ambiguity) ce = cudaMemcpyAsync(ambiguity, amb_src, sizeof(double) * N, cudaMemcpyDefault, s);
   if (ce == cudaSuccess && (high || low || active)) {
-    k_split_flags<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(flag_src, (long long)N, tmp, tmp + N, tmp + 2 * N);
+    GPIS_LAUNCH_SMEM(k_split_flags, (unsigned)((N + 255) / 256), 256, 0, s, flag_src, (long long)N, tmp, tmp + N, tmp + 2 * N);
     e->launches++;
     ce = cudaGetLastError();
     if (ce == cudaSuccess && high) ce = cudaMemcpyAsync(high, tmp, N, cudaMemcpyDefault, s);
@@ -1197,7 +1216,7 @@ gpis_status gpis_get_candidate_posterior(gpis_handle e, double* mean, double* va
     const bool dev = on_device(mean) && on_device(var);
     double* tmp = nullptr;
     if (!dev) CU(cudaMalloc(&tmp, sizeof(double) * 2 * N));
-    k_grid_export<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(e->P, dev ? mean : tmp, dev ? var : tmp + N, nullptr, nullptr);
+    GPIS_LAUNCH_SMEM(k_grid_export, (unsigned)((N + 255) / 256), 256, 0, s, e->P, dev ? mean : tmp, dev ? var : tmp + N, nullptr, nullptr);
     e->launches++;
     cudaError_t ce = cudaGetLastError();
     if (!dev) {

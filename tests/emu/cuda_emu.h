@@ -25,6 +25,7 @@
 
 struct uint3 { unsigned x, y, z; };
 struct double2 { double x, y; };
+inline double2 make_double2(double a, double b) { return double2{a, b}; }
 struct uchar2 { unsigned char x, y; };
 inline uchar2 make_uchar2(unsigned char a, unsigned char b) { return uchar2{a, b}; }
 struct dim3 {
