@@ -4,8 +4,8 @@
 #pragma once
 #ifdef GPIS_EMULATE
 #include "cuda_emu.h"
-#define GPIS_LAUNCH(kern, grid, block, stream, ...) emu::launch(grid, block, 0, [&]() { kern(__VA_ARGS__); })
-#define GPIS_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) emu::launch(grid, block, smem, [&]() { kern(__VA_ARGS__); })
+#define GPIS_LAUNCH(kern, grid, block, stream, ...) emu::launch_kernel(grid, block, 0, kern, __VA_ARGS__)
+#define GPIS_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) emu::launch_kernel(grid, block, smem, kern, __VA_ARGS__)
 #define GPIS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem)
 #define GPIS_DYN_SMEM_F64(name) double* name = reinterpret_cast<double*>(emu::dyn_smem)
 #define GPIS_DYN_SMEM_F64A(name) double* name = reinterpret_cast<double*>(emu::dyn_smem)

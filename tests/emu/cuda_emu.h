@@ -83,6 +83,13 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
       }
 }
 
+// kernel<<<grid, block, smem>>>(args...): the arguments are evaluated ONCE, by the launching thread (an
+// argument expression may have side effects), and every emulated thread gets a copy
+template <class K, class... A>
+void launch_kernel(dim3 grid, dim3 block, size_t smem_bytes, K kern, A... args) {
+  launch(grid, block, smem_bytes, [&]() { kern(args...); });
+}
+
 // one exchange among the 32 lanes of the calling warp
 inline unsigned long long exchange(unsigned long long bits, int from_lane, unsigned* ballot) {
   WarpBox* w = my_warp;

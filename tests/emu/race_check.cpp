@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
   if (argc > 1 && std::string(argv[1]) == "--self-test") {
     std::vector<double> out(64);
     double* o = out.data();
-    emu::launch(dim3(1), dim3(64), 0, [&]() { k_missing_barrier(o); });
+    emu::launch_kernel(dim3(1), dim3(64), 0, k_missing_barrier, o);
     std::printf("self-test done\n");
     return 0;
   }
