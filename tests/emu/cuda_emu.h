@@ -11,7 +11,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -45,14 +47,36 @@ struct WarpBox {
   double a[2][32], b[2][32];
   unsigned long long slot[2][32];
 };
+// Barrier of a thread block whose participants may leave (a CUDA thread that returned no longer takes part
+// in __syncthreads()); reset between blocks.
+struct BlockBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int expected = 0, arrived = 0;
+  unsigned gen = 0;
+  void reset(int n) { std::lock_guard<std::mutex> lk(m); expected = n; arrived = 0; }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned g = gen;
+    if (++arrived == expected) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+  void drop() {
+    std::lock_guard<std::mutex> lk(m);
+    --expected;
+    if (expected > 0 && arrived == expected) { arrived = 0; ++gen; cv.notify_all(); }
+  }
+};
 inline thread_local uint3 t_idx, b_idx;
 inline thread_local WarpBox* my_warp;
 inline thread_local int my_lane;
 inline thread_local unsigned my_gen;     // collectives executed by this thread (parity selects the staging buffer)
 inline dim3 g_dim, b_dim;
-inline std::barrier<>* cta_bar;
+inline BlockBarrier* cta_bar;
 inline unsigned char* dyn_smem;          // the block's dynamic shared memory (GPIS_DYN_SMEM*)
 
+// One OS thread per CUDA thread of a block, kept for the whole launch: the threads walk the grid's blocks
+// together, one block after another (__shared__ arrays are function-statics, so blocks cannot overlap).
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
   const unsigned nth = block.x * block.y * block.z;
@@ -60,27 +84,32 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
   b_dim = block;
   std::vector<unsigned char> smem(smem_bytes + 64);
   dyn_smem = smem.data() + (64 - reinterpret_cast<uintptr_t>(smem.data()) % 64) % 64;
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::barrier<> bar(nth);
-        cta_bar = &bar;
-        std::vector<std::unique_ptr<WarpBox>> warps;
-        for (unsigned w = 0; w < (nth + 31) / 32; ++w) warps.emplace_back(new WarpBox);
-        std::vector<std::thread> th;
-        th.reserve(nth);
-        for (unsigned t = 0; t < nth; ++t)
-          th.emplace_back([&, t]() {
-            t_idx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+  BlockBarrier cta;
+  cta.reset((int)nth);
+  cta_bar = &cta;
+  std::barrier<> block_end((std::ptrdiff_t)nth);
+  std::vector<std::unique_ptr<WarpBox>> warps;
+  for (unsigned w = 0; w < (nth + 31) / 32; ++w) warps.emplace_back(new WarpBox);
+  std::vector<std::thread> th;
+  th.reserve(nth);
+  for (unsigned t = 0; t < nth; ++t)
+    th.emplace_back([&, t]() {
+      t_idx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      my_warp = warps[t / 32].get();
+      my_lane = (int)(t % 32);
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             b_idx = uint3{bx, by, bz};
-            my_warp = warps[t / 32].get();
-            my_lane = (int)(t % 32);
             my_gen = 0;
             body();
-            bar.arrive_and_drop();          // a thread that returned no longer takes part in barriers
-          });
-        for (auto& x : th) x.join();
-      }
+            cta.drop();                       // a thread that returned no longer takes part in __syncthreads()
+            block_end.arrive_and_wait();      // the whole block has finished
+            if (t == 0) cta.reset((int)nth);
+            block_end.arrive_and_wait();      // ... and the barrier is armed for the next block
+          }
+    });
+  for (auto& x : th) x.join();
 }
 
 // kernel<<<grid, block, smem>>>(args...): the arguments are evaluated ONCE, by the launching thread (an
@@ -113,7 +142,7 @@ inline unsigned long long exchange(unsigned long long bits, int from_lane, unsig
 
 using std::max;
 using std::min;
-inline void __syncthreads() { emu::cta_bar->arrive_and_wait(); }
+inline void __syncthreads() { emu::cta_bar->wait(); }
 inline void __syncwarp() { emu::my_warp->bar.arrive_and_wait(); }
 inline void __threadfence_block() {}
 inline void __threadfence() { __sync_synchronize(); }
