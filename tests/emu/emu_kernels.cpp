@@ -1,6 +1,6 @@
-// TEST INFRASTRUCTURE ONLY: the kernels and launch sequences of gpis_sample.cuh compiled for the CPU
-// emulation in cuda_emu.h, behind a small C entry point that follows gpis_posterior_cov /
-// gpis_sample_shapes in gpis_capi.cu step by step (allocate, zero, launch, copy out).
+// TEST INFRASTRUCTURE ONLY: kernel headers of gpis_b200/csrc compiled for the CPU emulation in cuda_emu.h,
+// each behind a small C entry point that sets up buffers and launches the way gpis_capi.cu does
+// (gpis_sample.cuh shares its launch sequences with the shipped library; the others replicate them).
 #define GPIS_EMULATE 1
 #include "../../gpis_b200/csrc/gpis_sample.cuh"
 

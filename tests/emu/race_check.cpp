@@ -2,7 +2,7 @@
 // In the emulation every CUDA thread is an OS thread and __syncthreads() / warp collectives are the only
 // synchronisation, so a missing barrier between a shared-memory (or same-block global-memory) write and a
 // read by another thread is a data race TSan reports.  Build: g++ -std=c++20 -O1 -g -fsanitize=thread.
-#include "emu_sample.cpp"
+#include "emu_kernels.cpp"
 
 #include <cstdio>
 #include <random>

@@ -1,8 +1,10 @@
-"""The posterior-covariance / shape-sampling kernels and launch sequences of
-gpis_b200/csrc/gpis_sample.cuh, run on the CPU emulation of the CUDA execution model in tests/emu
-(g++ -DGPIS_EMULATE) and compared with the oracle's restatement of gp_mean.m, gp_cov.m and
-mc_sampling/sample_shapes.m.  This checks indexing and launch arithmetic where there is no GPU;
-tests/test_gpu_sampling.py is the same comparison through the C ABI on the device."""
+"""Kernels of gpis_b200/csrc run one header at a time on the CPU emulation of the CUDA execution model in
+tests/emu (g++ -DGPIS_EMULATE) and compared with the oracle: posterior covariance / blocked Cholesky / draws
+(gpis_sample.cuh, with the launch sequences the shipped library calls), the object-batched selection kernel
+(gpis_batch.cuh), the dense prediction kernels (gpis_predict.cuh) and the panel backend's selection loop
+(gpis_select.cuh).  This checks indexing, barrier structure and launch arithmetic where there is no GPU;
+the `-m gpu` tests are the same comparisons through the C ABI on the device, and tests/test_emu_library.py
+runs the whole library (gpis_capi.cu) under the same emulation."""
 import ctypes as C
 import os
 import subprocess
@@ -15,8 +17,8 @@ from conftest import ROOT, golden_model, load_golden
 from oracle import gpis_oracle as O
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_SO = os.path.join(ROOT, "build", "libemu_sample.so")
-EMU_DEPS = [os.path.join(EMU_DIR, "emu_sample.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+EMU_SO = os.path.join(ROOT, "build", "libemu_kernels.so")
+EMU_DEPS = [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_sample.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch.cuh"),
