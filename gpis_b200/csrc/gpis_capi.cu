@@ -1110,10 +1110,12 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
   P.err = d_cnt + 2 * (size_t)n_objects;
   // the tuned inner loops (gpis_batch.cuh) are the default; GPIS_BATCH_KERNEL=plain selects the plain form
   // they are tested against (same picks; 0.167 s instead of 0.126 s for 512 x 32^3 objects on a B200)
+  // GPIS_BATCH_KERNEL=dmma selects the tensor-pipe form of the update (opt-in: verified on the CPU emulation only)
   const char* variant = getenv("GPIS_BATCH_KERNEL");
-  const bool fast = !(variant && strcmp(variant, "plain") == 0);
+  const int fast = (variant && strcmp(variant, "plain") == 0) ? 0 : (variant && strcmp(variant, "dmma") == 0) ? 2 : 1;
   CU(cudaFuncSetAttribute((const void*)k_batch_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+  CU(cudaFuncSetAttribute((const void*)k_batch_select_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   struct EventPair {                    // released on every return path
     cudaEvent_t a = nullptr, b = nullptr;
     ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }

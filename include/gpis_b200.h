@@ -201,7 +201,8 @@ gpis_status gpis_get_sampling_timing(gpis_handle h, double* cov_ms, double* chol
  * n_selected[k]), n_in_model[k] (NULL allowed), and -- each may be NULL -- the posterior mean /
  * variance of every lattice point and the level-set flags (bit 0 active, bit 1 high, bit 2 low),
  * [n_objects][N].  device_ms (NULL allowed): CUDA-event time of the launch.  The environment variable
- * GPIS_BATCH_KERNEL=plain selects the untuned form of the kernel's inner loops (same picks).  Returns
+ * GPIS_BATCH_KERNEL=plain selects the untuned form of the kernel's inner loops, =dmma the tensor-pipe form
+ * of the update (opt-in; same picks).  Returns
  * GPIS_ERR_NOT_PD if any object's factor lost positive definiteness (its counts tell where). */
 gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin,
                               const double* spacing, int32_t n_objects, const double* tsdf,

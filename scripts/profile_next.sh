@@ -8,6 +8,9 @@ CMD="python scripts/bench_batch.py --fused --objects 148 --active 96 --variants 
 $CMD > gpurun_out/batch_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_batch_select -s 1 -c 1 \
     -o gpurun_out/k_batch_select $CMD > gpurun_out/batch_ncu.log 2>&1
+# 1b. the tensor-pipe form of the update (opt-in, never run on a GPU in round 1): parity, then timing
+python -m pytest tests/test_zz_gpu_batch_fused.py -m gpu -q > gpurun_out/batch_dmma_tests.log 2>&1
+python scripts/bench_batch.py --fused --variants plain tuned dmma > gpurun_out/batch_variants.json 2> gpurun_out/batch_variants.err
 # 2. shape sampling after the two-level Cholesky (the committed launch list predates it)
 CMD="python scripts/bench_sampling.py --grid 25 --reps 0"
 $CMD > gpurun_out/sampling_plain.log 2>&1 &&

@@ -200,6 +200,7 @@ inline void s_dmma(double& c0, double& c1, double a, double b) {
 }
 inline void p_dmma(double& c0, double& c1, double a, double b) { s_dmma(c0, c1, a, b); }
 inline void dmma8x8x4(double& c0, double& c1, double a, double b) { s_dmma(c0, c1, a, b); }
+inline void b_dmma(double& c0, double& c1, double a, double b) { s_dmma(c0, c1, a, b); }
 
 // cp.async stand-ins: the copy happens at once, commit / wait are no-ops (a superset of the allowed
 // behaviours: a missing wait cannot be detected here)

@@ -76,7 +76,7 @@ extern "C" int emu_batch_select(const int* dims, const double* origin, const dou
   P.tsdf = tsdf; P.mu = mu; P.var = var; P.flags = flags; P.ids = ids; P.n_sel = n_sel; P.n_model = n_model; P.err = err;
   std::vector<double> W((size_t)n_blocks * BRMAX * BRMAX, -7.0), Wt((size_t)n_blocks * BRMAX * BRMAX, -7.0);   // poisoned
   P.W = W.data(); P.Wt = Wt.data();
-  launch_batch_select(P, n_blocks, fast != 0, nullptr);
+  launch_batch_select(P, n_blocks, fast, nullptr);
   return 0;
 }
 

@@ -19,6 +19,7 @@ from oracle import gpis_oracle as O
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_SO = os.path.join(ROOT, "build", "libemu_kernels.so")
 EMU_DEPS = [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(EMU_DIR, "cuda_emu.h"),
+            os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch_kernel.inc"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_sample.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_common.cuh"),
             os.path.join(ROOT, "gpis_b200", "csrc", "gpis_batch.cuh"),
@@ -215,7 +216,7 @@ def lattice_points(dims):
     return np.ascontiguousarray(idx.T.astype(np.float64))
 
 
-@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("fast", [0, 1, 2])
 @pytest.mark.parametrize("dims,K,n_blocks", [((10, 9, 7), 24, 2), ((13, 12), 30, 3), ((6, 5, 19), 14, 1)])
 def test_emulated_batch_kernel_matches_the_oracle_per_object(emu, dims, K, n_blocks, fast):
     """Three objects over two or three blocks (a block takes its objects one after another, reusing

@@ -131,6 +131,14 @@ def test_batch_and_panel_through_the_emulated_library(G):
     hyp = {"cov": np.array([np.log(2.0), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
     tr = dict(TRAIN, activeSetSize=9)
     res = select_batch_fused(objs, dims, 9, 11, **cfg)
+    for form in ("plain", "dmma"):                       # the other forms of the kernel, chosen by the environment
+        os.environ["GPIS_BATCH_KERNEL"] = form
+        try:
+            other = select_batch_fused(objs, dims, 9, 11, **cfg)
+        finally:
+            os.environ.pop("GPIS_BATCH_KERNEL", None)
+        for a, b in zip(res, other):
+            assert np.array_equal(a["ids"], b["ids"]) and np.max(np.abs(a["mean"] - b["mean"])) < 1e-12
     for k in (0, 3):
         shape = {"points": pts, "tsdf": objs[k], "normals": None, "noise": None}
         ora = O.select_straddle_incremental(shape, tr, 11, hyp=hyp, prune=False)

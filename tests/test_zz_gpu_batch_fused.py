@@ -30,9 +30,11 @@ def test_arguments_are_validated_before_the_device_is_touched():
         assert ei.value.status == _lib.ERR_NO_DEVICE
 
 
-@pytest.fixture(params=["plain", "tuned"])
+@pytest.fixture(params=["plain", "tuned",
+                        pytest.param("dmma", marks=pytest.mark.xfail(strict=False, reason="opt-in tensor-pipe form of the "
+                                     "update: verified on the CPU emulation only in round 1 (no GPU minutes left)"))])
 def variant(request, monkeypatch):
-    """Both forms of the kernel's inner loops (GPIS_BATCH_KERNEL, read at every gpis_batch_select)."""
+    """The forms of the kernel's inner loops (GPIS_BATCH_KERNEL, read at every gpis_batch_select)."""
     monkeypatch.setenv("GPIS_BATCH_KERNEL", request.param)
     return request.param
 
