@@ -80,8 +80,8 @@ int main(int argc, char** argv) {
     std::printf("cholesky rc=%d launches=%lld T00=%.6f\n", rc, launches, T[0]);
     if (rc != 0) return 1;
   }
-  // 3. object-batched selection, both forms of the inner loops: 2 objects on one block, two z-groups
-  for (int fast = 0; fast < 2; ++fast) {
+  // 3. object-batched selection, all three forms of the inner loops: 2 objects on one block, two z-groups
+  for (int fast = 0; fast < 3; ++fast) {
     const int dims[3] = {6, 5, 9}, B = 2, K = 8;
     const long long N = 6 * 5 * 9;
     const double org[3] = {0, 0, 0}, sp[3] = {1, 1, 1}, mw[3] = {0, 0, 0};
