@@ -116,6 +116,50 @@ def one_gradient_case(rng, case):
     return tag, len(ora["order"])
 
 
+def one_sampling_case(rng, case):
+    """Dense fit, prediction at arbitrary points, full posterior covariance and draws against the oracle."""
+    D = int(rng.integers(2, 4))
+    m = int(rng.integers(1, 40))
+    grad = bool(rng.integers(0, 2))
+    X = rng.uniform(0, 6, (m, D))
+    y = np.linalg.norm(X - 3.0, axis=1) - 2.0 + 0.01 * rng.standard_normal(m)
+    dy = rng.standard_normal((m, D)) * 0.3 if grad else None
+    per_point = bool(rng.integers(0, 2))
+    nzv = 10 ** rng.uniform(-3, -1.3, m) if per_point else None
+    ell, sf, noise = rng.uniform(0.8, 3.0), rng.uniform(0.7, 1.4), 10 ** rng.uniform(-3, -1.5)
+    mean = np.concatenate([0.02 * rng.standard_normal(D), [0.05 * rng.standard_normal()]])
+    hyp = {"cov": np.array([np.log(ell), np.log(sf)]), "mean": mean, "lik": 0.5 * np.log(noise)}
+    ora = O.create_gpis(X, y, dy, nzv, hyp)
+    mdl = gpis_b200.create_gpis(X, y, dy, nzv, False, hyp)
+    nq = int(rng.integers(1, 75))
+    q = rng.uniform(-1, 7, (nq, D))
+    deriv = bool(rng.integers(0, 2)) and grad            # the reference's gp_mean / gp_cov need matching derivative flags
+    tag = f"sampling case {case}: D={D} m={m} grad={grad} per_point_noise={per_point} nq={nq} deriv={deriv}"
+    mu_f, _, _ = O.gp_mean(ora, q, grad)
+    pm, pv, pn = gpis_b200.predict_points(mdl, q, True)
+    assert np.max(np.abs(pm - mu_f[:nq])) < 1e-9, (tag, "mean")
+    assert np.max(np.abs(pv - O.gp_var_diag(ora, q))) < 1e-9, (tag, "var")
+    if grad:
+        assert np.max(np.abs(pn - mu_f[nq:].reshape(nq, D, order="F"))) < 1e-9, (tag, "normals")
+    if True:
+        MEAN, _, Kx = O.gp_mean(ora, q, grad)
+        COV = O.gp_cov(ora, q, Kx, grad)
+        if grad and not deriv:                             # function block of the joint posterior
+            MEAN, COV = MEAN[:nq], COV[:nq, :nq]
+        mean_g, cov_g = mdl.engine.posterior_cov(q, use_derivative=deriv)
+        assert np.max(np.abs(mean_g - MEAN)) < 1e-9 and np.max(np.abs(cov_g - COV)) < 1e-10, (tag, "cov")
+        ns = int(rng.integers(1, 4))
+        z = rng.standard_normal((ns, len(MEAN)))
+        try:
+            ref, lp, _ = O.sample_from_posterior(MEAN, COV, z, 1e-8)
+        except np.linalg.LinAlgError:
+            return tag + " (oracle: not PD)", 0
+        draws, logpdf = mdl.engine.sample_shapes(q, z, use_derivative=deriv, jitter=1e-8)
+        assert np.max(np.abs(draws - ref)) < 1e-6 and np.max(np.abs(logpdf - lp)) < 1e-5 * max(1.0, np.max(np.abs(lp))), (tag, "draws")
+    mdl.engine.close()
+    return tag, nq
+
+
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
@@ -126,4 +170,7 @@ if __name__ == "__main__":
     for case in range(max(1, n // 3)):
         tag, picks = one_gradient_case(rng, case)
         print(f"ok  {tag} -> {picks} picks  ({time.time() - t0:.0f} s)", flush=True)
+    for case in range(max(1, n // 3)):
+        tag, nq = one_sampling_case(rng, case)
+        print(f"ok  {tag}  ({time.time() - t0:.0f} s)", flush=True)
     print("fuzz done:", n, "cases")
