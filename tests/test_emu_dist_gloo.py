@@ -23,12 +23,19 @@ HYP = {"cov": np.array([np.log(2.0), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np
 TRAIN = {"activeSetSize": K, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
 
 
-def lattice():
+def lattice(with_normals=False):
     idx = np.indices(DIMS[::-1]).reshape(3, -1)[::-1]
     pts = np.ascontiguousarray(idx.T.astype(np.float64))
     rng = np.random.default_rng(4)
-    tsdf = np.clip((np.linalg.norm(pts - np.array([3.6, 3.1, 1.7]), axis=1) - 2.4) / 2.0, -1, 1) + 1e-3 * rng.standard_normal(len(pts))
-    return pts, tsdf
+    c = np.array([3.6, 3.1, 1.7])
+    dist_c = np.linalg.norm(pts - c, axis=1)
+    sd = (dist_c - 2.4) / 2.0
+    tsdf = np.clip(sd, -1, 1) + 1e-3 * rng.standard_normal(len(pts))
+    if not with_normals:
+        return pts, tsdf
+    nrm = (pts - c) / np.maximum(dist_c, 1e-9)[:, None] / 2.0
+    nrm[np.abs(sd) >= 1.0] = 0.0
+    return pts, tsdf, nrm
 
 
 def host_exchange(eng, world):
@@ -45,19 +52,22 @@ def _worker(rank, world, port, backend, q):
         from gpis_b200 import GpisEngine, _lib
         from gpis_b200 import dist as gdist
         _lib.LIB_PATH, _lib._lib = EMU_LIB, None
-        pts, tsdf = lattice()
+        grad = backend.endswith("-gradients")
+        pts, tsdf, nrm = lattice(True)
         nx, ny, nz = DIMS
         N = len(pts)
-        cfg = dict(ell=2.0, noise=0.05, level=0.0, eps=1e-2, beta=10.0, rank=rank, world_size=world, total_candidates=N)
-        if backend == "grid":
+        cfg = dict(ell=2.0, noise=0.05, level=0.0, eps=1e-2, beta=10.0, rank=rank, world_size=world, total_candidates=N,
+                   use_gradients=grad)
+        if backend.startswith("grid"):
             z0, z1 = gdist.slab_range(nz, rank, world)
             lo, hi = nx * ny * z0, nx * ny * z1
             eng = GpisEngine(3, hi - lo, K, id_base=lo, **cfg)
-            eng.set_grid_candidates((nx, ny, z1 - z0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), tsdf[lo:hi], z0=z0, nz_total=nz)
+            eng.set_grid_candidates((nx, ny, z1 - z0), (0.0, 0.0, 0.0), (1.0, 1.0, 1.0), tsdf[lo:hi],
+                                    normals=nrm[lo:hi] if grad else None, z0=z0, nz_total=nz)
         else:
             lo, hi = gdist.shard_range(N, rank, world)
             eng = GpisEngine(3, hi - lo, K, id_base=lo, **cfg)
-            eng.set_candidates(pts[lo:hi], tsdf[lo:hi])
+            eng.set_candidates(pts[lo:hi], tsdf[lo:hi], normals=nrm[lo:hi] if grad else None)
         sel = gdist.ShardedSelector(eng, rank, world, lo, hi, exchange=host_exchange)
         sel.select(FIRST, K)
         ids, n_model = eng.active()
@@ -80,7 +90,7 @@ def emu_lib():
     return EMU_LIB
 
 
-@pytest.mark.parametrize("backend", ["grid", "panel"])
+@pytest.mark.parametrize("backend", ["grid", "panel", "grid-gradients"])
 def test_two_ranks_real_engine_over_gloo(emu_lib, backend):
     world = 2
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
@@ -93,9 +103,9 @@ def test_two_ranks_real_engine_over_gloo(emu_lib, backend):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    pts, tsdf = lattice()
-    ora = O.select_straddle_incremental({"points": pts, "tsdf": tsdf, "normals": None, "noise": None}, TRAIN, FIRST,
-                                        hyp=HYP, prune=(backend == "panel"))
+    pts, tsdf, nrm = lattice(True)
+    ora = O.select_straddle_incremental({"points": pts, "tsdf": tsdf, "normals": nrm if backend.endswith("-gradients") else None,
+                                         "noise": None}, TRAIN, FIRST, hyp=HYP, prune=(backend == "panel"))
     assert res[0][3] == res[1][3] == list(ora["order"])              # every rank reports the oracle's sequence
     assert res[0][4] == res[1][4] == ora["n_in_model"]
     assert np.array_equal(res[0][7], res[1][7])                      # replicated factor: bit-identical on both ranks
