@@ -7,10 +7,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgpis_b200.so")
 
 GPIS_OK = 0
-ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_NOT_PD, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_NOT_PD, ERR_NO_DEVICE, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6, -7
 BETA_FIXED, BETA_GOTOVOS, BETA_SELECTCHOL = 0, 1, 2
 VAR_LATENT, VAR_PREDICTIVE = 0, 1
 PREC_FP64, PREC_TF32 = 0, 1
+LOOP_AUTO, LOOP_STEPS = 0, 1
+APPEND_AUTO, APPEND_TWO_KERNELS, APPEND_TWO_PASS = 0, 1, 2
+BATCH_AUTO, BATCH_PLAIN, BATCH_DMMA, BATCH_DFMA = 0, 1, 2, 3
+CONFIG_SIZE_V1 = 152
 
 # every symbol include/gpis_b200.h declares
 SYMBOLS = [
@@ -20,6 +24,7 @@ SYMBOLS = [
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
     "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing", "gpis_batch_select",
+    "gpis_get_persist_timing",
 ]
 
 
@@ -34,6 +39,8 @@ class GpisConfig(C.Structure):
         ("mean_w", C.c_double * 3), ("mean_c", C.c_double),
         ("noise", C.c_double), ("level", C.c_double), ("eps", C.c_double), ("beta", C.c_double),
         ("beta_delta", C.c_double),
+        ("loop_mode", C.c_int32), ("append_mode", C.c_int32), ("batch_kernel", C.c_int32),
+        ("spin_timeout_ms", C.c_int32),
     ]
 
 
@@ -88,6 +95,7 @@ def load():
         "gpis_get_stats": [vp, i64p, i64p, i64p, i64p],
         "gpis_get_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), i64p],
         "gpis_set_profiling": [vp, C.c_int32],
+        "gpis_get_persist_timing": [vp, vp],
         "gpis_get_phase_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "gpis_peer_export": [vp, vp],
         "gpis_peer_import": [vp, vp, C.c_int32],
@@ -109,8 +117,7 @@ def load():
 def check(lib, handle, status):
     if status != GPIS_OK:
         msg = lib.gpis_status_string(status).decode()
-        if handle:
-            detail = lib.gpis_last_error(handle).decode()
-            if detail:
-                msg += ": " + detail
+        detail = lib.gpis_last_error(handle if handle else None).decode()
+        if detail:
+            msg += ": " + detail
         raise GpisError(status, msg)

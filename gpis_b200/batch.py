@@ -47,12 +47,11 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
     results = [None] * len(mine)
     errors = []
     n_workers = max(1, min(n_workers, len(mine)))
-    # Engines of a batch run concurrently on one device.  The single-engine fast path fuses two
-    # kernels behind an in-kernel grid barrier, which needs ALL its CTAs resident at once -- not
-    # guaranteed when several engines' kernels share the SMs -- so the batch uses the unfused
-    # kernels (read by gpis_create; see include/gpis_b200.h).
-    prev = os.environ.get("GPIS_SOLVE_REGS")
-    os.environ["GPIS_SOLVE_REGS"] = "1"
+    # Engines of a batch run concurrently on one device.  The single-engine fast paths (the persistent
+    # selection kernel, the fused append) hold every SM behind in-kernel grid barriers, which is not
+    # possible when several engines' kernels share the SMs -- so the batch asks for the plain per-step
+    # kernels in each engine's config (include/gpis_b200.h: loop_mode, append_mode).
+    cfg = dict(cfg, loop_mode=_lib.LOOP_STEPS, append_mode=_lib.APPEND_TWO_KERNELS)
 
     def work(w):
         try:
@@ -78,10 +77,6 @@ def select_batch(tsdfs, dims, K, first_index, n_workers=8, rank=0, world=1, keep
         t.start()
     for t in threads:
         t.join()
-    if prev is None:
-        os.environ.pop("GPIS_SOLVE_REGS", None)
-    else:
-        os.environ["GPIS_SOLVE_REGS"] = prev
     if errors:
         raise errors[0]
     return results
@@ -97,7 +92,7 @@ class _Null:
 
 def select_batch_fused(tsdfs, dims, K, first_index, rank=0, world=1, keep_posterior=True, *, ell, sf2=1.0,
                        mean_w=None, mean_c=0.0, noise=0.01, level=0.0, eps=1e-2, beta=10.0,
-                       variance_mode=_lib.VAR_LATENT, device=-1):
+                       variance_mode=_lib.VAR_LATENT, device=-1, kernel=_lib.BATCH_AUTO):
     """Same inputs and result structure as `select_batch` (list of dict(object, ids, n_in_model[, mean,
     var, flags])), through gpis_batch_select: one kernel launch for this rank's share of the objects.
     `tsdfs` may be a sequence of per-object arrays or one (n_objects, N) array (NumPy or torch CUDA).
@@ -125,6 +120,7 @@ def select_batch_fused(tsdfs, dims, K, first_index, rank=0, world=1, keep_poster
         cfg.mean_w[d] = float(mw[d])
     cfg.mean_c, cfg.noise = float(mean_c), float(noise)
     cfg.level, cfg.eps, cfg.beta = float(level), float(eps), float(beta)
+    cfg.batch_kernel = int(kernel)
     dims_a = np.ascontiguousarray(np.asarray(dims, np.int32))
     ids = np.empty((B, int(K)), np.int64)
     n_sel, n_model = np.empty(B, np.int32), np.empty(B, np.int32)

@@ -24,8 +24,12 @@ constexpr int TF32_THREADS = 32, TKC = 32, TZ = 2;
 constexpr size_t TF32_SMEM = 0;
 template <int NB>
 void k_grid_gemm_tf32(EngineParams) {}
+constexpr size_t PERSIST_SMEM = 0;      // in-kernel grid barriers are not emulated either: the per-step path runs
+template <int D>
+void k_grid_persist(EngineParams, int) {}
 }  // namespace gpis
 #endif
+#include "gpis_grid_persist.cuh"
 #include "gpis_predict.cuh"
 #include "gpis_batch.cuh"
 #include "gpis_sample.cuh"
@@ -53,6 +57,11 @@ struct gpis_engine {
   int backend = 0;              // 0 none, 1 panel (arbitrary points), 2 grid (lattice, separable)
   int grid_ctas = 0, solve_ctas = 0;
   bool fused_solve = false, onepass = false, solve_ring = false;
+  bool persist = false;            // gpis_select runs the whole greedy loop in one cooperative kernel
+  bool self_peer = false;          // world_size 1: the exchange region is this engine's own (flags release the CTAs)
+  unsigned long long* d_phase_clk = nullptr;
+  size_t tile_cnt_cap = 0;
+  double persist_ms[12] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
   int solve1_ctas = 0;
   size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
@@ -84,10 +93,54 @@ namespace {
 
 const char* kVersion = "gpis_b200 0.1 (sm_100a)";
 
+thread_local std::string g_last_error;      // failures without a handle (gpis_create, gpis_batch_select)
+
 gpis_status fail(gpis_engine* e, gpis_status s, const std::string& msg) {
   if (e) e->err = msg;
+  else g_last_error = msg;
   return s;
 }
+
+// Every entry point runs on the engine's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define GUARD(e) DeviceGuard _guard((e)->device)
+
+// gpis_config grew after version 0.1: accept any size from the v1 prefix up, zero-fill the rest
+bool read_config(const gpis_config* in, gpis_config* out) {
+  if (!in || in->struct_size < (int32_t)GPIS_CONFIG_SIZE_V1 || in->struct_size > (int32_t)sizeof(gpis_config)) return false;
+  memset(out, 0, sizeof(*out));
+  memcpy(out, in, (size_t)in->struct_size);
+  out->struct_size = (int32_t)sizeof(gpis_config);
+  return true;
+}
+
+#ifdef GPIS_EMULATE
+template <class K>
+cudaError_t launch_cooperative(K, unsigned, unsigned, size_t, cudaStream_t, void**) { return cudaErrorNotSupported; }
+#else
+template <class K>
+cudaError_t launch_cooperative(K kern, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void** args) {
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(block);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  lc.attrs = at;
+  lc.numAttrs = 1;
+  return cudaLaunchKernelExC(&lc, (const void*)kern, args);
+}
+#endif
 
 #define CU(call)                                                                         \
   do {                                                                                   \
@@ -118,12 +171,13 @@ struct Dispatch {
   void (*g_gemm)(EngineParams);
   void (*g_gemm_tf32)(EngineParams);
   void (*g_epi)(EngineParams);
+  void (*g_persist)(EngineParams, int);
 };
 
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>, k_grid_persist<D>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -148,7 +202,8 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
     } else {
       if (e->onepass) {
         if (e->solve_ring) {      // solve + grid barrier + new row of W in ONE launch (one CTA per SM)
-          GPIS_LAUNCH_SMEM(d.g_solve2, e->solve1_ctas + 1, GSOLVE_THREADS, GS2_SMEM, s, e->P);
+          void* args[] = {(void*)&e->P};
+          CU(launch_cooperative(d.g_solve2, (unsigned)(e->solve1_ctas + 1), GSOLVE_THREADS, GS2_SMEM, s, args));
           e->launches += 1;
         } else {
           GPIS_LAUNCH_SMEM(d.g_solve1, e->solve1_ctas + 1, GSOLVE_THREADS, sizeof(double) * GS1_RMAX, s, e->P);
@@ -197,8 +252,8 @@ gpis_status read_state(gpis_engine* e, cudaStream_t s) {
   CU(cudaStreamSynchronize(s));
   if (e->host_state.err == GPIS_ERR_NOT_PD)
     return fail(e, GPIS_ERR_NOT_PD, "covariance block lost positive definiteness while appending a point");
-  if (e->host_state.err == -7)
-    return fail(e, GPIS_ERR_CUDA, "timed out waiting for a peer's exchange record");
+  if (e->host_state.err == GPIS_ERR_TIMEOUT)
+    return fail(e, GPIS_ERR_TIMEOUT, "an in-kernel wait (a peer's exchange record or a grid barrier) exceeded spin_timeout_ms");
   return GPIS_OK;
 }
 
@@ -246,16 +301,21 @@ const char* gpis_status_string(gpis_status s) {
     case GPIS_ERR_STATE: return "call out of order";
     case GPIS_ERR_NOT_PD: return "matrix not positive definite";
     case GPIS_ERR_NO_DEVICE: return "no CUDA device (there is no CPU path)";
+    case GPIS_ERR_TIMEOUT: return "in-kernel wait timed out";
     default: return "unknown status";
   }
 }
 
-const char* gpis_last_error(gpis_handle h) { return h ? h->err.c_str() : "null handle"; }
+const char* gpis_last_error(gpis_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 
-gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
-  if (!out || !cfg) return GPIS_ERR_INVALID;
+gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
+  if (!out || !cfg_in) return GPIS_ERR_INVALID;
   *out = nullptr;
-  if (cfg->struct_size != (int32_t)sizeof(gpis_config)) return GPIS_ERR_INVALID;
+  gpis_config cfg_v, *cfg = &cfg_v;
+  if (!read_config(cfg_in, cfg)) return fail(nullptr, GPIS_ERR_INVALID, "gpis_config.struct_size is not a known size");
+  if (cfg->loop_mode < 0 || cfg->loop_mode > GPIS_LOOP_STEPS || cfg->append_mode < 0 || cfg->append_mode > GPIS_APPEND_TWO_PASS ||
+      cfg->spin_timeout_ms < 0)
+    return fail(nullptr, GPIS_ERR_INVALID, "loop_mode / append_mode / spin_timeout_ms out of range");
   if (cfg->dim < 1 || cfg->dim > MAXD || cfg->num_candidates < 0 || cfg->max_active < 1) return GPIS_ERR_INVALID;
   if (!(cfg->ell > 0.0) || !(cfg->sf2 > 0.0) || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
     return GPIS_ERR_INVALID;
@@ -272,6 +332,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
   e->D = cfg->dim;
   e->NB = cfg->use_gradients ? cfg->dim + 1 : 1;
   gpis_status rc = GPIS_OK;
+  int caller_device = -1;
+  cudaGetDevice(&caller_device);
   auto body = [&]() -> gpis_status {
     if (cfg->device >= 0) CU(cudaSetDevice(cfg->device));
     CU(cudaGetDevice(&e->device));
@@ -355,17 +417,39 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     e->solve_ctas = e->num_sms * 4;
     e->solve_smem = sizeof(double) * (size_t)NB * P.R_cap;
     e->fused_solve = e->solve_smem <= 48 * 1024;      // kvec of every CTA in shared memory, 4 CTAs/SM
-    e->onepass = (NB == 1) && P.R_cap <= GS1_RMAX && getenv("GPIS_TWO_PASS") == nullptr;
-    e->solve_ring = getenv("GPIS_SOLVE_REGS") == nullptr;       // rows of W through a bulk-copy smem ring
+    {
+      int khz = 0;
+      CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
+      const long long ms = cfg->spin_timeout_ms > 0 ? cfg->spin_timeout_ms : 30000;
+      P.spin_cycles = ms * (long long)(khz > 0 ? khz : 2000000);
+    }
+    e->onepass = (NB == 1) && P.R_cap <= GS1_RMAX && cfg->append_mode != GPIS_APPEND_TWO_PASS;
+    e->solve_ring = cfg->append_mode == GPIS_APPEND_AUTO;       // rows of W through a bulk-copy smem ring + grid barrier
+    e->persist = e->onepass && cfg->loop_mode == GPIS_LOOP_AUTO && cfg->precision == GPIS_PREC_FP64;
 #ifdef GPIS_EMULATE
-    e->solve_ring = false;      // the ring form ends in an in-kernel grid barrier; emulated blocks run one after another
+    e->solve_ring = false;      // in-kernel grid barriers: emulated blocks run one after another
+    e->persist = false;
 #endif
-    e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
     if (e->onepass) {
+      int coop = 0;
+      CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
       CU(cudaFuncSetAttribute((const void*)disp.g_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS2_SMEM));
       CU(cudaFuncSetAttribute((const void*)disp.g_solve1, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)(sizeof(double) * GS1_RMAX)));
-      CU(dalloc(e, &P.ypart, (size_t)e->solve1_ctas * GS1_RMAX));
+#ifndef GPIS_EMULATE
+      CU(cudaFuncSetAttribute((const void*)disp.g_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSIST_SMEM));
+      // kernels with in-kernel grid barriers need every CTA resident: one per SM, or not at all
+      int occ2 = 0, occp = 0;
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void*)disp.g_solve2, GSOLVE_THREADS, GS2_SMEM));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, (const void*)disp.g_persist, GEMM_THREADS, PERSIST_SMEM));
+      if (!coop || occ2 < 1) e->solve_ring = false;
+      if (!coop || occp < 1) e->persist = false;
+#endif
+      e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
+      CU(dalloc(e, &P.ypart, (size_t)std::max(e->solve1_ctas, e->num_sms) * GS1_RMAX));
+      CU(dalloc(e, &e->d_phase_clk, (size_t)16));
+      CU(cudaMemset(e->d_phase_clk, 0, 16 * sizeof(unsigned long long)));
+      P.phase_clk = e->d_phase_clk;
     }
     if (e->fused_solve)
       CU(cudaFuncSetAttribute((const void*)disp.g_solve_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -384,10 +468,18 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
     return GPIS_OK;
   };
   rc = body();
+  if (rc == GPIS_OK && e->P.world == 1 && e->persist) {
+    // world_size 1: the exchange region is the engine's own; its generation flags are what release the
+    // CTAs of the persistent kernel into the next step
+    char h64[64];
+    rc = gpis_peer_export(e, h64);
+    void* self = e->xchg_base;
+    if (rc == GPIS_OK) rc = gpis_peer_import(e, &self, 1);
+    e->self_peer = rc == GPIS_OK;
+  }
+  if (caller_device >= 0) cudaSetDevice(caller_device);      // the caller's current device is not ours to change
   if (rc != GPIS_OK) {
-    // keep the message reachable through a static for the failed-create case
-    static thread_local std::string last;
-    last = e->err;
+    g_last_error = e->err;        // reachable through gpis_last_error(NULL)
     gpis_destroy(e);
     return rc;
   }
@@ -397,6 +489,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg) {
 
 gpis_status gpis_destroy(gpis_handle e) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (e->step_graph) cudaGraphExecDestroy(e->step_graph);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -412,6 +505,7 @@ gpis_status gpis_destroy(gpis_handle e) {
 gpis_status gpis_set_candidates(gpis_handle e, const double* pts, const double* tsdf, const double* normals,
                                 const double* noise, const int64_t* ids, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
   if (e->cfg.precision == GPIS_PREC_TF32)
@@ -442,6 +536,7 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
                                      const double* spacing, int32_t z0, int32_t nz_total, const double* tsdf,
                                      const double* normals, const double* noise, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (!dims || !origin || !spacing || !tsdf) return fail(e, GPIS_ERR_INVALID, "dims, origin, spacing and tsdf are required");
   cudaStream_t s = (cudaStream_t)stream;
   const int D = e->D;
@@ -522,6 +617,10 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
       e->gws_bytes = need;
     }
   }
+  if (e->persist && (size_t)2 * tiles > e->tile_cnt_cap) {
+    CU(dalloc(e, &P.tile_cnt, (size_t)2 * tiles));
+    e->tile_cnt_cap = (size_t)2 * tiles;
+  }
   e->backend = 2;
   e->have_candidates = true;
   e->selecting = false;
@@ -541,6 +640,7 @@ __global__ void k_fill_ones_col0(double* T, float* Tf, int ld, long long rows) {
 
 gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (!e->have_candidates) return fail(e, GPIS_ERR_STATE, "gpis_set_candidates has not been called");
   if (first_local >= e->P.N) return fail(e, GPIS_ERR_INVALID, "first index out of range");
   cudaStream_t s = (cudaStream_t)stream;
@@ -556,6 +656,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   }
   if (e->backend == 2) {
     CU(cudaMemsetAsync(e->P.W, 0, e->w_bytes, s));
+    if (e->P.tile_cnt) CU(cudaMemsetAsync(e->P.tile_cnt, 0, sizeof(unsigned) * e->tile_cnt_cap, s));
     if (e->P.bimg) CU(cudaMemsetAsync(e->P.bimg, 0, sizeof(float) * e->bimg_floats, s));
     CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
     for (int d = 0; d < MAXD; ++d) {
@@ -578,6 +679,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
 
 gpis_status gpis_step_append(gpis_handle e, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
   e->inverse_rows = -1;
   return launch_append(e, (cudaStream_t)stream, 0, 0);
@@ -585,18 +687,21 @@ gpis_status gpis_step_append(gpis_handle e, void* stream) {
 
 gpis_status gpis_step_update(gpis_handle e, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
   return launch_update(e, (cudaStream_t)stream);
 }
 
 gpis_status gpis_select_end(gpis_handle e, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (!e->selecting) return fail(e, GPIS_ERR_STATE, "gpis_select_begin has not been called");
   return launch_append(e, (cudaStream_t)stream, 0, 1);
 }
 
 gpis_status gpis_exchange_buffers(gpis_handle e, void** send, void** recv, int64_t* bytes_per_rank) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (send) *send = e->P.pay_send;
   if (recv) *recv = e->P.pay_recv;
   if (bytes_per_rank) *bytes_per_rank = (int64_t)(e->P.pay_stride * sizeof(double));
@@ -605,15 +710,17 @@ gpis_status gpis_exchange_buffers(gpis_handle e, void** send, void** recv, int64
 
 gpis_status gpis_peer_export(gpis_handle e, void* handle64) {
   if (!e || !handle64) return GPIS_ERR_INVALID;
+  GUARD(e);
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   EngineParams& P = e->P;
   if (!e->xchg_base) {
     const size_t rec = sizeof(double) * 2 * (size_t)P.world * P.pay_stride;
-    e->xchg_bytes = rec + sizeof(unsigned long long) * 2 * P.world;
+    e->xchg_bytes = rec + sizeof(unsigned long long) * 3 * P.world;     // records, generation flags [2][world], done [world]
     CU(dalloc(e, reinterpret_cast<char**>(&e->xchg_base), e->xchg_bytes));
     CU(cudaMemset(e->xchg_base, 0, e->xchg_bytes));
     P.xchg = static_cast<double*>(e->xchg_base);
     P.xflag = reinterpret_cast<unsigned long long*>(static_cast<char*>(e->xchg_base) + rec);
+    P.xdone = P.xflag + 2 * P.world;
   }
   cudaIpcMemHandle_t hd;
   CU(cudaIpcGetMemHandle(&hd, e->xchg_base));
@@ -623,11 +730,12 @@ gpis_status gpis_peer_export(gpis_handle e, void* handle64) {
 
 gpis_status gpis_peer_import(gpis_handle e, const void* handles, int32_t same_process) {
   if (!e || !handles) return GPIS_ERR_INVALID;
+  GUARD(e);
   EngineParams& P = e->P;
   if (!e->xchg_base) return fail(e, GPIS_ERR_STATE, "gpis_peer_export has not been called");
   const size_t rec = sizeof(double) * 2 * (size_t)P.world * P.pay_stride;
   std::vector<double*> xp(P.world);
-  std::vector<unsigned long long*> fp(P.world);
+  std::vector<unsigned long long*> fp(P.world), dn(P.world);
   for (int r = 0; r < P.world; ++r) {
     void* base = nullptr;
     if (r == P.rank) base = e->xchg_base;
@@ -640,11 +748,14 @@ gpis_status gpis_peer_import(gpis_handle e, const void* handles, int32_t same_pr
     }
     xp[r] = static_cast<double*>(base);
     fp[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + rec);
+    dn[r] = fp[r] + 2 * P.world;
   }
   if (!P.peer_xchg) {
     CU(dalloc(e, &P.peer_xchg, (size_t)P.world));
     CU(dalloc(e, &P.peer_xflag, (size_t)P.world));
+    CU(dalloc(e, &P.peer_xdone, (size_t)P.world));
   }
+  CU(cudaMemcpy(P.peer_xdone, dn.data(), sizeof(unsigned long long*) * P.world, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(P.peer_xchg, xp.data(), sizeof(double*) * P.world, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(P.peer_xflag, fp.data(), sizeof(unsigned long long*) * P.world, cudaMemcpyHostToDevice));
   P.peer_mode = 1;
@@ -654,6 +765,7 @@ gpis_status gpis_peer_import(gpis_handle e, const void* handles, int32_t same_pr
 
 gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (e->P.world != 1 && !e->P.peer_mode)
     return fail(e, GPIS_ERR_STATE, "gpis_select with world_size > 1 needs the peer exchange (gpis_peer_import); "
                                    "otherwise drive the step calls and all-gather the exchange buffer");
@@ -664,6 +776,37 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   gpis_status rc = gpis_select_begin(e, first_local, stream);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
+  // one persistent cooperative kernel for the whole greedy loop (lattice candidates, function values, fp64)
+  const bool persist = e->persist && e->backend == 2 && !e->profiling && e->P.peer_mode && e->P.tile_cnt;
+  if (persist) {
+    if (iters > 0) {
+      Dispatch d = get_dispatch(e->D, false);
+      int it_arg = iters;
+      void* args[] = {(void*)&e->P, (void*)&it_arg};
+      CU(launch_cooperative(d.g_persist, (unsigned)e->num_sms, GEMM_THREADS, PERSIST_SMEM, s, args));
+      e->launches += 1;
+    }
+    rc = gpis_select_end(e, stream);
+    if (rc != GPIS_OK) return rc;
+    CU(cudaEventRecord(e->ev1, s));
+    CU(cudaEventSynchronize(e->ev1));
+    float pms = 0.f;
+    CU(cudaEventElapsedTime(&pms, e->ev0, e->ev1));
+    e->select_ms = pms;
+    unsigned long long clk[PCLK_N];
+    memset(clk, 0, sizeof(clk));
+    if (iters > 0) CU(cudaMemcpy(clk, e->d_phase_clk, sizeof(clk), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < PCLK_N; ++i) e->persist_ms[i] = (double)clk[i] * 1e-6;
+    e->persist_ms[PCLK_STEPS] = (double)clk[PCLK_STEPS];
+    // CTA 0's view of the phases, summed over the steps: W pass + finish (with their barriers) = append,
+    // GEMM, fused epilogue
+    e->append_ms = e->persist_ms[PCLK_WPASS] + e->persist_ms[PCLK_BAR1] + e->persist_ms[PCLK_FINISH] + e->persist_ms[PCLK_BAR2];
+    e->main_ms = e->persist_ms[PCLK_GEMM];
+    e->epilogue_ms = e->persist_ms[PCLK_EPI];
+    e->update_ms = e->main_ms + e->epilogue_ms;
+    e->update_launches = (long long)clk[PCLK_STEPS];
+    return read_state(e, s);
+  }
   if (iters > 0 && !e->step_graph && !e->profiling) {
     // capture one (append, update) pair; every argument is constant, all state is on the device
     cudaStream_t cs = nullptr;
@@ -737,6 +880,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
 
 gpis_status gpis_get_active(gpis_handle e, int64_t* ids, int32_t* n_selected, int32_t* n_in_model, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   cudaStream_t s = (cudaStream_t)stream;
   gpis_status rc = read_state(e, s);
   if (rc != GPIS_OK) return rc;
@@ -751,6 +895,7 @@ gpis_status gpis_get_active(gpis_handle e, int64_t* ids, int32_t* n_selected, in
 
 gpis_status gpis_get_factor(gpis_handle e, double* L, int64_t ldl, double* alpha, int32_t* rows, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   cudaStream_t s = (cudaStream_t)stream;
   gpis_status rc = ensure_inverse(e, s);
   if (rc != GPIS_OK) return rc;
@@ -769,6 +914,7 @@ gpis_status gpis_get_factor(gpis_handle e, double* L, int64_t ldl, double* alpha
 gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const double* normals,
                      const double* noise, int32_t m, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (m < 0 || m > e->P.M_cap) return fail(e, GPIS_ERR_INVALID, "m must be in 0..max_active");
   if (m && (!pts || !tsdf)) return fail(e, GPIS_ERR_INVALID, "pts and tsdf are required");
   if (e->NB > 1 && m && !normals) return fail(e, GPIS_ERR_INVALID, "use_gradients needs normals");
@@ -784,7 +930,7 @@ gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const
   {
     EngineParams q = e->P;
     q.peer_mode = 0;
-    GPIS_LAUNCH_SMEM(k_begin, 1, 32, 0, s, q, -1, ++e->epoch);
+    GPIS_LAUNCH_SMEM(k_begin, 1, 32, 0, s, q, -1, 0u);
   }
   CU(cudaGetLastError());
   e->launches++;
@@ -826,6 +972,7 @@ gpis_status gpis_fit(gpis_handle e, const double* pts, const double* tsdf, const
 gpis_status gpis_predict(gpis_handle e, const double* query, int64_t nq, double* mean, double* var,
                          double* normals, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (nq < 0 || (nq && (!query || !mean || !var))) return fail(e, GPIS_ERR_INVALID, "query, mean and var are required");
   if (nq == 0) return GPIS_OK;
   cudaStream_t s = (cudaStream_t)stream;
@@ -955,6 +1102,7 @@ extern "C" {
 gpis_status gpis_posterior_cov(gpis_handle e, const double* query, int64_t nq, int32_t use_derivative, double* mean,
                                double* cov, int64_t ldc, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (nq < 0 || (nq && !query)) return fail(e, GPIS_ERR_INVALID, "query is required");
   if (nq == 0) return GPIS_OK;
   const long long nv = (long long)nq * (use_derivative ? e->D + 1 : 1);
@@ -980,6 +1128,7 @@ gpis_status gpis_sample_shapes(gpis_handle e, const double* query, int64_t nq, i
                                int32_t num_samples, const double* z, double jitter, double* samples, double* logpdf,
                                double* chol, int64_t ldt, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (nq <= 0 || !query) return fail(e, GPIS_ERR_INVALID, "query is required");
   if (num_samples < 0 || (num_samples && (!z || !samples))) return fail(e, GPIS_ERR_INVALID, "z and samples are required");
   if (!(jitter >= 0.0)) return fail(e, GPIS_ERR_INVALID, "jitter must be >= 0");
@@ -1037,12 +1186,13 @@ gpis_status gpis_sample_shapes(gpis_handle e, const double* query, int64_t nq, i
   return GPIS_OK;
 }
 
-gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin, const double* spacing,
+gpis_status gpis_batch_select(const gpis_config* cfg_in, const int32_t* dims, const double* origin, const double* spacing,
                               int32_t n_objects, const double* tsdf, int64_t first_index, int32_t K, int64_t* ids,
                               int32_t* n_selected, int32_t* n_in_model, double* mean, double* var, uint8_t* flags,
                               double* device_ms, void* stream) {
-  if (!cfg || cfg->struct_size != (int32_t)sizeof(gpis_config) || !dims || !tsdf || !ids || !n_selected)
-    return GPIS_ERR_INVALID;
+  gpis_config cfg_v, *cfg = &cfg_v;
+  if (!read_config(cfg_in, cfg) || !dims || !tsdf || !ids || !n_selected) return GPIS_ERR_INVALID;
+  if (cfg->batch_kernel < 0 || cfg->batch_kernel > GPIS_BATCH_DFMA) return GPIS_ERR_INVALID;
   const int D = cfg->dim;
   if (D < 2 || D > 3 || cfg->use_gradients || cfg->precision != GPIS_PREC_FP64 || cfg->beta_mode != GPIS_BETA_FIXED ||
       cfg->world_size > 1)
@@ -1108,11 +1258,8 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
   P.n_sel = d_cnt;
   P.n_model = d_cnt + n_objects;
   P.err = d_cnt + 2 * (size_t)n_objects;
-  // the tuned inner loops (gpis_batch.cuh) are the default; GPIS_BATCH_KERNEL=plain selects the plain form
-  // they are tested against (same picks; 0.167 s instead of 0.126 s for 512 x 32^3 objects on a B200)
-  // GPIS_BATCH_KERNEL=dmma selects the tensor-pipe form of the update (opt-in: verified on the CPU emulation only)
-  const char* variant = getenv("GPIS_BATCH_KERNEL");
-  const int fast = (variant && strcmp(variant, "plain") == 0) ? 0 : (variant && strcmp(variant, "dmma") == 0) ? 2 : 1;
+  // inner loops of the kernel (gpis_batch.cuh): cfg->batch_kernel, GPIS_BATCH_AUTO = the tuned DFMA form
+  const int fast = cfg->batch_kernel == GPIS_BATCH_PLAIN ? 0 : cfg->batch_kernel == GPIS_BATCH_DMMA ? 2 : 1;
   CU(cudaFuncSetAttribute((const void*)k_batch_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
@@ -1148,6 +1295,7 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
 
 gpis_status gpis_get_sampling_timing(gpis_handle e, double* cov_ms, double* chol_ms, double* draw_ms) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (cov_ms) *cov_ms = e->cov_ms;
   if (chol_ms) *chol_ms = e->chol_ms;
   if (draw_ms) *draw_ms = e->draw_ms;
@@ -1170,6 +1318,7 @@ __global__ void k_split_flags(const unsigned char* f, long long n, unsigned char
 gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, uint8_t* low, uint8_t* active,
                               void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
   if (!N) return GPIS_OK;
@@ -1204,6 +1353,7 @@ gpis_status gpis_get_levelset(gpis_handle e, double* ambiguity, uint8_t* high, u
 
 gpis_status gpis_get_candidate_posterior(gpis_handle e, double* mean, double* var, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t N = (size_t)e->P.N;
   if (!N) return GPIS_OK;
@@ -1239,8 +1389,10 @@ gpis_status gpis_get_candidate_posterior(gpis_handle e, double* mean, double* va
 gpis_status gpis_get_stats(gpis_handle e, int64_t* kernel_launches, int64_t* live_tiles, int64_t* iterations,
                            int64_t* panel_bytes) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (kernel_launches) *kernel_launches = e->launches;
   if (live_tiles || iterations) {
+    CU(cudaDeviceSynchronize());        // the state may have been produced on any stream
     gpis_status rc = read_state(e, 0);
     if (rc != GPIS_OK && rc != GPIS_ERR_NOT_PD) return rc;
     if (live_tiles) *live_tiles = e->host_state.n_live[e->host_state.iter & 1];
@@ -1253,6 +1405,7 @@ gpis_status gpis_get_stats(gpis_handle e, int64_t* kernel_launches, int64_t* liv
 gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms, double* update_ms,
                             int64_t* update_launches) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (select_ms) *select_ms = e->select_ms;
   if (predict_ms) *predict_ms = e->predict_ms;
   if (update_ms) *update_ms = e->update_ms;
@@ -1262,20 +1415,30 @@ gpis_status gpis_get_timing(gpis_handle e, double* select_ms, double* predict_ms
 
 gpis_status gpis_get_phase_timing(gpis_handle e, double* append_ms, double* main_ms, double* epilogue_ms) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   if (append_ms) *append_ms = e->append_ms;
   if (main_ms) *main_ms = e->main_ms;
   if (epilogue_ms) *epilogue_ms = e->epilogue_ms;
   return GPIS_OK;
 }
 
+gpis_status gpis_get_persist_timing(gpis_handle e, double* ms12) {
+  if (!e || !ms12) return GPIS_ERR_INVALID;
+  for (int i = 0; i < 12; ++i) ms12[i] = e->persist_ms[i];
+  return GPIS_OK;
+}
+
 gpis_status gpis_set_profiling(gpis_handle e, int32_t on) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
   e->profiling = on != 0;
   return GPIS_OK;
 }
 
 gpis_status gpis_get_history(gpis_handle e, int32_t* rows, int32_t* live_tiles, int32_t* scored, int32_t* n) {
   if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  CU(cudaDeviceSynchronize());          // the history may have been produced on any stream
   gpis_status rc = read_state(e, 0);
   if (rc != GPIS_OK && rc != GPIS_ERR_NOT_PD) return rc;
   const int it = std::min(e->host_state.iter, e->P.M_cap + 1);

@@ -85,6 +85,10 @@ struct EngineParams {
   unsigned long long* xflag;       // [2][world]
   double** peer_xchg;              // device array of world pointers (own region included)
   unsigned long long** peer_xflag;
+  // selection fence: xdone[p] = last selection (epoch) rank p has finished reading records of; a rank
+  // publishes nothing of selection e + 1 into a peer's region before every peer has finished e
+  unsigned long long* xdone;       // [world], written by the peers
+  unsigned long long** peer_xdone;
   int ell_chunk;           // factor rows staged in shared memory per pass
   // grid backend (glen[0] > 0): lattice geometry, separable axis tables, explicit W = L^-1
   int glen[MAXD];          // candidates per axis on THIS rank (z: the local slab)
@@ -106,6 +110,9 @@ struct EngineParams {
   double* gws;             // split-K workspace [NB][tiles][gws_segmax][128*128]
   int gws_segmax;
   int gemm_ctas;           // persistent grid of the update GEMM
+  unsigned int* tile_cnt;  // persistent selection kernel: [2][tiles] split-K arrival counters (step parity)
+  unsigned long long* phase_clk;   // persistent selection kernel: CTA 0's phase times (globaltimer ns), [8]
+  long long spin_cycles;   // SM clocks an in-kernel wait (peer record, grid barrier) may take before it gives up
   // model
   double inv_ell2, sf2, level, eps, beta, beta_delta, noise_scalar;
   double mean_w[MAXD], mean_c;

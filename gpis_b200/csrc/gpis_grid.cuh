@@ -205,7 +205,10 @@ template <int NB, int D>
 __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int finalize_only) {
   DevState* st = P.st;
   __shared__ int s_win;
-  if (st->done) return;
+  if (st->done) {
+    if (finalize_only) signal_selection_done(P, st);
+    return;
+  }
   const int tid = threadIdx.x;
   const int gen = st->iter;
   if (!wait_records(P, st, gen)) return;
@@ -218,7 +221,10 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
   }
   __syncthreads();
   const int win = s_win;
-  if (win < 0) return;
+  if (win < 0) {
+    if (finalize_only) signal_selection_done(P, st);
+    return;
+  }
   const double* pay = recs + (long long)win * P.pay_stride;
   const long long* pl = reinterpret_cast<const long long*>(pay);
   const int r0 = st->r, m = st->m;
@@ -227,7 +233,10 @@ __global__ void __launch_bounds__(1024, 1) k_grid_point(EngineParams P, int fina
     P.sel_ids[m] = pl[PAY_ID];
     st->n_sel = m + 1;
   }
-  if (finalize_only) return;
+  if (finalize_only) {
+    signal_selection_done(P, st);
+    return;
+  }
   double nx[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) nx[d] = pay[PAY_X + d];
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(GSOLVE_THREADS, 1) k_grid_solve2(EngineParams 
     atomicAdd(&st->grid_bar, 1u);
     const long long t0 = clock64();
     while (*(volatile unsigned*)&st->grid_bar < target) {
-      if (clock64() - t0 > 4000000000LL) { s_bar_to = 1; break; }
+      if (clock64() - t0 > P.spin_cycles) { s_bar_to = 1; break; }
       __nanosleep(64);
     }
     __threadfence();

@@ -124,14 +124,14 @@ __device__ inline bool wait_records(const EngineParams& P, DevState* st, int gen
     volatile unsigned long long* f = P.xflag + (gen & 1) * P.world + threadIdx.x;
     const long long t0 = clock64();
     while (*f != want) {
-      if (clock64() - t0 > 6000000000LL) { s_to = 1; break; }     // ~3 s
+      if (clock64() - t0 > P.spin_cycles || *(volatile int*)&st->err != 0) { s_to = 1; break; }
       __nanosleep(100);
     }
   }
   __threadfence_system();
   __syncthreads();
   if (s_to) {
-    if (threadIdx.x == 0) { st->err = -7; st->done = 1; }
+    if (threadIdx.x == 0) { atomicCAS(&st->err, 0, -7); st->done = 1; }
     return false;
   }
   return true;
@@ -155,8 +155,30 @@ __device__ inline void publish_record(const EngineParams& P, const DevState* st,
   }
 }
 
+// whole block, when this rank has consumed the last records of its selection: tell every peer
+__device__ inline void signal_selection_done(const EngineParams& P, const DevState* st) {
+  if (!P.peer_mode || !P.peer_xdone) return;
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < P.world) {
+    volatile unsigned long long* f = P.peer_xdone[threadIdx.x] + P.rank;
+    *f = (unsigned long long)st->epoch;
+  }
+}
+
 __global__ void k_begin(EngineParams P, long long first_local, unsigned epoch) {
   DevState* st = P.st;
+  // peer mode: the regions are double-buffered by generation parity only, so selection `epoch` may not
+  // write into a peer's region while that peer still reads the last generation of selection epoch - 1
+  if (P.peer_mode && P.xdone && (int)threadIdx.x < P.world && epoch > 0) {
+    volatile unsigned long long* f = P.xdone + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f + 1 < (unsigned long long)epoch) {
+      if (clock64() - t0 > P.spin_cycles) break;      // the records' own tags still protect the readers
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     st->r = st->r0 = st->m = st->n_sel = st->done = st->iter = st->err = 0;
     st->n_live[0] = P.n_tiles;
@@ -188,7 +210,10 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
   __shared__ double s_x[NB][32];
   __shared__ double s_red[APP_THREADS / 32];
   __shared__ double s_dot[NB][NB + 1];
-  if (st->done) return;
+  if (st->done) {
+    if (finalize_only && !external) signal_selection_done(P, st);
+    return;
+  }
   const int tid = threadIdx.x;
   const int gen = st->iter;
   if (!external && !wait_records(P, st, gen)) return;
@@ -209,7 +234,10 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
   }
   __syncthreads();
   const int win = s_win;
-  if (win < 0) return;
+  if (win < 0) {
+    if (finalize_only && !external) signal_selection_done(P, st);
+    return;
+  }
   const double* pay = recs + (long long)win * P.pay_stride;
   const long long* pl = reinterpret_cast<const long long*>(pay);
   const int r0 = st->r, m = st->m;
@@ -218,7 +246,10 @@ __global__ void __launch_bounds__(APP_THREADS, 1) k_append(EngineParams P, int e
     P.sel_ids[m] = pl[PAY_ID];
     st->n_sel = m + 1;
   }
-  if (finalize_only) return;
+  if (finalize_only) {
+    if (!external) signal_selection_done(P, st);
+    return;
+  }
 
   double nx[D];
 #pragma unroll

@@ -65,7 +65,8 @@ class GpisEngine:
     def __init__(self, dim, num_candidates, max_active, *, ell, sf2=1.0, mean_w=None, mean_c=0.0,
                  noise=0.01, level=0.0, eps=1e-2, beta=10.0, use_gradients=False,
                  beta_mode=_lib.BETA_FIXED, beta_delta=0.01, variance_mode=_lib.VAR_LATENT,
-                 precision=_lib.PREC_FP64, rank=0, world_size=1, total_candidates=0, id_base=0, device=-1):
+                 precision=_lib.PREC_FP64, rank=0, world_size=1, total_candidates=0, id_base=0, device=-1,
+                 loop_mode=_lib.LOOP_AUTO, append_mode=_lib.APPEND_AUTO, spin_timeout_ms=0):
         self.lib = _lib.load()
         self.dim, self.N, self.max_active = int(dim), int(num_candidates), int(max_active)
         self.use_gradients = bool(use_gradients)
@@ -83,6 +84,7 @@ class GpisEngine:
             cfg.mean_w[d] = float(mw[d])
         cfg.mean_c, cfg.noise = float(mean_c), float(noise)
         cfg.level, cfg.eps, cfg.beta, cfg.beta_delta = float(level), float(eps), float(beta), float(beta_delta)
+        cfg.loop_mode, cfg.append_mode, cfg.spin_timeout_ms = int(loop_mode), int(append_mode), int(spin_timeout_ms)
         self.cfg = cfg
         self.peer_mode = False
         self.h = C.c_void_p()
@@ -282,6 +284,15 @@ class GpisEngine:
         self._ck(self.lib.gpis_get_phase_timing(self.h, C.byref(p), C.byref(q), C.byref(r)))
         return {"select_ms": a.value, "predict_ms": b.value, "update_ms": c.value, "update_launches": n.value,
                 "append_ms": p.value, "main_ms": q.value, "epilogue_ms": r.value}
+
+    PERSIST_SLOTS = ("record_wait", "w_pass", "barrier1", "new_row", "barrier2", "gemm", "epilogue", "arrive_wait",
+                     "publish", "steps")
+
+    def persist_timing(self):
+        """Lap times (ms, block 0's clock) of the persistent selection kernel in the last select()."""
+        a = np.zeros(12)
+        self._ck(self.lib.gpis_get_persist_timing(self.h, _ptr(a)))
+        return dict(zip(self.PERSIST_SLOTS, a.tolist()))
 
     def set_profiling(self, on=True):
         self._ck(self.lib.gpis_set_profiling(self.h, int(bool(on))))

@@ -21,10 +21,12 @@
  *     calls are asynchronous on it unless they return values through host pointers,
  *     in which case they synchronise the stream before returning;
  *   - there is no CPU fallback: without a CUDA device gpis_create fails;
- *   - a handle assumes it has the device to itself while gpis_select runs (its factor-append kernel
- *     uses an in-kernel grid barrier: one CTA per SM, all resident).  To run several handles
- *     concurrently on one device (gpis_b200/batch.py does), set the environment variable
- *     GPIS_SOLVE_REGS=1 before gpis_create: the append then uses two plain kernels instead.
+ *   - kernels that wait on one another inside a launch (the persistent selection kernel, the fused
+ *     factor append) are COOPERATIVE launches: the driver guarantees their blocks are co-resident or
+ *     refuses the launch, in which case the engine uses its plain multi-kernel forms.  To run several
+ *     handles concurrently on one device (gpis_b200/batch.py does) ask for those forms up front:
+ *     gpis_config.loop_mode = GPIS_LOOP_STEPS, append_mode = GPIS_APPEND_TWO_KERNELS.
+ *   - behaviour is selected by gpis_config fields only; the library reads no environment variable.
  */
 #ifndef GPIS_B200_H
 #define GPIS_B200_H
@@ -45,7 +47,8 @@ enum {
   GPIS_ERR_NOMEM = -3,     /* device allocation failed                       */
   GPIS_ERR_STATE = -4,     /* call out of order (e.g. select before set)     */
   GPIS_ERR_NOT_PD = -5,    /* covariance block lost positive definiteness    */
-  GPIS_ERR_NO_DEVICE = -6  /* no usable CUDA device: there is no CPU path    */
+  GPIS_ERR_NO_DEVICE = -6, /* no usable CUDA device: there is no CPU path    */
+  GPIS_ERR_TIMEOUT = -7    /* an in-kernel wait (peer record, grid barrier) timed out */
 };
 
 enum { GPIS_BETA_FIXED = 0,      /* select_active_set_straddle.m:10 (varScale fixed)            */
@@ -54,6 +57,15 @@ enum { GPIS_BETA_FIXED = 0,      /* select_active_set_straddle.m:10 (varScale fi
 enum { GPIS_VAR_LATENT = 0,      /* gp_cov.m:6 (beta = 0 on the test block)                     */
        GPIS_VAR_PREDICTIVE = 1   /* max_subset_buffers.cu:113-115 (k(x,x) + noise - reduction)  */ };
 enum { GPIS_PREC_FP64 = 0, GPIS_PREC_TF32 = 1 };
+/* How gpis_select drives the greedy loop of a lattice (grid) engine. */
+enum { GPIS_LOOP_AUTO = 0,       /* one persistent cooperative kernel per selection when eligible   */
+       GPIS_LOOP_STEPS = 1       /* per-step launches (captured CUDA graph)                         */ };
+/* Factor-append form of the per-step path (function-only lattice models up to 4096 rows). */
+enum { GPIS_APPEND_AUTO = 0,         /* fused: W pass + in-kernel grid barrier + new row, one cooperative launch */
+       GPIS_APPEND_TWO_KERNELS = 1,  /* the same pass as two plain launches (safe next to other work on the GPU) */
+       GPIS_APPEND_TWO_PASS = 2      /* rows of W, then of W' (the form gradient / larger models always use)     */ };
+/* Inner loops of gpis_batch_select. */
+enum { GPIS_BATCH_AUTO = 0, GPIS_BATCH_PLAIN = 1, GPIS_BATCH_DMMA = 2, GPIS_BATCH_DFMA = 3 };
 
 /* Replaces GaussianProcessHyperparams + the scalar arguments of SelectChol
  * (include/active_set_selection_types.h:10-13, gpu_active_set_selector.hpp:41-46) and the
@@ -76,11 +88,21 @@ typedef struct gpis_config {
   double noise;             /* scalar noise variance (exp(2*hyp.lik)) when no per-point noise */
   double level, eps, beta;  /* trainingParams.levelSet / eps / beta                          */
   double beta_delta;        /* delta (GOTOVOS) or tolerance (SELECTCHOL)                     */
+  /* -- fields added after version 0.1; a caller compiled against the shorter struct passes its own
+   *    sizeof in struct_size and gets the defaults (all zero) for what it does not know -- */
+  int32_t loop_mode;        /* GPIS_LOOP_*                                                   */
+  int32_t append_mode;      /* GPIS_APPEND_*                                                 */
+  int32_t batch_kernel;     /* GPIS_BATCH_* (gpis_batch_select only)                         */
+  int32_t spin_timeout_ms;  /* longest in-kernel wait for a peer's record or a grid barrier before the
+                             * selection is abandoned with GPIS_ERR_TIMEOUT; 0 = 30000              */
 } gpis_config;
+/* sizeof(gpis_config) of version 0.1 (up to and including beta_delta) */
+#define GPIS_CONFIG_SIZE_V1 152
 
 const char* gpis_version(void);
 const char* gpis_status_string(gpis_status s);
-/* Text of the last error on this handle ("" if none). */
+/* Text of the last error on this handle ("" if none); h == NULL: the message of the last failed
+ * gpis_create / gpis_batch_select on the calling thread. */
 const char* gpis_last_error(gpis_handle h);
 
 /* construct_active_set_buffers + construct_max_subset_buffers + construct_classification_buffers
@@ -200,9 +222,9 @@ gpis_status gpis_get_sampling_timing(gpis_handle h, double* cov_ms, double* chol
  * Outputs (host or device pointers): ids[k*K + i] picks in selection order (-1 beyond
  * n_selected[k]), n_in_model[k] (NULL allowed), and -- each may be NULL -- the posterior mean /
  * variance of every lattice point and the level-set flags (bit 0 active, bit 1 high, bit 2 low),
- * [n_objects][N].  device_ms (NULL allowed): CUDA-event time of the launch.  The environment variable
- * GPIS_BATCH_KERNEL=plain selects the untuned form of the kernel's inner loops, =dmma the tensor-pipe form
- * of the update (opt-in; same picks).  Returns
+ * [n_objects][N].  device_ms (NULL allowed): CUDA-event time of the launch.  cfg->batch_kernel selects
+ * the form of the kernel's inner loops (GPIS_BATCH_PLAIN: untuned, GPIS_BATCH_DMMA: the update on the fp64
+ * tensor pipe, GPIS_BATCH_DFMA / AUTO: the tuned register-tile form; same picks in all).  Returns
  * GPIS_ERR_NOT_PD if any object's factor lost positive definiteness (its counts tell where). */
 gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin,
                               const double* spacing, int32_t n_objects, const double* tsdf,
@@ -229,6 +251,11 @@ gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms
 /* Profiling only: summed device time of the last gpis_select's factor-append kernels, of the
  * main update kernel (k_update / k_grid_gemm) and of the grid backend's epilogue kernel. */
 gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main_ms, double* epilogue_ms);
+/* The persistent selection kernel's own lap timer (block 0, %globaltimer), summed over the steps of the
+ * last gpis_select, ms: [0] wait for the exchange records, [1] W pass of the factor append, [2] grid
+ * barrier, [3] new row of W, [4] grid barrier, [5] update GEMM, [6] fused epilogue, [7] wait for all
+ * blocks, [8] winner reduction + record publication, [9] = number of steps (a count, not ms). */
+gpis_status gpis_get_persist_timing(gpis_handle h, double* ms12);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
  * stream (plain launches instead of the captured graph). */
 gpis_status gpis_set_profiling(gpis_handle h, int32_t on);

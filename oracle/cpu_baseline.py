@@ -15,7 +15,8 @@ import numpy as np
 import scipy.linalg as sla
 
 
-def select_compact(points, tsdf, hyp, train, first_index, max_steps=None, time_budget_s=None):
+def select_compact(points, tsdf, hyp, train, first_index, max_steps=None, time_budget_s=None, checkpoint=None):
+    """checkpoint: optional callable(order_list, step) invoked every 100 steps (long fixture runs)."""
     pts = np.asarray(points, np.float64)
     y = np.asarray(tsdf, np.float64).reshape(-1)
     N, D = pts.shape
@@ -78,10 +79,14 @@ def select_compact(points, tsdf, hyp, train, first_index, max_steps=None, time_b
             keep = live.copy()
             keep[b] = True
             idx = np.flatnonzero(keep)
-            V = np.ascontiguousarray(V[:, idx])
+            Vn = np.zeros((steps + 1, idx.size))        # untouched rows stay unmapped (calloc)
+            Vn[:r] = V[:r, idx]
+            V = Vn
             P, cols, mu, var, live = P[idx], cols[idx], mu[idx], var[idx], live[idx]
             pend_col = int(np.flatnonzero(cols == pending)[0])
         step_times.append(time.perf_counter() - ts)
+        if checkpoint is not None and (it + 1) % 100 == 0:
+            checkpoint(order, it + 1)
         if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
             break
     return {"order": np.asarray(order), "n_in_model": r, "L": Lf[:r, :r], "g": g[:r],

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
+from gpis_b200 import _lib
 from gpis_b200.batch import select_batch, select_batch_fused, superellipsoid_tsdf
 
 ap = argparse.ArgumentParser()
@@ -29,7 +30,8 @@ ref = None
 if a.fused:
     stack = np.ascontiguousarray(np.stack(tsdfs))
     for variant in a.variants:
-        os.environ["GPIS_BATCH_KERNEL"] = variant           # read at every gpis_batch_select
+        kern = {"plain": _lib.BATCH_PLAIN, "tuned": _lib.BATCH_DFMA, "dmma": _lib.BATCH_DMMA}[variant]
+        cfg["kernel"] = kern                                  # gpis_config.batch_kernel
         select_batch_fused(stack[:8], (g, g, g), a.active, 3254, keep_posterior=False, **cfg)       # warm-up
         best = None
         for _ in range(2):

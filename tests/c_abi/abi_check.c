@@ -36,7 +36,14 @@ int main(int argc, char** argv) {
   gpis_status st = p_gpis_create(&h, &cfg);
   if (argc < 3) {                      /* CPU box: must refuse, never fall back */
     printf("create status=%d\n", st);
-    return st == GPIS_ERR_NO_DEVICE ? 0 : 1;
+    /* a caller compiled against the version-0.1 header passes the shorter struct: accepted (same answer);
+     * a size that was never published is rejected as such */
+    cfg.struct_size = GPIS_CONFIG_SIZE_V1;
+    gpis_status st1 = p_gpis_create(&h, &cfg);
+    cfg.struct_size = 40;
+    gpis_status st2 = p_gpis_create(&h, &cfg);
+    printf("create(v1 struct)=%d create(bad size)=%d\n", st1, st2);
+    return (st == GPIS_ERR_NO_DEVICE && st1 == GPIS_ERR_NO_DEVICE && st2 == GPIS_ERR_INVALID) ? 0 : 1;
   }
   if (st != GPIS_OK) { printf("create failed %d\n", st); return 1; }
   static double tsdf[N], mu[N], var[N];

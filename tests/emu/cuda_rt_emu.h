@@ -69,6 +69,9 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
   return cudaSuccess;
 }
 inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return cudaSuccess; }
+enum { cudaDevAttrClockRate = 13, cudaDevAttrCooperativeLaunch = 95 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) { *v = attr == cudaDevAttrClockRate ? 1000000 : 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeDevice; return cudaSuccess; }
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }

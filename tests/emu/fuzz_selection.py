@@ -67,14 +67,13 @@ def one_case(rng, case):
             assert np.max(np.abs(mu[live] - fm[live])) < 1e-9 and np.max(np.abs(var[live] - fv[live])) < 1e-9, (tag, backend, "posterior")
         mdl.engine.close()
     cfg = dict(ell=ell, sf2=sf2, mean_w=mean[:D], mean_c=mean[D], noise=noise, level=level, eps=eps, beta=beta)
-    for form in ("plain", "tuned", "dmma"):
-        os.environ["GPIS_BATCH_KERNEL"] = form
-        res = select_batch_fused([tsdf, tsdf], dims, K, first, **cfg)
+    from gpis_b200 import _lib as glib
+    for form in (glib.BATCH_PLAIN, glib.BATCH_DFMA, glib.BATCH_DMMA):
+        res = select_batch_fused([tsdf, tsdf], dims, K, first, kernel=form, **cfg)
         for r in res:
             assert np.array_equal(r["ids"], ora["order"]) and r["n_in_model"] == ora["n_in_model"], (tag, "batch", form)
             assert np.max(np.abs(r["mean"] - fm)) < 1e-9 and np.max(np.abs(r["var"] - fv)) < 1e-9, (tag, "batch", form)
             assert np.array_equal((r["flags"] & 2) > 0, ora["high"]) and np.array_equal((r["flags"] & 4) > 0, ora["low"]), (tag, form)
-    os.environ.pop("GPIS_BATCH_KERNEL", None)
     return tag, len(ora["order"])
 
 

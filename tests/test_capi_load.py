@@ -33,8 +33,19 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_config_struct_matches_header_layout():
     from gpis_b200 import _lib
-    # 2 i32, 3 i64, 8 i32, 2+4+5 doubles
-    assert C.sizeof(_lib.GpisConfig) == 8 + 24 + 32 + 8 * 11
+    # version 0.1 prefix: 2 i32, 3 i64, 8 i32, 2+4+5 doubles; then 4 i32 of mode fields
+    assert _lib.CONFIG_SIZE_V1 == 8 + 24 + 32 + 8 * 11
+    assert C.sizeof(_lib.GpisConfig) == _lib.CONFIG_SIZE_V1 + 16
+    assert _lib.GpisConfig.loop_mode.offset == _lib.CONFIG_SIZE_V1
+    hdr = open(os.path.join(ROOT, "include", "gpis_b200.h")).read()
+    assert "#define GPIS_CONFIG_SIZE_V1 %d" % _lib.CONFIG_SIZE_V1 in hdr
+
+
+def test_library_reads_no_environment_variable():
+    """Behaviour is selected by gpis_config fields only (no getenv inside the product library)."""
+    src = os.path.join(ROOT, "gpis_b200", "csrc")
+    for f in os.listdir(src):
+        assert "getenv" not in open(os.path.join(src, f)).read(), f
 
 
 def test_status_strings(lib):
@@ -82,7 +93,7 @@ def test_header_is_valid_c_and_a_c_caller_gets_no_device(lib, tmp_path):
         pytest.skip("GPU present: covered by the gpu-marked C test")
     r = subprocess.run([exe, _lib.LIB_PATH], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "sizeof(gpis_config)=152" in r.stdout and "create status=-6" in r.stdout
+    assert "sizeof(gpis_config)=168" in r.stdout and "create status=-6" in r.stdout
 
 
 @pytest.mark.gpu

@@ -46,7 +46,7 @@ def host_exchange(eng, world):
 
 
 def _worker(rank, world, port, backend, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GPIS_EMU_SMS="2", GPIS_SOLVE_REGS="1")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), GPIS_EMU_SMS="2")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from gpis_b200 import GpisEngine, _lib

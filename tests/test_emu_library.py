@@ -131,12 +131,9 @@ def test_batch_and_panel_through_the_emulated_library(G):
     hyp = {"cov": np.array([np.log(2.0), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
     tr = dict(TRAIN, activeSetSize=9)
     res = select_batch_fused(objs, dims, 9, 11, **cfg)
-    for form in ("plain", "dmma"):                       # the other forms of the kernel, chosen by the environment
-        os.environ["GPIS_BATCH_KERNEL"] = form
-        try:
-            other = select_batch_fused(objs, dims, 9, 11, **cfg)
-        finally:
-            os.environ.pop("GPIS_BATCH_KERNEL", None)
+    from gpis_b200 import _lib as glib
+    for form in (glib.BATCH_PLAIN, glib.BATCH_DMMA):     # the other forms of the kernel (gpis_config.batch_kernel)
+        other = select_batch_fused(objs, dims, 9, 11, kernel=form, **cfg)
         for a, b in zip(res, other):
             assert np.array_equal(a["ids"], b["ids"]) and np.max(np.abs(a["mean"] - b["mean"])) < 1e-12
     for k in (0, 3):

@@ -30,13 +30,10 @@ def test_arguments_are_validated_before_the_device_is_touched():
         assert ei.value.status == _lib.ERR_NO_DEVICE
 
 
-@pytest.fixture(params=["plain", "tuned",
-                        pytest.param("dmma", marks=pytest.mark.xfail(strict=False, reason="opt-in tensor-pipe form of the "
-                                     "update: verified on the CPU emulation only in round 1 (no GPU minutes left)"))])
-def variant(request, monkeypatch):
-    """The forms of the kernel's inner loops (GPIS_BATCH_KERNEL, read at every gpis_batch_select)."""
-    monkeypatch.setenv("GPIS_BATCH_KERNEL", request.param)
-    return request.param
+@pytest.fixture(params=["plain", "tuned", "dmma"])
+def variant(request):
+    """The forms of the kernel's inner loops (gpis_config.batch_kernel)."""
+    return {"plain": _lib.BATCH_PLAIN, "tuned": _lib.BATCH_DFMA, "dmma": _lib.BATCH_DMMA}[request.param]
 
 
 @pytest.mark.gpu
@@ -46,7 +43,7 @@ def test_fused_batch_matches_solo_engines_and_oracle(variant):
     g, K, B = 16, 60, 7
     first = 3254 % g ** 3
     tsdfs = [superellipsoid_tsdf(g, k) for k in range(B)]
-    res = select_batch_fused(tsdfs, (g, g, g), K, first, **CFG)
+    res = select_batch_fused(tsdfs, (g, g, g), K, first, kernel=variant, **CFG)
     assert [r["object"] for r in res] == list(range(B)) and res[0]["device_ms"] > 0
     for k in (0, 3, 6):
         eng = gpis_b200.GpisEngine(3, g ** 3, K, **CFG)
@@ -82,7 +79,7 @@ def test_fused_batch_more_objects_than_sms_2d_and_device_input(variant):
     tsdfs = np.stack([np.clip((np.linalg.norm(pts - np.array(dims) * rng.uniform(0.35, 0.65, 2), axis=1)
                                - rng.uniform(2.5, 4.5)) / 2.0, -1, 1) + 1e-3 * rng.standard_normal(len(pts))
                       for _ in range(200)])
-    res = select_batch_fused(torch.as_tensor(tsdfs, device="cuda"), dims, K, 5, **CFG)
+    res = select_batch_fused(torch.as_tensor(tsdfs, device="cuda"), dims, K, 5, kernel=variant, **CFG)
     assert len(res) == 200
     hyp = {"cov": HYP["cov"], "mean": np.zeros(3), "lik": HYP["lik"]}
     for k in (0, 147, 148, 199):
@@ -93,6 +90,6 @@ def test_fused_batch_more_objects_than_sms_2d_and_device_input(variant):
         fm, fv, _ = O.predict_points(ora["gp"], pts)
         assert np.max(np.abs(res[k]["mean"] - fm)) < 1e-9 and np.max(np.abs(res[k]["var"] - fv)) < 1e-9
     # sharding the OBJECTS across ranks: rank r of 3 gets objects r::3
-    part = select_batch_fused(tsdfs, dims, K, 5, rank=1, world=3, keep_posterior=False, **CFG)
+    part = select_batch_fused(tsdfs, dims, K, 5, rank=1, world=3, keep_posterior=False, kernel=variant, **CFG)
     assert [r["object"] for r in part] == list(range(1, 200, 3))
     assert all(np.array_equal(r["ids"], res[r["object"]]["ids"]) for r in part)
