@@ -28,6 +28,10 @@
 
 namespace gpis {
 
+// lap timer of CTA 0 (globaltimer ns): each stamp books the time since the previous stamp
+enum { PCLK_RECWAIT = 0, PCLK_WPASS = 1, PCLK_BAR1 = 2, PCLK_FINISH = 3, PCLK_BAR2 = 4, PCLK_GEMM = 5, PCLK_EPI = 6,
+       PCLK_ARRIVE = 7, PCLK_PUBLISH = 8, PCLK_STEPS = 9, PCLK_N = 12 };
+
 #ifndef GPIS_EMULATE
 
 constexpr int PB = 3;                                   // rows of W per batch in phase B (3 x 16 + 16 doubles per thread)
@@ -39,9 +43,6 @@ constexpr size_t PERSIST_SMEM =
 static_assert((size_t)GPIPE * GSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
 
-// lap timer of CTA 0 (globaltimer ns): each stamp books the time since the previous stamp
-enum { PCLK_RECWAIT = 0, PCLK_WPASS = 1, PCLK_BAR1 = 2, PCLK_FINISH = 3, PCLK_BAR2 = 4, PCLK_GEMM = 5, PCLK_EPI = 6,
-       PCLK_ARRIVE = 7, PCLK_PUBLISH = 8, PCLK_STEPS = 9, PCLK_N = 12 };
 #define PSTAMP(slot)                                                       \
   do {                                                                     \
     if (cta == 0 && tid == 0) {                                            \
