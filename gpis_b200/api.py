@@ -172,7 +172,11 @@ def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hy
     """select_active_set_straddle.m:1-147 on the GPU engine.
 
     shapeParams: points (N,D), tsdf (N,), normals (N,D) or None/empty, noise (N,) or None/empty
-    trainingParams: activeSetSize, beta, eps, levelSet
+    trainingParams: activeSetSize, beta, eps, levelSet; optionally the discrete_gp_lse.m variant of
+      the rule: betaSchedule = ("gotovos", delta) for beta_t = 2 log(N t pi^2 / (6 delta))
+      (matlab/lse/discrete_gp_lse.m:87) and predictiveVariance = True for the variance GPML's gp()
+      returns (:297-299).  Its tolerance `tol` (:200-201) is `eps` here: ucb_max < tol is
+      hi - eps < h, ucb_min < tol is lo + eps > h.
     Returns (gpModel, predShape, testIndices) like the reference; predShape additionally
     carries the level-set state (ambiguity, high, low)."""
     pts = np.asarray(shapeParams["points"], np.float64)
@@ -185,8 +189,14 @@ def select_active_set_straddle(shapeParams, trainingParams, first_index=None, hy
     hyp = default_hyp(D) if hyp is None else hyp
     K = int(trainingParams["activeSetSize"])
     first = _default_first(N) if first_index is None else int(first_index)
+    sched = trainingParams.get("betaSchedule")
+    if sched is not None and sched[0] != "gotovos":
+        raise ValueError("betaSchedule must be ('gotovos', delta)")
     eng = GpisEngine(D, N, K, use_gradients=use_grad, level=float(trainingParams["levelSet"]),
                      eps=float(trainingParams["eps"]), beta=float(trainingParams["beta"]), precision=precision,
+                     beta_mode=_lib.BETA_GOTOVOS if sched is not None else _lib.BETA_FIXED,
+                     beta_delta=float(sched[1]) if sched is not None else 0.01,
+                     variance_mode=_lib.VAR_PREDICTIVE if trainingParams.get("predictiveVariance") else _lib.VAR_LATENT,
                      **_hyp_to_cfg(hyp, D))
     lat = detect_lattice(pts) if backend in ("auto", "grid") else None
     if backend == "grid" and lat is None:

@@ -437,7 +437,16 @@ def select_straddle_incremental(shape, train, first_index, hyp=None, prune=True,
     (block rank-nb) updates so that it runs at 32^3..128^3.  With prune=True
     only unclassified candidates are updated (the reference only predicts on
     them, straddle.m:79-81,93-96); classified ones are frozen.
-    Returns the same keys as the literal version, minus the refit model."""
+    Returns the same keys as the literal version, minus the refit model.
+
+    train may carry the discrete_gp_lse.m variant of the rule (matlab/lse/discrete_gp_lse.m):
+      "betaSchedule": ("gotovos", delta)  -> beta_t = 2 log(N t pi^2 / (6 delta)), t = 1, 2, ..  (:87)
+      "predictiveVariance": True          -> the variance GPML's gp() returns second (:297-299), which GPML
+                                             documents as the predictive variance (latent + noise); GPML is
+                                             not in the reference tree, so this reading is unverified there.
+    Its classification `ucb_max < tol -> below`, `ucb_min < tol -> above` (:200-201) with
+    ucb_max = hi - h, ucb_min = h - lo (:300-301) is the straddle's `hi - eps < h`, `lo + eps > h`
+    with eps = tol, so "eps" carries tol."""
     pts = np.asarray(shape["points"], np.float64)
     tsdf = np.asarray(shape["tsdf"], np.float64).reshape(-1)
     N, D = pts.shape
@@ -450,6 +459,8 @@ def select_straddle_incremental(shape, train, first_index, hyp=None, prune=True,
     hyp = default_hyp(D) if hyp is None else hyp
     nz = np.asarray(noise, np.float64).reshape(-1) if use_noise else np.full(N, np.exp(2.0 * hyp["lik"]))
     h, s, eps, K = float(train["levelSet"]), np.sqrt(float(train["beta"])), float(train["eps"]), int(train["activeSetSize"])
+    sched = train.get("betaSchedule")
+    pred_var = bool(train.get("predictiveVariance", False))
 
     gp = IncrementalGP(pts, hyp, K, use_grad)
     active = np.zeros(N, bool); high = np.zeros(N, bool); low = np.zeros(N, bool)
@@ -469,6 +480,10 @@ def select_straddle_incremental(shape, train, first_index, hyp=None, prune=True,
             break
         idx = np.flatnonzero(unc)
         mu, var = gp.mu[idx], gp.var[idx]
+        if pred_var:
+            var = var + nz[idx]
+        if sched is not None and sched[0] == "gotovos":                   # discrete_gp_lse.m:87
+            s = np.sqrt(2.0 * np.log(N * (_i - 1) * np.pi ** 2 / (6.0 * float(sched[1]))))
         hi = mu + s * var
         lo = mu - s * var
         amb = np.minimum(hi - h, h - lo)

@@ -11,11 +11,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ.setdefault("GPIS_EMULATE_TESTS", "1")
-import conftest                                           # noqa: E402  (builds / swaps in the emulated library)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emulated_gpu_plugin                                # noqa: E402  (builds / swaps in the emulated library)
 
-conftest._swap_in_the_emulated_library()
+emulated_gpu_plugin._swap_in_the_emulated_library()
 import gpis_b200                                          # noqa: E402
 from gpis_b200 import _lib                                # noqa: E402
 from gpis_b200.batch import select_batch_fused            # noqa: E402

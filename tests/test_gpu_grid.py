@@ -201,13 +201,24 @@ def test_batch_of_independent_objects_matches_solo_runs(G):
     res = select_batch(tsdfs, (g, g, g), K, 3254 % g ** 3, n_workers=4, **cfg)
     assert [r["object"] for r in res] == list(range(B))
     for k in (0, 5, 11):
-        eng = G.GpisEngine(3, g ** 3, K, **cfg)
+        # the pool's engines run the per-step launches (several handles share the device): the same form
+        # solo is bit-identical; the persistent kernel (the solo default) sums the factor append in another order
+        eng = G.GpisEngine(3, g ** 3, K, loop_mode=G._lib.LOOP_STEPS, append_mode=G._lib.APPEND_TWO_KERNELS, **cfg)
         eng.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdfs[k])
         eng.select(3254 % g ** 3, K)
         ids, nm = eng.active()
         mu, var = eng.candidate_posterior()
         assert np.array_equal(ids, res[k]["ids"]) and nm == res[k]["n_in_model"]
         assert np.array_equal(mu, res[k]["mean"]) and np.array_equal(var, res[k]["var"])   # bit-identical
+        eng.close()
+        eng = G.GpisEngine(3, g ** 3, K, **cfg)
+        eng.set_grid_candidates((g, g, g), (0, 0, 0), (1, 1, 1), tsdfs[k])
+        eng.select(3254 % g ** 3, K)
+        ids, nm = eng.active()
+        mu, var = eng.candidate_posterior()
+        assert np.array_equal(ids, res[k]["ids"]) and nm == res[k]["n_in_model"]
+        assert np.max(np.abs(mu - res[k]["mean"])) < 1e-12 and np.max(np.abs(var - res[k]["var"])) < 1e-12
+        eng.close()
     # objects differ from each other
     assert not np.array_equal(res[0]["ids"], res[1]["ids"])
 
