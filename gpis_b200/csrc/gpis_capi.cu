@@ -60,7 +60,8 @@ struct gpis_engine {
   bool persist = false;            // gpis_select runs the whole greedy loop in one cooperative kernel
   bool self_peer = false;          // world_size 1: the exchange region is this engine's own (flags release the CTAs)
   unsigned long long* d_phase_clk = nullptr;
-  size_t tile_cnt_cap = 0;
+  size_t tile_cnt_cap = 0, rlist_cap = 0;
+  bool persist_grid_ok = false;    // the lattice of the last gpis_set_grid_candidates fits the persistent kernel
   double persist_ms[12] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
   int solve1_ctas = 0;
   size_t solve_smem = 0;
@@ -610,17 +611,31 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     const int groups = txy * ((P.glen[2] + P.gemm_zgroup - 1) / P.gemm_zgroup);
     P.gws_segmax = P.gemm_ctas / groups + 2;
   }
+  // persistent selection kernel: 64 x 64 lattice tiles, a row list and a split-K counter per tile, two
+  // workspace slots per CTA
+  const long long tiles_q = (long long)((P.glen[0] + QT - 1) / QT) * ((P.glen[1] + QT - 1) / QT) * P.glen[2];
+  e->persist_grid_ok = e->persist && tiles_q <= QT_MAX && P.R_cap <= 65535;
   {
-    const size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
+    size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
+    if (e->persist_grid_ok) need = std::max(need, sizeof(double) * (size_t)e->num_sms * 2 * QTILE_ELEMS);
     if (need > e->gws_bytes) {
       CU(dalloc(e, &P.gws, need / sizeof(double)));
       e->gws_bytes = need;
     }
   }
-  if (e->persist && (size_t)2 * tiles > e->tile_cnt_cap) {
-    CU(dalloc(e, &P.tile_cnt, (size_t)2 * tiles));
-    e->tile_cnt_cap = (size_t)2 * tiles;
+  if (e->persist_grid_ok) {
+    if ((size_t)tiles_q > e->tile_cnt_cap) {
+      CU(dalloc(e, &P.tile_cnt, (size_t)tiles_q));
+      CU(dalloc(e, &P.rcnt, (size_t)tiles_q));
+      e->tile_cnt_cap = (size_t)tiles_q;
+    }
+    P.rlist_stride = (P.R_cap + 7) & ~7;
+    if ((size_t)tiles_q * P.rlist_stride > e->rlist_cap) {
+      CU(dalloc(e, &P.rlist, (size_t)tiles_q * P.rlist_stride));
+      e->rlist_cap = (size_t)tiles_q * P.rlist_stride;
+    }
   }
+  P.tile_e = GT;
   e->backend = 2;
   e->have_candidates = true;
   e->selecting = false;
@@ -638,15 +653,26 @@ __global__ void k_fill_ones_col0(double* T, float* Tf, int ld, long long rows) {
 }
 }  // namespace
 
+namespace {
+gpis_status select_begin_impl(gpis_handle e, int64_t first_local, void* stream, int tile_e);
+}
+
 gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
   GUARD(e);
+  return select_begin_impl(e, first_local, stream, GT);      // the per-step kernels work on 128 x 128 tiles
+}
+
+namespace {
+gpis_status select_begin_impl(gpis_handle e, int64_t first_local, void* stream, int tile_e) {
   if (!e->have_candidates) return fail(e, GPIS_ERR_STATE, "gpis_set_candidates has not been called");
   if (first_local >= e->P.N) return fail(e, GPIS_ERR_INVALID, "first index out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const long long n = std::max<long long>(e->P.N, e->P.n_tiles);
   if (e->backend == 2) {
-    GPIS_LAUNCH_SMEM(k_grid_init_state, (unsigned)((e->grid_slots + 255) / 256), 256, 0, s, e->P, (long long)e->grid_slots);
+    e->P.tile_e = tile_e;             // layout of the per-candidate state for THIS selection
+    const long long nslots = grid_slot_count(e->P);
+    GPIS_LAUNCH_SMEM(k_grid_init_state, (unsigned)((nslots + 255) / 256), 256, 0, s, e->P, nslots);
     CU(cudaGetLastError());
     e->launches++;
   } else if (n > 0) {
@@ -656,7 +682,10 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   }
   if (e->backend == 2) {
     CU(cudaMemsetAsync(e->P.W, 0, e->w_bytes, s));
-    if (e->P.tile_cnt) CU(cudaMemsetAsync(e->P.tile_cnt, 0, sizeof(unsigned) * e->tile_cnt_cap, s));
+    if (e->P.tile_cnt) {
+      CU(cudaMemsetAsync(e->P.tile_cnt, 0, sizeof(unsigned) * e->tile_cnt_cap, s));
+      CU(cudaMemsetAsync(e->P.rcnt, 0, sizeof(int) * e->tile_cnt_cap, s));
+    }
     if (e->P.bimg) CU(cudaMemsetAsync(e->P.bimg, 0, sizeof(float) * e->bimg_floats, s));
     CU(cudaMemsetAsync(e->d_Wt, 0, sizeof(double) * e->rk_pad * e->ldw, s));
     for (int d = 0; d < MAXD; ++d) {
@@ -676,6 +705,7 @@ gpis_status gpis_select_begin(gpis_handle e, int64_t first_local, void* stream) 
   e->inverse_rows = -1;
   return GPIS_OK;
 }
+}  // namespace
 
 gpis_status gpis_step_append(gpis_handle e, void* stream) {
   if (!e) return GPIS_ERR_INVALID;
@@ -773,11 +803,11 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   if (first_local < 0 && e->P.world == 1) return fail(e, GPIS_ERR_INVALID, "first index out of range");
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaEventRecord(e->ev0, s));
-  gpis_status rc = gpis_select_begin(e, first_local, stream);
+  // one persistent cooperative kernel for the whole greedy loop (lattice candidates, function values, fp64)
+  const bool persist = e->persist && e->backend == 2 && e->persist_grid_ok && !e->profiling && e->P.peer_mode && e->P.tile_cnt;
+  gpis_status rc = select_begin_impl(e, first_local, stream, persist ? QT : GT);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
-  // one persistent cooperative kernel for the whole greedy loop (lattice candidates, function values, fp64)
-  const bool persist = e->persist && e->backend == 2 && !e->profiling && e->P.peer_mode && e->P.tile_cnt;
   if (persist) {
     if (iters > 0) {
       Dispatch d = get_dispatch(e->D, false);
@@ -800,8 +830,9 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
     e->persist_ms[PCLK_STEPS] = (double)clk[PCLK_STEPS];
     // CTA 0's view of the phases, summed over the steps: W pass + finish (with their barriers) = append,
     // GEMM, fused epilogue
-    e->append_ms = e->persist_ms[PCLK_WPASS] + e->persist_ms[PCLK_BAR1] + e->persist_ms[PCLK_FINISH] + e->persist_ms[PCLK_BAR2];
-    e->main_ms = e->persist_ms[PCLK_GEMM];
+    e->append_ms = e->persist_ms[PCLK_WSETUP] + e->persist_ms[PCLK_WPASS] + e->persist_ms[PCLK_BAR1] + e->persist_ms[PCLK_FINISH] +
+                   e->persist_ms[PCLK_BAR2];
+    e->main_ms = e->persist_ms[PCLK_PREFIX] + e->persist_ms[PCLK_GEMM];
     e->epilogue_ms = e->persist_ms[PCLK_EPI];
     e->update_ms = e->main_ms + e->epilogue_ms;
     e->update_launches = (long long)clk[PCLK_STEPS];

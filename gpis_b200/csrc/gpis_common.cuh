@@ -111,6 +111,13 @@ struct EngineParams {
   int gws_segmax;
   int gemm_ctas;           // persistent grid of the update GEMM
   unsigned int* tile_cnt;  // persistent selection kernel: [2][tiles] split-K arrival counters (step parity)
+  // persistent selection kernel: tile edge of the per-candidate state layout of THIS selection (128 for the
+  // per-step kernels, 64 for the persistent kernel) and, per 64 x 64 tile, the list of model rows whose
+  // kernel factor over the tile's box is not below 2^-70 (the others cannot change a double-precision sum)
+  int tile_e;
+  unsigned short* rlist;   // [tiles][rlist_stride] model-row indices, append order (ascending)
+  int* rcnt;               // [tiles]
+  int rlist_stride;
   unsigned long long* phase_clk;   // persistent selection kernel: CTA 0's phase times (globaltimer ns), [8]
   long long spin_cycles;   // SM clocks an in-kernel wait (peer record, grid barrier) may take before it gives up
   // model

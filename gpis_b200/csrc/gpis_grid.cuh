@@ -32,15 +32,19 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 }
 #endif
 // Internal layout of the per-candidate state (mu, var, ambiguity, flags) in the grid backend:
-// tile-major, and inside a 128x128 tile the order of the update GEMM's accumulator fragments,
-// so that the epilogue streams it with fully coalesced 16-byte accesses.
+// tile-major, and inside a TE x TE tile (TE = P.tile_e: 128 for the per-step kernels, 64 for the persistent
+// selection kernel) the order of the update GEMM's accumulator fragments -- 8 warps as 4 (jy) x 2 (jx), each
+// warp tile (TE/4) x (TE/2) in 8 x 8 DMMA blocks -- so that the epilogue streams it with fully coalesced
+// 16-byte accesses.
+__host__ __device__ inline int grid_tile_edge(const EngineParams& P) { return P.tile_e > 0 ? P.tile_e : GT; }
 __host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, int jy, int tz) {
-  const int tiles_x = (P.glen[0] + GT - 1) / GT, tiles_y = (P.glen[1] + GT - 1) / GT;
-  const long long tile = ((long long)tz * tiles_y + jy / GT) * tiles_x + jx / GT;
-  const int my = jy % GT, mx = jx % GT;
-  const int gwarp = (my / 32) * 2 + mx / 64;
-  const int frag = (gwarp * 32 + ((my % 32) / 8) * 8 + (mx % 64) / 8) * 32 + (my % 8) * 4 + (mx % 8) / 2;
-  return tile * (GT * GT) + frag * 2 + (mx & 1);
+  const int TE = grid_tile_edge(P), WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
+  const int tiles_x = (P.glen[0] + TE - 1) / TE, tiles_y = (P.glen[1] + TE - 1) / TE;
+  const long long tile = ((long long)tz * tiles_y + jy / TE) * tiles_x + jx / TE;
+  const int my = jy % TE, mx = jx % TE;
+  const int gwarp = (my / WY) * 2 + mx / WX;
+  const int frag = ((gwarp * NI + (my % WY) / 8) * NJ + (mx % WX) / 8) * 32 + (my % 8) * 4 + (mx % 8) / 2;
+  return tile * (TE * TE) + frag * 2 + (mx & 1);
 }
 __host__ __device__ inline long long grid_slot_of_local(const EngineParams& P, long long jl) {
   const int nx = P.glen[0], ny = P.glen[1];
@@ -48,18 +52,24 @@ __host__ __device__ inline long long grid_slot_of_local(const EngineParams& P, l
 }
 // inverse: slot -> (jx, jy, tz); returns false for padding slots
 __host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
-  const int tiles_x = (P.glen[0] + GT - 1) / GT, tiles_y = (P.glen[1] + GT - 1) / GT;
-  const long long tile = slot / (GT * GT);
-  const int w = (int)(slot % (GT * GT));
+  const int TE = grid_tile_edge(P), WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
+  const int tiles_x = (P.glen[0] + TE - 1) / TE, tiles_y = (P.glen[1] + TE - 1) / TE;
+  const long long tile = slot / (TE * TE);
+  const int w = (int)(slot % (TE * TE));
   const int e = w & 1, frag = w >> 1;
   const int lane = frag & 31, t = frag >> 5;
-  const int j = t & 7, i = (t >> 3) & 3, gwarp = t >> 5;
-  const int my = (gwarp >> 1) * 32 + i * 8 + (lane >> 2);
-  const int mx = (gwarp & 1) * 64 + j * 8 + (lane & 3) * 2 + e;
+  const int j = t % NJ, i = (t / NJ) % NI, gwarp = t / (NJ * NI);
+  const int my = (gwarp >> 1) * WY + i * 8 + (lane >> 2);
+  const int mx = (gwarp & 1) * WX + j * 8 + (lane & 3) * 2 + e;
   tz = (int)(tile / (tiles_x * tiles_y));
-  jy = (int)((tile / tiles_x) % tiles_y) * GT + my;
-  jx = (int)(tile % tiles_x) * GT + mx;
+  jy = (int)((tile / tiles_x) % tiles_y) * TE + my;
+  jx = (int)(tile % tiles_x) * TE + mx;
   return jx < P.glen[0] && jy < P.glen[1];
+}
+// slots of the whole (tile-padded) lattice in the layout of this selection
+__host__ __device__ inline long long grid_slot_count(const EngineParams& P) {
+  const int TE = grid_tile_edge(P);
+  return (long long)((P.glen[0] + TE - 1) / TE) * ((P.glen[1] + TE - 1) / TE) * P.glen[2] * TE * TE;
 }
 
 __global__ void k_grid_init_state(EngineParams P, long long nslots) {

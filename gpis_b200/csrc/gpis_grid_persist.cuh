@@ -7,21 +7,26 @@
 // select_active_set_straddle.m:62-126; the phases of a step are separated by in-kernel grid
 // barriers (cooperative launch: all CTAs are co-resident by construction):
 //
-//   A  wait for the exchange records of this generation (local flags; peers store them over NVLink),
-//      every CTA picks the same winner
+//   A  the winner of the previous step: on one GPU every CTA reduces the per-CTA winners itself (no
+//      record, no flag); sharded, every CTA waits for the ranks' exchange records (local flags; peers
+//      store them over NVLink) and picks the same winner
 //   B  factor append, W pass: rows of W = L^-1 stream through a shared-memory ring by bulk async
 //      copies; three rows per batch: l[s] = W[s,:] k (ONE block reduction per batch, not per row) and,
 //      while the rows are still in registers, Y += l[s] W[s,:] into per-thread column accumulators.
-//      The last CTA also writes the winner's axis-table rows and the bookkeeping.         -- barrier
+//      The last CTA also writes the winner's axis-table rows and the bookkeeping; every CTA appends
+//      the new model row to the row lists of the lattice tiles it can reach.          -- barrier
 //   C  d, g_new and the new row of W = [-Y/d, 1/d] from the per-CTA partial Y's (fixed order)  -- barrier
 //   D  update GEMM v[jy,jx] = sum_rho (W[r,rho] Tz[rho][jz]) Ty[rho][jy] Tx[rho][jx] on the fp64 tensor
-//      pipe (DMMA.8x8x4), stream-K over all CTAs, with the epilogue FUSED: once the segments of a tile
-//      have arrived (per-tile counter), its contributors share the tile's epilogue -- sum of the
-//      split-K partials in segment order, posterior update, straddle score (straddle.m:106-108),
-//      classification (:122-125), arg-max.  CTA 0 reduces the per-CTA winners and publishes the next
-//      record (which is also what releases the other CTAs into the next step).
+//      pipe (DMMA.8x8x4) over 64 x 64 lattice tiles.  A tile only sums the model rows of ITS list: the
+//      rows whose SE factor over the tile's box is >= 2^-70 -- the dropped terms are below 2^-70 |W| each,
+//      far under one ulp of the sum, so the result is the double-precision sum of all rows.  Stream-K over
+//      the (tile, 16-row chunk) units of all lists; a tile that lies inside one CTA's range (most do)
+//      goes from the accumulator registers straight into the epilogue (posterior update, straddle score
+//      straddle.m:106-108, classification :122-125, arg-max) while the producer warp already fills the
+//      ring with the next tile's rows; a tile cut by a range boundary goes through a per-CTA workspace and its contributors
+//      share its epilogue.                                                            -- barrier
 //
-// mbarriers and the pipeline are set up inside the resident kernel; nothing returns to the host
+// mbarriers and the pipelines are set up once in the resident kernel; nothing returns to the host
 // until the selection has stopped.
 #pragma once
 #include "gpis_grid.cuh"
@@ -29,18 +34,29 @@
 namespace gpis {
 
 // lap timer of CTA 0 (globaltimer ns): each stamp books the time since the previous stamp
-enum { PCLK_RECWAIT = 0, PCLK_WPASS = 1, PCLK_BAR1 = 2, PCLK_FINISH = 3, PCLK_BAR2 = 4, PCLK_GEMM = 5, PCLK_EPI = 6,
-       PCLK_ARRIVE = 7, PCLK_PUBLISH = 8, PCLK_STEPS = 9, PCLK_N = 12 };
+enum { PCLK_RECWAIT = 0, PCLK_WSETUP = 1, PCLK_WPASS = 2, PCLK_BAR1 = 3, PCLK_FINISH = 4, PCLK_BAR2 = 5, PCLK_PREFIX = 6,
+       PCLK_GEMM = 7, PCLK_EPI = 8, PCLK_BAR3 = 9, PCLK_WINNER = 10, PCLK_STEPS = 11, PCLK_N = 12 };
+
+constexpr int QT = 64;                                  // lattice tile edge (jy x jx) of the persistent kernel
+constexpr int QKC = 16;                                 // model rows per pipeline stage
+constexpr int QLD = QT + 4;                             // padded smem row (conflict-free DMMA fragment loads)
+constexpr int QSTAGE_DOUBLES = 2 * QKC * QLD + QKC;     // Ty rows, Tx rows, coefficients
+constexpr int QPIPE = 8;
+constexpr int QTILE_ELEMS = QT * QT;
+constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment slots (x-adjacent pairs) per tile
+constexpr int QT_MAX = 2048;                            // most tiles per rank the kernel takes (prefix table in smem)
+// exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2
+constexpr double QCUT = 48.52030263919617;
 
 #ifndef GPIS_EMULATE
 
 constexpr int PB = 3;                                   // rows of W per batch in phase B (3 x 16 + 16 doubles per thread)
 constexpr int PRING_SLOTS_MAX = 24;
-constexpr int PRING_DOUBLES = 6 * GS1_RMAX;             // 192 KB ring (aliases the GEMM stages of phase D)
+constexpr int PRING_DOUBLES = 5 * GS1_RMAX;             // 160 KB ring (aliases the GEMM stages of phase D)
 constexpr int PCW = GEMM_CWARPS * 32;                   // 256 compute threads (warps 0-7); warp 8 produces
 constexpr size_t PERSIST_SMEM =
-    sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * GPIPE);
-static_assert((size_t)GPIPE * GSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
+    sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * QPIPE);
+static_assert((size_t)QPIPE * QSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
 
 #define PSTAMP(slot)                                                       \
@@ -105,6 +121,42 @@ __device__ __forceinline__ bool grid_barrier(const EngineParams& P, DevState* st
   return *s_flag != 0;
 }
 
+struct PBest {
+  double s;
+  long long id, j;
+};
+
+// posterior update + straddle rule for one accumulator fragment slot (two x-adjacent lattice points)
+__device__ __forceinline__ void persist_pair(const EngineParams& P, long long slot2, double2 v, double2 mu, double2 var, uchar2 fl,
+                                             double sb, double gn1, int nx, int ny, PBest& b) {
+  mu.x += v.x * gn1; mu.y += v.y * gn1;
+  var.x -= v.x * v.x; var.y -= v.y * v.y;
+  __stcg(reinterpret_cast<double2*>(P.mu) + slot2, mu);
+  __stcg(reinterpret_cast<double2*>(P.var) + slot2, var);
+  unsigned char f[2] = {fl.x, fl.y};
+  if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) return;
+  const double mus[2] = {mu.x, mu.y}, vars[2] = {var.x, var.y};
+  int jx, jy, tz;
+  grid_unslot(P, slot2 * 2, jx, jy, tz);
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
+    const long long jl = (long long)(jx + e) + (long long)nx * (jy + (long long)ny * tz);
+    double ve = vars[e];
+    if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise ? P.noise[jl] : P.noise_scalar);
+    const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
+    const double hi = __dadd_rn(mus[e], w), lo = __dadd_rn(mus[e], -w);
+    const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
+    if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
+    if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
+    if (sc == sc) {
+      const long long id = cand_id(P, jl);
+      if (better(sc, id, b.s, b.id)) { b.s = sc; b.id = id; b.j = jl; }
+    }
+  }
+  if (f[0] != fl.x || f[1] != fl.y) __stcg(reinterpret_cast<uchar2*>(P.flags) + slot2, make_uchar2(f[0], f[1]));
+}
+
 template <int D>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P, int iters) {
   GPIS_DYN_SMEM_F64A(p_smem);
@@ -113,14 +165,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
   unsigned long long* rfull = reinterpret_cast<unsigned long long*>(ring + PRING_DOUBLES);
   unsigned long long* rempty = rfull + PRING_SLOTS_MAX;
   unsigned long long* gfull = rempty + PRING_SLOTS_MAX;
-  unsigned long long* gempty = gfull + GPIPE;
+  unsigned long long* gempty = gfull + QPIPE;
   __shared__ double s_red[2][PB][GEMM_CWARPS];
   __shared__ double s_rec[PAY_HDR];
   __shared__ double s_gram[GEMM_THREADS / 32][2];
   __shared__ double s_fin[3];                             // dinv, g_new, ok
   __shared__ BlockBest s_bb[GEMM_CWARPS];
+  __shared__ BlockBest s_next;                            // the winner every CTA reduced at the end of the previous step
   __shared__ int s_win, s_flag;
-  __shared__ unsigned long long s_clk[PCLK_N], s_tk[1];      // CTA 0, thread 0 only: lap timer (globaltimer ns)
+  __shared__ int s_pref[QT_MAX + 1];                      // exclusive prefix of the tiles' chunk counts
+  __shared__ int s_wsum[GEMM_CWARPS];
+  __shared__ unsigned long long s_clk[PCLK_N], s_tk[1];   // CTA 0, thread 0 only: lap timer (globaltimer ns)
 
   DevState* st = P.st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -129,77 +184,143 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
   if (*(volatile int*)&st->done) return;
   // a function-only selection started by k_begin: rows == points == generation, so ONE counter (r0) carries
   // the loop state and the barrier count (3 per step) is derived from it
-  int r0 = 0;
   if (*(volatile int*)&st->r != 0 || *(volatile int*)&st->m != 0 || *(volatile int*)&st->iter != 0) return;
   for (int i = tid; i < GS1_RMAX; i += GEMM_THREADS) s_kv[i] = 0.0;
   if (tid == 0) {
+    for (int i = 0; i < QPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
     for (int i = 0; i < PRING_SLOTS_MAX; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS); }
-    for (int i = 0; i < GPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
     mbar_init_fence();
+    s_next.score = NEG_INF; s_next.id = 0x7fffffffffffffffLL; s_next.local = -1;
   }
   __syncthreads();
 
   const int nx = P.glen[0], ny = P.glen[1];
-  const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT, txy = tiles_x * tiles_y;
+  const int tiles_x = (nx + QT - 1) / QT, tiles_y = (ny + QT - 1) / QT, txy = tiles_x * tiles_y;
   const int T = txy * P.glen[2];
   if (tid < PCLK_N) s_clk[tid] = 0;
   if (tid == 0) s_tk[0] = gtimer_ns();
   int stop = 0;          // 1: nothing unclassified / capacity (done), 2: not positive definite
+  int gstage = 0;        // GEMM ring position, carried across the steps (the barriers' phases run on)
+  unsigned gphase = 0;
+  int w_nslots = -1;     // W ring: slots of the current geometry and rows streamed through it so far
+  unsigned wseq = 0;
+  const bool exchange = P.world > 1;
+  int r0 = 0;
 
-  for (; r0 < iters;) {
+  for (; r0 < iters; ++r0) {
     const int m = r0, gen = r0;
     unsigned passed = 3u * (unsigned)r0;
-    // ------------------------------------------------------------------ A: records, winner
-    if (!wait_records(P, st, gen)) return;
-    PSTAMP(PCLK_RECWAIT);
-    const double* recs = records_ptr(P, gen);
-    if (tid == 0) {
-      int win = -1;
-      double bs = 0.0;
-      long long bid = 0;
-      for (int w = 0; w < P.world; ++w) {
-        const double* pay = recs + (long long)w * P.pay_stride;
-        const long long loc = __double_as_longlong(__ldcg(pay + PAY_LOCAL));
-        if (loc < 0) continue;
-        const double sc = __ldcg(pay + PAY_SCORE);
-        const long long id = __double_as_longlong(__ldcg(pay + PAY_ID));
-        if (win < 0 || better(sc, id, bs, bid)) { win = w; bs = sc; bid = id; }
+    // ------------------------------------------------------------------ A: the winner
+    if (exchange || r0 == 0) {
+      if (!wait_records(P, st, gen)) return;
+      const double* recs = records_ptr(P, gen);
+      if (tid == 0) {
+        int win = -1;
+        double bs = 0.0;
+        long long bid = 0;
+        for (int w = 0; w < P.world; ++w) {
+          const double* pay = recs + (long long)w * P.pay_stride;
+          const long long loc = __double_as_longlong(__ldcg(pay + PAY_LOCAL));
+          if (loc < 0) continue;
+          const double sc = __ldcg(pay + PAY_SCORE);
+          const long long id = __double_as_longlong(__ldcg(pay + PAY_ID));
+          if (win < 0 || better(sc, id, bs, bid)) { win = w; bs = sc; bid = id; }
+        }
+        if (win >= 0 && m >= P.M_cap) win = -1;
+        s_win = win;
       }
-      if (win >= 0 && m >= P.M_cap) win = -1;
-      s_win = win;
+      __syncthreads();
+      if (s_win >= 0 && tid < PAY_HDR) s_rec[tid] = __ldcg(recs + (long long)s_win * P.pay_stride + tid);
+    } else {
+      // one GPU: the per-CTA winners were reduced by every CTA after the last barrier of the previous step
+      if (tid == 0) {
+        const long long jl = s_next.local;
+        const int win = (jl >= 0 && m < P.M_cap) ? 0 : -1;
+        s_win = win;
+        if (win >= 0) {
+          s_rec[PAY_SCORE] = s_next.score;
+          s_rec[PAY_ID] = __longlong_as_double(s_next.id);
+          s_rec[PAY_LOCAL] = __longlong_as_double(jl);
+          s_rec[PAY_TSDF] = P.tsdf[jl];
+          s_rec[PAY_NOISE] = P.noise ? P.noise[jl] : P.noise_scalar;
+          long long rem = jl;
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            const long long len = P.glen[d] > 0 ? P.glen[d] : 1;
+            const long long jd = rem % len + (d == 2 ? P.gz0 : 0);
+            rem /= len;
+            s_rec[PAY_X + d] = P.gorg[d] + P.gh[d] * (double)jd;
+          }
+        }
+      }
     }
     __syncthreads();
     const int win = s_win;
     if (win < 0) { stop = 1; break; }
-    if (tid < PAY_HDR) s_rec[tid] = __ldcg(recs + (long long)win * P.pay_stride + tid);
-    __syncthreads();
+    PSTAMP(PCLK_RECWAIT);
 
     // ------------------------------------------------------------------ B: W pass
     // rows s = cta + i*G of W; slot stride fits the longest row of this step
     const int my_rows = cta < r0 ? (r0 - 1 - cta) / G + 1 : 0;
     const int stride = (r0 + 2) & ~1;                                   // doubles, 16-byte multiple
     const int nslots = min(PRING_SLOTS_MAX, PRING_DOUBLES / (stride > 0 ? stride : 2));
-    if (tid == 0) {      // fresh phase bits every step (the slot count changes with the row length)
-      for (int i = 0; i < PRING_SLOTS_MAX; ++i) {
-        mbar_inval(&rfull[i]); mbar_inval(&rempty[i]);
-        mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS);
+    if (nslots != w_nslots) {      // new ring geometry (a few times per selection): fresh phase bits
+      if (tid == 0) {
+        for (int i = 0; i < PRING_SLOTS_MAX; ++i) {
+          mbar_inval(&rfull[i]); mbar_inval(&rempty[i]);
+          mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS);
+        }
+        mbar_init_fence();
       }
-      mbar_init_fence();
+      __syncthreads();
+      w_nslots = nslots;
+      wseq = 0;
     }
-    __syncthreads();
     double nxp[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) nxp[d] = s_rec[PAY_X + d];
     if (warp == GEMM_CWARPS) {
-      // producer warp: one bulk copy per row
+      // producer warp, lane 0: one bulk copy per row
       if (lane == 0) {
         for (int i = 0; i < my_rows; ++i) {
-          const int slot = i % nslots, use = i / nslots;
-          if (use > 0) mbar_wait(&rempty[slot], (unsigned)((use - 1) & 1));
+          const unsigned q = wseq + (unsigned)i;
+          const int slot = (int)(q % (unsigned)nslots);
+          const unsigned use = q / (unsigned)nslots;
+          if (use > 0) mbar_wait(&rempty[slot], (use - 1) & 1u);
           const int row = cta + i * G;
           const unsigned bytes = (unsigned)(((row + 2) >> 1) << 4);    // row + 1 doubles, rounded up to 16 B
           mbar_arrive_expect_tx(&rfull[slot], bytes);
           bulk_g2s(ring + (size_t)slot * stride, P.W + (long long)row * P.ldW, bytes, &rfull[slot]);
+        }
+      } else {
+        // lanes 1..31: the new model row joins the row list of every tile whose box it reaches
+        // (tiles cta, cta + G, ..: one writer per tile), and the tiles' split-K counters are cleared
+        for (int t = cta + (lane - 1) * G; t < T; t += 31 * G) {
+          const int tz = t / txy, ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+          double d2 = 0.0;
+          {
+            const double lo = P.gorg[0] + P.gh[0] * (double)(tx * QT), hi = P.gorg[0] + P.gh[0] * (double)(min(tx * QT + QT, nx) - 1);
+            const double a = fmin(lo, hi), b = fmax(lo, hi);
+            const double df = nxp[0] < a ? a - nxp[0] : (nxp[0] > b ? nxp[0] - b : 0.0);
+            d2 += df * df;
+          }
+          if (D > 1) {
+            const double p1 = nxp[D > 1 ? 1 : 0];
+            const double lo = P.gorg[1] + P.gh[1] * (double)(ty * QT), hi = P.gorg[1] + P.gh[1] * (double)(min(ty * QT + QT, ny) - 1);
+            const double a = fmin(lo, hi), b = fmax(lo, hi);
+            const double df = p1 < a ? a - p1 : (p1 > b ? p1 - b : 0.0);
+            d2 += df * df;
+          }
+          if (D > 2) {
+            const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - nxp[D > 2 ? 2 : 0];
+            d2 += df * df;
+          }
+          if (0.5 * d2 * P.inv_ell2 <= QCUT) {
+            const int n = __ldcg(P.rcnt + t);
+            P.rlist[(size_t)t * P.rlist_stride + n] = (unsigned short)r0;
+            __stcg(P.rcnt + t, n + 1);
+          }
+          P.tile_cnt[t] = 0u;
         }
       }
       // bookkeeping + the winner's axis-table rows: last CTA, this warp (the others stream rows)
@@ -233,6 +354,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
         s_kv[i] = P.sf2 * exp(-0.5 * d2 * P.inv_ell2);
       }
       named_sync(1, PCW);
+      PSTAMP(PCLK_WSETUP);
       double acc[GS1_CPT];
 #pragma unroll
       for (int c = 0; c < GS1_CPT; ++c) acc[c] = 0.0;
@@ -245,8 +367,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
           p[b] = 0.0;
           const int i = i0 + b;
           if (i < my_rows) {
-            const int slot = i % nslots, row = cta + i * G;
-            mbar_wait(&rfull[slot], (unsigned)((i / nslots) & 1));
+            const unsigned q = wseq + (unsigned)i;
+            const int slot = (int)(q % (unsigned)nslots), row = cta + i * G;
+            mbar_wait(&rfull[slot], (q / (unsigned)nslots) & 1u);
             const double* buf = ring + (size_t)slot * stride;
 #pragma unroll
             for (int c = 0; c < GS1_CPT; ++c) {
@@ -262,7 +385,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
         if (lane == 0) {
 #pragma unroll
           for (int b = 0; b < PB; ++b)
-            if (i0 + b < my_rows) mbar_arrive(&rempty[(i0 + b) % nslots]);
+            if (i0 + b < my_rows) mbar_arrive(&rempty[(int)((wseq + (unsigned)(i0 + b)) % (unsigned)nslots)]);
         }
 #pragma unroll
         for (int b = 0; b < PB; ++b) {
@@ -299,6 +422,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
           if (tid + PCW * c < r0) yp[PCW * c] = acc[c];
       }
     }
+    wseq += (unsigned)my_rows;
     PSTAMP(PCLK_WPASS);
     if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
     PSTAMP(PCLK_BAR1);
@@ -363,114 +487,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
     if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
     PSTAMP(PCLK_BAR2);
 
-    // ------------------------------------------------------------------ D: update GEMM + fused epilogue
-    const int C = (r0 + 1 + GKC - 1) / GKC;              // chunks per tile
-    const long long U = (long long)T * C;
+    // ------------------------------------------------------------------ D: update GEMM + epilogue
+    // exclusive prefix of the tiles' chunk counts (every tile has at least one chunk: its candidates are
+    // scored every step even when no model row reaches it)
+    {
+      const int per = (T + PCW - 1) / PCW;             // <= QT_MAX / 256 = 8
+      int cbuf[QT_MAX / PCW], loc = 0;
+      if (tid < PCW) {
+#pragma unroll
+        for (int k = 0; k < QT_MAX / PCW; ++k) {
+          const int t = tid * per + k;
+          int c = 0;
+          if (k < per && t < T) { c = (__ldcg(P.rcnt + t) + QKC - 1) / QKC; c = c > 0 ? c : 1; }
+          cbuf[k] = c;
+          loc += c;
+        }
+      }
+      int inc = loc;
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+      if (tid < PCW && lane == 31) s_wsum[warp] = inc;
+      __syncthreads();
+      if (tid < PCW) {
+        int run = inc - loc;
+        for (int w = 0; w < warp; ++w) run += s_wsum[w];
+#pragma unroll
+        for (int k = 0; k < QT_MAX / PCW; ++k) {
+          const int t = tid * per + k;
+          if (k < per && t < T) s_pref[t] = run;
+          run += cbuf[k];
+        }
+        if (tid == PCW - 1) s_pref[T] = run;
+      }
+      __syncthreads();
+    }
+    const long long U = s_pref[T];
     const int Gw = (int)min((long long)G, U);
     const bool working = cta < Gw;
     const long long u0 = working ? (long long)cta * U / Gw : 0, u1 = working ? (long long)(cta + 1) * U / Gw : 0;
-    const int n_units = (int)(u1 - u0), tile0 = (int)(u0 / C), c0 = (int)(u0 % C);
-    unsigned* tcnt = P.tile_cnt + (size_t)(gen & 1) * T;
-    unsigned* tcnt_next = P.tile_cnt + (size_t)((gen + 1) & 1) * T;
-    if (tid == 0) {
-      for (int i = 0; i < GPIPE; ++i) {
-        mbar_inval(&gfull[i]); mbar_inval(&gempty[i]);
-        mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS);
-      }
-      mbar_init_fence();
+    const int n_units = (int)(u1 - u0);
+    int tile0 = 0;
+    {   // last tile whose first unit is <= u0
+      int lo = 0, hi = T - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_pref[mid] <= u0) lo = mid; else hi = mid - 1; }
+      tile0 = lo;
     }
-    __syncthreads();
+    const int c0 = (int)(u0 - s_pref[tile0]);
+    PSTAMP(PCLK_PREFIX);
+    PBest best;
+    best.s = NEG_INF; best.id = 0x7fffffffffffffffLL; best.j = -1;
     if (warp == GEMM_CWARPS) {
       // ------------------------------- producer -------------------------------
-      int stage = 0;
-      unsigned phase = 0;
       const double* wrow = P.W + (long long)r0 * P.ldW;
-      const int klen = r0 + 1;
-      int tile = tile0, c = c0;
-      int tz = tile / txy, ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
+      int t = tile0, c = c0;
+      int cnt = 0, Ct = 1, tz = 0, ty = 0, tx = 0;
+      const unsigned short* rl = P.rlist;
+      bool fresh = true;
       for (int ul = 0; ul < n_units; ++ul) {
-        mbar_wait(&gempty[stage], phase ^ 1);
-        double* As = ring + (size_t)stage * GSTAGE_DOUBLES;
-        double* Bs = As + GKC * GLD;
-        double* cs = Bs + GKC * GLD;
-        const int rho0 = c * GKC;
-        if (lane < GKC) {
-          const int rho = rho0 + lane;
-          double cv = rho < klen ? __ldcg(wrow + rho) : 0.0;
-          cv *= __ldcg(P.T[2] + (long long)rho * P.ldt[2] + P.gz0 + tz);
+        if (fresh) {
+          cnt = __ldcg(P.rcnt + t);
+          Ct = s_pref[t + 1] - s_pref[t];
+          tz = t / txy; ty = (t / tiles_x) % tiles_y; tx = t % tiles_x;
+          rl = P.rlist + (size_t)t * P.rlist_stride;
+          fresh = false;
+        }
+        mbar_wait(&gempty[gstage], gphase ^ 1u);
+        double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
+        double* Bs = As + QKC * QLD;
+        double* cs = Bs + QKC * QLD;
+        const int k = c * QKC + (lane & (QKC - 1));
+        const int rho = k < cnt ? (int)__ldcg(rl + k) : 0;
+        if (lane < QKC) {
+          double cv = 0.0;
+          if (k < cnt) cv = __ldcg(wrow + rho) * __ldcg(P.T[2] + (long long)rho * P.ldt[2] + P.gz0 + tz);
           cs[lane] = cv;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * GKC * GT * (unsigned)sizeof(double));
+        if (lane == 0) mbar_arrive_expect_tx(&gfull[gstage], 2 * QKC * QT * (unsigned)sizeof(double));
         __syncwarp();
-        if (lane < GKC)
-          bulk_g2s(As + lane * GLD, P.T[1] + (long long)(rho0 + lane) * P.ldt[1] + ty * GT, GT * sizeof(double), &gfull[stage]);
+        if (lane < QKC)
+          bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + ty * QT, QT * sizeof(double), &gfull[gstage]);
         else
-          bulk_g2s(Bs + (lane - GKC) * GLD, P.T[0] + (long long)(rho0 + lane - GKC) * P.ldt[0] + tx * GT, GT * sizeof(double), &gfull[stage]);
-        if (++c == C) {
-          c = 0;
-          ++tile;
-          if (++tx == tiles_x) { tx = 0; if (++ty == tiles_y) { ty = 0; ++tz; } }
-        }
-        if (++stage == GPIPE) { stage = 0; phase ^= 1; }
+          bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + tx * QT, QT * sizeof(double), &gfull[gstage]);
+        if (++c == Ct) { c = 0; ++t; fresh = true; }
+        if (++gstage == QPIPE) { gstage = 0; gphase ^= 1u; }
       }
     } else {
       // --------------------------------- consumers ---------------------------------
-      int stage = 0;
-      unsigned phase = 0;
-      const int wm = warp >> 1, wn = warp & 1;
-      int ul = 0, tile = tile0, c = c0;
-      while (ul < n_units) {
-        const int seg_units = min(n_units - ul, C - c);
-        double acc[4][8][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int q = 0; q < seg_units; ++q) {
-          mbar_wait(&gfull[stage], phase);
-          const double* As = ring + (size_t)stage * GSTAGE_DOUBLES;
-          const double* Bs = As + GKC * GLD;
-          const double* cs = Bs + GKC * GLD;
-#pragma unroll
-          for (int k4 = 0; k4 < GKC / 4; ++k4) {
-            const int kb = k4 * 4 + (lane & 3);
-            const double cv = cs[kb];
-            double af[4], bf[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[kb * GLD + wm * 32 + i * 8 + (lane >> 2)] * cv;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = Bs[kb * GLD + wn * 64 + j * 8 + (lane >> 2)];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&gempty[stage]);
-          if (++stage == GPIPE) { stage = 0; phase ^= 1; }
-        }
-        ul += seg_units;
-        // partial accumulators of this (tile, segment) -> workspace (fragment order), then arrive on the tile
-        const int seg = cta - unit_owner((long long)tile * C, U, Gw);
-        double2* ws = reinterpret_cast<double2*>(P.gws + ((long long)tile * P.gws_segmax + seg) * GTILE_ELEMS);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            __stcg(&ws[(warp * 32 + i * 8 + j) * 32 + lane], make_double2(acc[i][j][0], acc[i][j][1]));
-        __threadfence();
-        named_sync(1, PCW);
-        if (tid == 0) {
-          if (seg == 0) *(volatile unsigned*)&tcnt_next[tile] = 0u;      // reset the other parity for the next step
-          atomicAdd(&tcnt[tile], 1u);
-        }
-        ++tile;
-        c = 0;
-      }
-      PSTAMP(PCLK_GEMM);
-
-      // ---- fused epilogue: the contributors of a tile share it, 256-slot units split by segment index
       const double sb = [&]() {
         double beta = P.beta;
         if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
@@ -478,89 +580,138 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
         return sqrt(beta);
       }();
       const double gn1 = s_fin[1];
-      double best_s = NEG_INF;
-      long long best_id = 0x7fffffffffffffffLL, best_j = -1;
+      const int wm = warp >> 1, wn = warp & 1;
+      int ul = 0, t = tile0, c = c0;
+      int def_t[2], ndef = 0;
+      while (ul < n_units) {
+        const int Ct = s_pref[t + 1] - s_pref[t];
+        const int seg_units = min(n_units - ul, Ct - c);
+        const bool whole = (c == 0) && (seg_units == Ct);
+        const long long tbase = (long long)t * QPAIRS;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int q = 0; q < seg_units; ++q) {
+          mbar_wait(&gfull[gstage], gphase);
+          const double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
+          const double* Bs = As + QKC * QLD;
+          const double* cs = Bs + QKC * QLD;
+#pragma unroll
+          for (int k4 = 0; k4 < QKC / 4; ++k4) {
+            const int kb = k4 * 4 + (lane & 3);
+            const double cv = cs[kb];
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = As[kb * QLD + wm * 16 + i * 8 + (lane >> 2)] * cv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[kb * QLD + wn * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gempty[gstage]);
+          if (++gstage == QPIPE) { gstage = 0; gphase ^= 1u; }
+        }
+        ul += seg_units;
+        if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
+          double2 pmu[2][4], pvar[2][4];
+          uchar2 pfl[2][4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const long long s2 = tbase + ((warp * 2 + i) * 4 + j) * 32 + lane;
+              pmu[i][j] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+              pvar[i][j] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+              pfl[i][j] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
+            }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              persist_pair(P, tbase + ((warp * 2 + i) * 4 + j) * 32 + lane, make_double2(acc[i][j][0], acc[i][j][1]),
+                           pmu[i][j], pvar[i][j], pfl[i][j], sb, gn1, nx, ny, best);
+        } else {
+          // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
+          // first tile, 1: its last), then arrive on the tile
+          double2* ws = reinterpret_cast<double2*>(P.gws) + ((size_t)cta * 2 + (t == tile0 ? 0 : 1)) * QPAIRS;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              __stcg(&ws[((warp * 2 + i) * 4 + j) * 32 + lane], make_double2(acc[i][j][0], acc[i][j][1]));
+          __threadfence();
+          named_sync(1, PCW);
+          if (tid == 0) atomicAdd(&P.tile_cnt[t], 1u);
+          def_t[ndef++] = t;
+        }
+        ++t;
+        c = 0;
+      }
+      PSTAMP(PCLK_GEMM);
+
+      // ---- tiles shared with neighbouring CTAs: wait for all segments, split the epilogue by segment index
       bool ok = true;
-      const int tile_last = n_units > 0 ? (int)((u1 - 1) / C) : tile0 - 1;
-      for (int tile = tile0; tile <= tile_last && ok; ++tile) {
-        const int g_first = unit_owner((long long)tile * C, U, Gw);
-        const int nseg = unit_owner((long long)(tile + 1) * C - 1, U, Gw) - g_first + 1;
+      for (int d = 0; d < ndef && ok; ++d) {
+        const int t2 = def_t[d];
+        const int g_first = unit_owner((long long)s_pref[t2], U, Gw);
+        const int nseg = unit_owner((long long)s_pref[t2 + 1] - 1, U, Gw) - g_first + 1;
         const int seg = cta - g_first;
-        if (tid == 0) s_flag = spin_ge(&tcnt[tile], (unsigned)nseg, P, st) ? 1 : 0;
+        if (tid == 0) s_flag = spin_ge(&P.tile_cnt[t2], (unsigned)nseg, P, st) ? 1 : 0;
         named_sync(1, PCW);
         if (!s_flag) { ok = false; break; }
         __threadfence();
-        constexpr int UNITS = GTILE_ELEMS / 2 / PCW;                   // 32 units of 256 fragment slots
+        constexpr int UNITS = QPAIRS / PCW;                              // 8 units of 256 fragment slots
         const int un0 = seg * UNITS / nseg, un1 = (seg + 1) * UNITS / nseg;
-        const double2* wsb = reinterpret_cast<const double2*>(P.gws + (long long)tile * P.gws_segmax * GTILE_ELEMS);
+        // the first contributor's partial sits in its slot 1 unless the tile starts its range
+        const int slot_first = ((long long)g_first * U / Gw == (long long)s_pref[t2]) ? 0 : 1;
+        const double2* wsb = reinterpret_cast<const double2*>(P.gws);
+        const long long tbase = (long long)t2 * QPAIRS;
         for (int ub = un0; ub < un1; ub += GEPI_SPT) {
           double2 v[GEPI_SPT], mu[GEPI_SPT], var[GEPI_SPT];
           uchar2 fl[GEPI_SPT];
 #pragma unroll
           for (int k = 0; k < GEPI_SPT; ++k) {
             const int q = (ub + k < un1 ? ub + k : un1 - 1) * PCW + tid;
-            v[k] = __ldcg(wsb + q);
+            v[k] = __ldcg(wsb + ((size_t)g_first * 2 + slot_first) * QPAIRS + q);
           }
           for (int sgi = 1; sgi < nseg; ++sgi) {
             double2 pz[GEPI_SPT];
 #pragma unroll
             for (int k = 0; k < GEPI_SPT; ++k) {
               const int q = (ub + k < un1 ? ub + k : un1 - 1) * PCW + tid;
-              pz[k] = __ldcg(wsb + (long long)sgi * (GTILE_ELEMS / 2) + q);
+              pz[k] = __ldcg(wsb + ((size_t)(g_first + sgi) * 2) * QPAIRS + q);
             }
 #pragma unroll
             for (int k = 0; k < GEPI_SPT; ++k) { v[k].x += pz[k].x; v[k].y += pz[k].y; }
           }
 #pragma unroll
           for (int k = 0; k < GEPI_SPT; ++k) {
-            const long long slot2 = (long long)tile * (GTILE_ELEMS / 2) + (ub + k < un1 ? ub + k : un1 - 1) * PCW + tid;
-            mu[k] = __ldcg(reinterpret_cast<const double2*>(P.mu) + slot2);
-            var[k] = __ldcg(reinterpret_cast<const double2*>(P.var) + slot2);
-            fl[k] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + slot2);
+            const long long s2 = tbase + (ub + k < un1 ? ub + k : un1 - 1) * PCW + tid;
+            mu[k] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+            var[k] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+            fl[k] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
           }
 #pragma unroll
           for (int k = 0; k < GEPI_SPT; ++k) {
             if (ub + k >= un1) continue;
-            const long long slot2 = (long long)tile * (GTILE_ELEMS / 2) + (ub + k) * PCW + tid;
-            mu[k].x += v[k].x * gn1; mu[k].y += v[k].y * gn1;
-            var[k].x -= v[k].x * v[k].x; var[k].y -= v[k].y * v[k].y;
-            __stcg(reinterpret_cast<double2*>(P.mu) + slot2, mu[k]);
-            __stcg(reinterpret_cast<double2*>(P.var) + slot2, var[k]);
-            unsigned char f[2] = {fl[k].x, fl[k].y};
-            if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) continue;
-            const double mus[2] = {mu[k].x, mu[k].y}, vars[2] = {var[k].x, var[k].y};
-            int jx, jy, tz;
-            grid_unslot(P, slot2 * 2, jx, jy, tz);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
-              const long long jl = (long long)(jx + e) + (long long)nx * (jy + (long long)ny * tz);
-              double ve = vars[e];
-              if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise ? P.noise[jl] : P.noise_scalar);
-              const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
-              const double hi = __dadd_rn(mus[e], w), lo = __dadd_rn(mus[e], -w);
-              const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-              if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
-              if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
-              if (sc == sc) {
-                const long long id = cand_id(P, jl);
-                if (better(sc, id, best_s, best_id)) { best_s = sc; best_id = id; best_j = jl; }
-              }
-            }
-            if (f[0] != fl[k].x || f[1] != fl[k].y)
-              __stcg(reinterpret_cast<uchar2*>(P.flags) + slot2, make_uchar2(f[0], f[1]));
+            persist_pair(P, tbase + (ub + k) * PCW + tid, v[k], mu[k], var[k], fl[k], sb, gn1, nx, ny, best);
           }
         }
       }
       if (!ok && tid == 0) persist_fail(st);
       // CTA winner
       for (int o = 16; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, best_s, o);
-        const long long oid = __shfl_xor_sync(0xffffffffu, best_id, o);
-        const long long oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-        if (oj >= 0 && better(os, oid, best_s, best_id)) { best_s = os; best_id = oid; best_j = oj; }
+        const double os = __shfl_xor_sync(0xffffffffu, best.s, o);
+        const long long oid = __shfl_xor_sync(0xffffffffu, best.id, o);
+        const long long oj = __shfl_xor_sync(0xffffffffu, best.j, o);
+        if (oj >= 0 && better(os, oid, best.s, best.id)) { best.s = os; best.id = oid; best.j = oj; }
       }
-      if (lane == 0) { s_bb[warp].score = best_s; s_bb[warp].id = best_id; s_bb[warp].local = best_j; }
+      if (lane == 0) { s_bb[warp].score = best.s; s_bb[warp].id = best.id; s_bb[warp].local = best.j; }
       named_sync(1, PCW);
       if (tid == 0) {
         BlockBest b = s_bb[0];
@@ -573,61 +724,50 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
       }
       PSTAMP(PCLK_EPI);
     }
-    // ---- arrive; CTA 0 waits for everyone, reduces the CTA winners and publishes the next record
-    __syncthreads();
-    if (tid == 0) s_win = *(volatile int*)&st->err;      // one reader: the exit must be uniform
-    __syncthreads();
-    if (s_win != 0) return;
-    ++passed;
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(&st->grid_bar, 1u);
-    }
-    r0 += 1;
-    if (cta == 0) {
-      if (tid == 0) {
-        s_flag = spin_ge(&st->grid_bar, passed * G, P, st) ? 1 : 0;
-        __threadfence();
-      }
-      __syncthreads();
-      if (!s_flag) { if (tid == 0) persist_fail(st); return; }
-      PSTAMP(PCLK_ARRIVE);
+    // ---- every CTA waits for all, then reduces the CTA winners itself: the same winner everywhere
+    if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
+    PSTAMP(PCLK_BAR3);
+    if (warp == 0) {
       BlockBest b;
       b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
-      if (warp == 0) {
-        for (int i = lane; i < G; i += 32) {
-          const BlockBest* pp = &P.partials[i];
-          const double ps = __ldcg(&pp->score);
-          const long long pid = __ldcg(&pp->id), ploc = __ldcg(&pp->local);
-          if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
-          const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
-          const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
-          if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; }
-        }
-        if (lane == 0) s_bb[0] = b;
+      for (int i = lane; i < G; i += 32) {
+        const BlockBest* pp = &P.partials[i];
+        const double ps = __ldcg(&pp->score);
+        const long long pid = __ldcg(&pp->id), ploc = __ldcg(&pp->local);
+        if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; }
       }
-      __syncthreads();
-      b = s_bb[0];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
+        const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
+        const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
+        if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; }
+      }
+      if (lane == 0) s_next = b;
+    }
+    __syncthreads();
+    if (cta == 0) {
       if (tid == 0) {
-        const int itx = r0 - 1;
+        const int itx = r0;
         if (itx <= P.M_cap) {
           P.hist[itx] = itx;
           P.hist[(P.M_cap + 1) + itx] = T;
           P.hist[2 * (P.M_cap + 1) + itx] = (int)min(P.N, (long long)0x7fffffff);
         }
         // state the host (and the finalize kernel) reads; iter tags the record published next
-        st->r = r0; st->r0 = r0 - 1; st->m = r0; st->n_sel = r0; st->iter = r0; st->gnew[0] = s_fin[1];
+        st->r = r0 + 1; st->r0 = r0; st->m = r0 + 1; st->n_sel = r0 + 1; st->iter = r0 + 1; st->gnew[0] = s_fin[1];
         st->nnoise = s_rec[PAY_NOISE];
 #pragma unroll
         for (int d = 0; d < D; ++d) st->nx[d] = s_rec[PAY_X + d];
       }
-      __syncthreads();
-      write_record(P, b.score, b.local, 0);
-      publish_record(P, st, r0, 0);
-      PSTAMP(PCLK_PUBLISH);
+      // sharded: this rank's record of every step goes to all peers; one GPU: only the last winner is
+      // published (the finalize kernel reads it)
+      if (exchange || r0 + 1 == iters) {
+        __syncthreads();
+        const BlockBest b = s_next;
+        write_record(P, b.score, b.local, 0);
+        publish_record(P, st, r0 + 1, 0);
+      }
+      PSTAMP(PCLK_WINNER);
       if (tid == 0) s_clk[PCLK_STEPS] += 1;
     }
   }

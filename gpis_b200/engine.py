@@ -285,8 +285,8 @@ class GpisEngine:
         return {"select_ms": a.value, "predict_ms": b.value, "update_ms": c.value, "update_launches": n.value,
                 "append_ms": p.value, "main_ms": q.value, "epilogue_ms": r.value}
 
-    PERSIST_SLOTS = ("record_wait", "w_pass", "barrier1", "new_row", "barrier2", "gemm", "epilogue", "arrive_wait",
-                     "publish", "steps")
+    PERSIST_SLOTS = ("record_wait", "w_setup", "w_pass", "barrier1", "new_row", "barrier2", "prefix", "gemm", "epilogue",
+                     "barrier3", "winner", "steps")
 
     def persist_timing(self):
         """Lap times (ms, block 0's clock) of the persistent selection kernel in the last select()."""

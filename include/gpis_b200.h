@@ -252,9 +252,10 @@ gpis_status gpis_get_timing(gpis_handle h, double* select_ms, double* predict_ms
  * main update kernel (k_update / k_grid_gemm) and of the grid backend's epilogue kernel. */
 gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main_ms, double* epilogue_ms);
 /* The persistent selection kernel's own lap timer (block 0, %globaltimer), summed over the steps of the
- * last gpis_select, ms: [0] wait for the exchange records, [1] W pass of the factor append, [2] grid
- * barrier, [3] new row of W, [4] grid barrier, [5] update GEMM, [6] fused epilogue, [7] wait for all
- * blocks, [8] winner reduction + record publication, [9] = number of steps (a count, not ms). */
+ * last gpis_select, ms: [0] winner / wait for the exchange records, [1] covariance of the winner with the model
+ * rows, [2] W pass of the factor append, [3] grid barrier, [4] new row of W, [5] grid barrier, [6] unit prefix,
+ * [7] update GEMM with the in-register epilogues of whole tiles, [8] epilogues of tiles shared between blocks,
+ * [9] grid barrier, [10] winner reduction (+ record publication when sharded), [11] = number of steps (a count). */
 gpis_status gpis_get_persist_timing(gpis_handle h, double* ms12);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
  * stream (plain launches instead of the captured graph). */

@@ -33,6 +33,7 @@ def test_arguments_are_validated_before_the_device_is_touched():
 @pytest.fixture(params=["plain", "tuned", "dmma"])
 def variant(request):
     """The forms of the kernel's inner loops (gpis_config.batch_kernel)."""
+    from gpis_b200 import _lib
     return {"plain": _lib.BATCH_PLAIN, "tuned": _lib.BATCH_DFMA, "dmma": _lib.BATCH_DMMA}[request.param]
 
 
