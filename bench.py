@@ -99,63 +99,49 @@ def _all_host_threads():
 
 
 def cpu_reference_job(args, pts, tsdf, first, select_budget_s, max_select_steps):
-    """The reference's CPU path on a bounded sample of the workload: ONE prefix of the greedy selection
-    (oracle/cpu_baseline.py, the incremental restatement of select_active_set_straddle.m:62-126 that the
-    fixtures tie to the literal loop) + a dense prediction sample (gp_mean.m / gp_cov.m on the final model,
-    straddle.m:136-145).  The whole-job time is the prefix as measured plus, for the remaining steps, the model
-    t(k) = a + b * U_k * k fitted to the prefix's own per-step times (U_k = unclassified candidates scored at
-    step k, k = model rows); U_k beyond the prefix comes from the committed full-size CPU run
-    (tests/golden/seq_c3.npz `scored`) when it covers them, else it is held at the last observed value."""
+    """The reference's CPU path on the same workload: the greedy selection of select_active_set_straddle.m:62-126
+    restated with incremental updates (oracle/cpu_baseline.py).  Two restatements exist: select_compact keeps
+    V = L^-1 K(active, unclassified candidates) like the reference's GPU loop keeps its kernel vectors (memory-bound;
+    45 minutes for 3800 of the 3999 steps on 8 cores, then out of memory), and select_separable, which like this
+    engine never stores V and forms each new row of it with one dense product from the separable SE factors of the
+    lattice (compute-bound; the whole job in minutes).  The FASTER one is timed here, with all host threads; the
+    running posterior of every lattice point is part of its state, so the posterior grid needs no extra pass.
+    The selection runs for at most `select_budget_s` seconds; when that is not the whole job the rest is the model
+    t(k) = a + b k fitted to the measured per-step times (the product's cost is linear in the model rows k)."""
     from oracle import cpu_baseline as B          # reported baseline only; never on the product path
     th = _all_host_threads()
     hyp = hyp_dict()
     train = {"activeSetSize": args.active, "beta": BETA, "eps": EPS, "levelSet": LEVEL}
     N = pts.shape[0]
+    g = args.grid
     total_steps = args.active - 1
-    sel = B.select_compact(pts, tsdf, hyp, train, first, max_steps=min(total_steps, max_select_steps),
-                           time_budget_s=select_budget_s)
+    sel = B.select_separable((g, g, g), tsdf, hyp, train, first, max_steps=min(total_steps, max_select_steps),
+                             time_budget_s=select_budget_s)
     ts = np.asarray(sel["step_seconds"], np.float64)
-    n = int(min(ts.size, len(sel["scored"])))
-    ts, U = ts[:n], np.asarray(sel["scored"], np.float64)[:n]
+    n = int(ts.size)
     k = np.arange(1, n + 1, dtype=np.float64)
-    A = np.stack([np.ones(n), U * k], axis=1)
+    A = np.stack([np.ones(n), k], axis=1)
     coef, *_ = np.linalg.lstsq(A, ts, rcond=None)
     a_fit, b_fit = float(max(coef[0], 0.0)), float(max(coef[1], 0.0))
-    U_rest, src = None, "held at the last observed value"
-    if n < total_steps:
-        try:
-            z = np.load(os.path.join(ROOT, "tests", "golden", "seq_c3.npz"))
-            if int(z["grid"]) == args.grid and int(z["K"]) == args.active and len(z["scored"]) >= total_steps:
-                U_rest, src = z["scored"][n:total_steps].astype(np.float64), "tests/golden/seq_c3.npz (full CPU run)"
-        except Exception:
-            pass
-        if U_rest is None:
-            U_rest = np.full(total_steps - n, U[-1] if n else float(N))
+    stopped_early = n < total_steps and len(sel["order"]) < n + 1
+    if n < total_steps and not stopped_early:
         k_rest = np.arange(n + 1, total_steps + 1, dtype=np.float64)
-        est_rest = float(np.sum(a_fit + b_fit * U_rest * k_rest))
+        est_rest = float(np.sum(a_fit + b_fit * k_rest))
     else:
         est_rest = 0.0
-    meas_sel = float(ts.sum())
-    est_sel = meas_sel + est_rest
-    rng = np.random.default_rng(1)
-    band = np.flatnonzero(np.abs(tsdf) < 0.9)
-    sub = rng.choice(band, size=min(args.active, band.size), replace=False)
-    nq = min(N, args.ref_predict_points)
-    qidx = rng.choice(N, size=nq, replace=False)
-    t1 = time.perf_counter()
-    L, alpha = B.dense_model(pts[sub], tsdf[sub], hyp)
-    B.predict_dense(pts[sub], (L, alpha), pts[qidx], hyp)
-    t_pred = time.perf_counter() - t1
-    est_pred = t_pred * N / nq
-    est = est_sel + est_pred
+    meas = float(ts.sum())
+    est = meas + est_rest
     resid = float(np.sqrt(np.mean((A @ np.array([a_fit, b_fit]) - ts) ** 2))) if n else 0.0
-    return {"est_total_s": est, "est_select_s": est_sel, "est_predict_s": est_pred, "measured_s": meas_sel + t_pred,
-            "prefix_steps": n, "prefix_seconds": meas_sel, "fit": {"a_s": a_fit, "b_s_per_candidate_row": b_fit, "rms_resid_s": resid},
-            "threads": th,
-            "sample": (f"first {n} of {total_steps} selection steps over all {N} candidates measured in {meas_sel:.1f} s; rest from "
-                       f"t(k) = {a_fit:.3g} + {b_fit:.3g} * U_k * k s fitted to those steps (rms residual {resid:.3g} s), U_k {src}: "
-                       f"{est_rest:.0f} s; dense {sub.size}-pt prediction of {nq} of {N} grid points measured in {t_pred:.2f} s, scaled "
-                       f"linearly: {est_pred:.0f} s; whole job {est:.0f} s; {th['cores']} cores, BLAS threads {th['blas_threads']}")}
+    whole = est_rest == 0.0
+    return {"est_total_s": est, "est_select_s": est, "est_predict_s": 0.0, "measured_s": meas,
+            "prefix_steps": n, "prefix_seconds": meas, "fit": {"a_s": a_fit, "b_s_per_row": b_fit, "rms_resid_s": resid},
+            "threads": th, "whole_job_measured": whole, "order": sel["order"],
+            "sample": ((f"the WHOLE job measured: all {n} selection steps over all {N} lattice points, running posterior grid included, {meas:.1f} s"
+                        if whole else
+                        f"first {n} of {total_steps} selection steps over all {N} lattice points (running posterior grid included) measured in "
+                        f"{meas:.1f} s; rest from t(k) = {a_fit:.3g} + {b_fit:.3g} * k s fitted to those steps (rms residual {resid:.3g} s): "
+                        f"{est_rest:.0f} s; whole job {est:.0f} s") +
+                       f"; oracle/cpu_baseline.py::select_separable (the faster of the two CPU restatements), {th['cores']} cores, BLAS threads {th['blas_threads']}")}
 
 
 def run_reference(args):
@@ -178,7 +164,8 @@ def run_reference(args):
                  "ms_per_step is the whole-job estimate the sample gives, measured_sample_ms what was actually timed"),
         "cpu_baseline": {"value": value, "unit": "pts/s", "cores": r["threads"]["cores"], "blas_threads": r["threads"]["blas_threads"],
                          "kind": "port", "sample": r["sample"], "prefix_steps": r["prefix_steps"],
-                         "prefix_seconds": r["prefix_seconds"], "fit": r["fit"]},
+                         "prefix_seconds": r["prefix_seconds"], "fit": r["fit"], "whole_job_measured": r["whole_job_measured"]},
+        "n_selected": int(len(r["order"])), "ids_crc32_of_measured_picks": int(__import__("zlib").crc32(np.asarray(r["order"], np.int64).tobytes())),
         "e2e": {"value": value, "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out))
@@ -264,7 +251,8 @@ def run_ours(args):
     def timed(host, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {"select_ms": 0.0, "predict_ms": 0.0, "update_ms": 0.0, "alg_bytes": 0.0, "panel_bytes": 0.0,
-               "update_launches": 0, "alg_flops": 0.0, "append_ms": 0.0, "main_ms": 0.0, "epilogue_ms": 0.0}
+               "update_launches": 0, "alg_flops": 0.0, "append_ms": 0.0, "main_ms": 0.0, "epilogue_ms": 0.0,
+               "persist": {}, "persist_steps": 0.0}
         barrier()
         e0.record()
         for _ in range(steps):
@@ -281,6 +269,12 @@ def run_ours(args):
             acc["alg_bytes"] += float(np.sum(8.0 * u * (r + 1) + u * (2 * 8 + 2)))
             acc["panel_bytes"] += float(np.sum(8.0 * 64 * tl * (r + 1)))
             acc["alg_flops"] += float(np.sum(2.0 * n_loc * (r + 1)))
+            if grid_backend:
+                pt = eng.persist_timing()
+                if pt["steps"] > 0:
+                    acc["persist_steps"] += pt["steps"]
+                    for k, v in pt.items():
+                        acc["persist"][k] = acc["persist"].get(k, 0.0) + v
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -303,9 +297,14 @@ def run_ours(args):
     step(True)
     ms_e2e, _ = timed(True, args.steps)
     # (3) instrumented: the same steps with a CUDA event pair around every update-kernel launch on
-    #     the launching stream (plain launches instead of the graph) -> roofline numerator/denominator
+    #     the launching stream (plain launches instead of the graph) -> roofline numerator/denominator.
+    #     The persistent selection kernel (one launch per selection) carries its own lap timer instead
+    #     (block 0, %globaltimer, one stamp per phase and step): its phases are read from the production run.
     ms_inst, acc = ms_dev, None
-    if not args.no_profile:
+    persist_used = grid_backend and eng.persist_timing()["steps"] > 0
+    if persist_used:
+        ms_inst, acc = timed(False, args.steps)
+    elif not args.no_profile:
         eng.set_profiling(True)
         sel.profile = True
         step(False)
@@ -349,7 +348,8 @@ def run_ours(args):
     post_sum = [float(cs[0]), float(cs[1])]
 
     # whole-job aggregates over ranks
-    tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"], acc["alg_flops"]], dtype=torch.float64, device=dev)
+    tot = torch.tensor([acc["alg_bytes"], acc["panel_bytes"], acc["alg_flops"], acc["persist"].get("units", 0.0)],
+                       dtype=torch.float64, device=dev)
     mx = torch.tensor([acc["update_ms"], acc["select_ms"], acc["predict_ms"], acc["main_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -385,7 +385,17 @@ def run_ours(args):
             # tcgen05 kind::tf32 runs at half the bf16 rate; three MMAs per algorithmic product (3xTF32)
             tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
             tach = 3.0 * tach
-        roof = {"kernel": "k_grid_gemm (per-step [ny x r] x [r x nx] contraction per z-slice on the fp64 tensor "
+        if persist_used:
+            # executed flops: (tile, 16-row chunk) units x 2 * 64 * 64 * 16, counted by the kernel itself; the phase
+            # time is rank 0's block-0 lap timer summed over the steps (phase D: unit prefix, coefficient
+            # precompute, MMAs and the in-register epilogues of whole tiles)
+            exe_flops = float(tot[3]) / args.steps * 2.0 * 64 * 64 * 16
+            tach = exe_flops / main_s / 1e12
+            ps = {k: v / args.steps for k, v in acc["persist"].items()}
+        roof = {"kernel": ("k_grid_persist, update-GEMM phase (per step and 64 x 64 lattice tile a [64 x rows] x [rows x 64] contraction over the "
+                           "model rows within reach of the tile, fp64 tensor pipe DMMA.8x8x4; stream-K over one resident CTA per SM)")
+                if persist_used else
+                "k_grid_gemm (per-step [ny x r] x [r x nx] contraction per z-slice on the fp64 tensor "
                           "pipe, DMMA.8x8x4; stream-K over 148 persistent CTAs)",
                 "with_epilogue_kernel_tflops": float(tot[2]) / args.steps / upd_s / 1e12,
                 "bound": "tensor", "achieved": tach, "peak": tpeak, "unit": "TFLOP/s", "frac": tach / tpeak,
@@ -397,6 +407,17 @@ def run_ours(args):
                 "traffic_note": "DRAM bytes read+written per launch from the committed ncu --set full capture (profiles/, launch at r~300): the operands come from L2, the kernel is not HBM-bound",
                 "algorithmic_flops_per_step": float(tot[2]) / args.steps,
                 "launches_per_step": acc["update_launches"] / args.steps}
+        if persist_used:
+            roof.update({
+                "executed_flops_per_step": exe_flops, "dense_flops_per_step": float(tot[2]) / args.steps,
+                "executed_over_dense": exe_flops / (float(tot[2]) / args.steps),
+                "flops_note": ("achieved / frac use the flops the MMAs EXECUTED: terms whose SE factor over a tile is below 2^-70 "
+                               "are not summed (they cannot change the fp64 result), so the executed flops are a fraction of the dense "
+                               "2 N (r + 1) per step that SURVEY 8(d) counts; dense_equivalent_tflops = dense flops / the same time"),
+                "dense_equivalent_tflops": float(tot[2]) / args.steps / main_s / 1e12,
+                "whole_job_executed_tflops": exe_flops / s_dev / 1e12, "whole_job_frac": exe_flops / s_dev / 1e12 / tpeak,
+                "launches_per_step": 1, "timer": "in-kernel lap timer of block 0 (%globaltimer), rank 0",
+                "traffic": None, "traffic_note": "operands (axis-table rows, 12 MB) and the posterior state come from L2; see profiles/ for the ncu capture"})
     else:
         roof = None
     out = {
@@ -408,9 +429,11 @@ def run_ours(args):
         "grid_pts_note": ("lattice points of the posterior grid / whole-job seconds: the running posterior of the lattice IS the grid, "
                           "it is a by-product of the selection and only copied out at the end") if grid_backend else "N / dense prediction seconds",
         "instrumented_ms_per_step": ms_inst / args.steps,
-        "phase_ms": {"note": "from the instrumented steps (per-launch CUDA events, plain launches)", "select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
+        "phase_ms": ({"note": "persistent selection kernel: lap timer of rank 0's block 0 (%globaltimer), summed over the steps of one selection",
+                      "select": 1e3 * sel_s, "predict": 1e3 * pred_s, **{("rank0_" + k): v for k, v in ps.items()}} if persist_used else
+                     {"note": "from the instrumented steps (per-launch CUDA events, plain launches)", "select": 1e3 * sel_s, "update_kernel": 1e3 * upd_s, "predict": 1e3 * pred_s,
                      "rank0_append_kernels": acc["append_ms"] / args.steps, "rank0_main_kernel": acc["main_ms"] / args.steps,
-                     "rank0_epilogue_kernel": acc["epilogue_ms"] / args.steps},
+                     "rank0_epilogue_kernel": acc["epilogue_ms"] / args.steps}),
         "n_selected": n_sel, "n_in_model": n_model,
         "ids_crc32": int(__import__("zlib").crc32(np.asarray(ids, np.int64).tobytes())),
         "parity": parity_block(args, ids, n_model, h_mean.numpy() if world == 1 else None, h_var.numpy() if world == 1 else None),
@@ -527,7 +550,8 @@ def cpu_baseline(args, pts, tsdf, first):
     r = cpu_reference_job(args, pts, tsdf, first, select_budget_s=args.cpu_baseline_budget_s, max_select_steps=args.ref_select_steps)
     return {"value": args.active / r["est_total_s"], "unit": "pts/s", "cores": r["threads"]["cores"],
             "blas_threads": r["threads"]["blas_threads"], "kind": "port", "sample": r["sample"],
-            "prefix_steps": r["prefix_steps"], "prefix_seconds": r["prefix_seconds"], "fit": r["fit"]}
+            "prefix_steps": r["prefix_steps"], "prefix_seconds": r["prefix_seconds"], "fit": r["fit"],
+            "whole_job_measured": r["whole_job_measured"]}
 
 
 def main():
@@ -538,8 +562,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=128)
     ap.add_argument("--active", type=int, default=4000)
-    ap.add_argument("--ref-select-steps", type=int, default=1200, help="reference arm: longest selection prefix timed on the CPU")
-    ap.add_argument("--ref-budget-s", type=float, default=200.0, help="reference arm: time budget of that prefix")
+    ap.add_argument("--ref-select-steps", type=int, default=1 << 30, help="reference arm: most selection steps timed on the CPU")
+    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="reference arm: time budget of the CPU selection (the whole job when it fits)")
     ap.add_argument("--cpu-baseline-budget-s", type=float, default=25.0, help="our arm's cpu_baseline leg: time budget of its prefix")
     ap.add_argument("--ref-predict-points", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -9,7 +9,8 @@ from .api import (GpModel, create_gpis, create_sparse_gpis, default_hyp, evaluat
                   select_active_set_straddle)
 from .engine import GpisEngine
 from .selector import GaussianProcessHyperparams, GpuActiveSetSelector, PredictionError
+from .tsdf import auto_tsdf, build_tsdf
 
 __all__ = ["GpisEngine", "GpuActiveSetSelector", "GaussianProcessHyperparams", "PredictionError", "GpModel", "create_gpis", "create_sparse_gpis", "default_hyp", "evaluate_errors",
            "gp_cov", "gp_mean", "predict_2d_grid", "predict_grid", "predict_points", "select_active_set",
-           "select_active_set_straddle", "sample_shapes"]
+           "select_active_set_straddle", "sample_shapes", "auto_tsdf", "build_tsdf"]

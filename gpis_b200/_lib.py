@@ -24,7 +24,8 @@ SYMBOLS = [
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
     "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing", "gpis_batch_select",
-    "gpis_get_persist_timing",
+    "gpis_get_persist_timing", "gpis_build_tsdf", "gpis_set_candidates_f32", "gpis_set_grid_candidates_f32",
+    "gpis_get_active_f32", "gpis_predict_f32", "gpis_get_candidate_posterior_f32",
 ]
 
 
@@ -41,6 +42,16 @@ class GpisConfig(C.Structure):
         ("beta_delta", C.c_double),
         ("loop_mode", C.c_int32), ("append_mode", C.c_int32), ("batch_kernel", C.c_int32),
         ("spin_timeout_ms", C.c_int32),
+    ]
+
+
+class GpisTsdfParams(C.Structure):
+    """gpis_tsdf_params (include/gpis_b200.h): varParams of matlab/core/auto_tsdf.m."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("edge_win", C.c_int32), ("specular_noise", C.c_int32), ("noise_grad_mode", C.c_int32),
+        ("noise_scale", C.c_double), ("occlusion_scale", C.c_double), ("interior_rate", C.c_double),
+        ("sparsity_rate", C.c_double), ("horiz_scale", C.c_double), ("vert_scale", C.c_double),
+        ("occ_y_low", C.c_double * 3), ("occ_y_high", C.c_double * 3), ("occ_x_low", C.c_double * 3), ("occ_x_high", C.c_double * 3),
     ]
 
 
@@ -105,6 +116,12 @@ def load():
         "gpis_get_sampling_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "gpis_batch_select": [C.POINTER(GpisConfig), vp, vp, vp, C.c_int32, dp, C.c_int64, C.c_int32, vp, vp, vp,
                               dp, dp, u8p, C.POINTER(C.c_double), vp],
+        "gpis_set_candidates_f32": [vp, dp, dp, dp, dp, vp, vp],
+        "gpis_set_grid_candidates_f32": [vp, vp, vp, vp, C.c_int32, C.c_int32, dp, dp, dp, vp],
+        "gpis_get_active_f32": [vp, C.c_int32, vp, vp, i32p, i32p, vp],
+        "gpis_predict_f32": [vp, dp, C.c_int64, dp, dp, dp, vp],
+        "gpis_get_candidate_posterior_f32": [vp, dp, dp, vp],
+        "gpis_build_tsdf": [u8p, C.c_int32, C.c_int32, C.POINTER(GpisTsdfParams), dp, dp, dp, dp, vp, i32p, C.c_int32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)

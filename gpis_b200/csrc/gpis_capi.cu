@@ -25,6 +25,7 @@ constexpr size_t TF32_SMEM = 0;
 template <int NB>
 void k_grid_gemm_tf32(EngineParams) {}
 constexpr size_t PERSIST_SMEM = 0;      // in-kernel grid barriers are not emulated either: the per-step path runs
+constexpr int PTHREADS = 32;
 template <int D>
 void k_grid_persist(EngineParams, int) {}
 }  // namespace gpis
@@ -34,6 +35,7 @@ void k_grid_persist(EngineParams, int) {}
 #include "gpis_batch.cuh"
 #include "gpis_sample.cuh"
 #include "gpis_select.cuh"
+#include "gpis_tsdf.cuh"
 
 using namespace gpis;
 
@@ -60,9 +62,9 @@ struct gpis_engine {
   bool persist = false;            // gpis_select runs the whole greedy loop in one cooperative kernel
   bool self_peer = false;          // world_size 1: the exchange region is this engine's own (flags release the CTAs)
   unsigned long long* d_phase_clk = nullptr;
-  size_t tile_cnt_cap = 0, rlist_cap = 0;
+  size_t tile_cnt_cap = 0, rlist_cap = 0, tt_cap[MAXD] = {0, 0, 0};
   bool persist_grid_ok = false;    // the lattice of the last gpis_set_grid_candidates fits the persistent kernel
-  double persist_ms[12] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
+  double persist_ms[16] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
   int solve1_ctas = 0;
   size_t solve_smem = 0;
   size_t table_bytes[MAXD] = {0, 0, 0};
@@ -442,7 +444,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
       // kernels with in-kernel grid barriers need every CTA resident: one per SM, or not at all
       int occ2 = 0, occp = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void*)disp.g_solve2, GSOLVE_THREADS, GS2_SMEM));
-      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, (const void*)disp.g_persist, GEMM_THREADS, PERSIST_SMEM));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, (const void*)disp.g_persist, PTHREADS, PERSIST_SMEM));
       if (!coop || occ2 < 1) e->solve_ring = false;
       if (!coop || occp < 1) e->persist = false;
 #endif
@@ -629,9 +631,18 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
       CU(dalloc(e, &P.rcnt, (size_t)tiles_q));
       e->tile_cnt_cap = (size_t)tiles_q;
     }
-    P.rlist_stride = (P.R_cap + 7) & ~7;
+    P.ldtt = e->rk_pad;
+    for (int d = 0; d < D; ++d) {
+      const size_t need = (size_t)P.gtlen[d] * (size_t)P.ldtt;
+      if (need > e->tt_cap[d]) {
+        CU(dalloc(e, &P.TT[d], need));
+        e->tt_cap[d] = need;
+      }
+    }
+    P.rlist_stride = (P.R_cap + 15) & ~15;      // whole 16-row chunks, 32-byte aligned
     if ((size_t)tiles_q * P.rlist_stride > e->rlist_cap) {
       CU(dalloc(e, &P.rlist, (size_t)tiles_q * P.rlist_stride));
+      CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));
       e->rlist_cap = (size_t)tiles_q * P.rlist_stride;
     }
   }
@@ -813,7 +824,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
       Dispatch d = get_dispatch(e->D, false);
       int it_arg = iters;
       void* args[] = {(void*)&e->P, (void*)&it_arg};
-      CU(launch_cooperative(d.g_persist, (unsigned)e->num_sms, GEMM_THREADS, PERSIST_SMEM, s, args));
+      CU(launch_cooperative(d.g_persist, (unsigned)e->num_sms, PTHREADS, PERSIST_SMEM, s, args));
       e->launches += 1;
     }
     rc = gpis_select_end(e, stream);
@@ -828,6 +839,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
     if (iters > 0) CU(cudaMemcpy(clk, e->d_phase_clk, sizeof(clk), cudaMemcpyDeviceToHost));
     for (int i = 0; i < PCLK_N; ++i) e->persist_ms[i] = (double)clk[i] * 1e-6;
     e->persist_ms[PCLK_STEPS] = (double)clk[PCLK_STEPS];
+    e->persist_ms[PCLK_UNITS] = (double)clk[PCLK_UNITS];
     // CTA 0's view of the phases, summed over the steps: W pass + finish (with their barriers) = append,
     // GEMM, fused epilogue
     e->append_ms = e->persist_ms[PCLK_WSETUP] + e->persist_ms[PCLK_WPASS] + e->persist_ms[PCLK_BAR1] + e->persist_ms[PCLK_FINISH] +
@@ -1453,9 +1465,226 @@ gpis_status gpis_get_phase_timing(gpis_handle e, double* append_ms, double* main
   return GPIS_OK;
 }
 
-gpis_status gpis_get_persist_timing(gpis_handle e, double* ms12) {
-  if (!e || !ms12) return GPIS_ERR_INVALID;
-  for (int i = 0; i < 12; ++i) ms12[i] = e->persist_ms[i];
+// ---------------------------------------------------------------------------------------------------
+// float entry points: the reference's ABI is fp32 (include/gpu_active_set_selector.hpp:41-46,
+// include/active_set_selection_types.h:16-41).  The engine computes in fp64; these convert on the device.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_f32_to_f64(const float* __restrict__ a, double* __restrict__ b, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (double)a[i];
+}
+__global__ void k_f64_to_f32(const double* __restrict__ a, float* __restrict__ b, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (float)a[i];
+}
+// y_a = m(x_a) + (L g)[row of f(x_a)]: the targets of the model points from the replicated factor
+__global__ void k_active_targets(EngineParams P, int m, int NB, int D, float* inputs, float* targets, int ld_out) {
+  const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (a >= m) return;
+  const long long row = (long long)a * NB;
+  double acc = 0.0;
+  for (long long c = lane; c <= row; c += 32) acc += P.L[row * P.R_cap + c] * P.g[c];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    double mf = P.mean_c;
+    for (int d = 0; d < D; ++d) mf += P.mean_w[d] * P.AX[d][a];
+    if (targets) targets[a] = (float)(mf + acc);
+    if (inputs)
+      for (int d = 0; d < D; ++d) inputs[a + (long long)d * ld_out] = (float)P.AX[d][a];      // active_inputs[a + d*max_active]
+  }
+}
+bool ptr_on_device(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+// n floats at a host or device pointer -> doubles on the device (scratch)
+cudaError_t stage_in_f32(Scratch& sc, const float* src, size_t n, cudaStream_t s, double** out) {
+  *out = nullptr;
+  if (!src || !n) return cudaSuccess;
+  const float* dsrc = src;
+  float* tmp = nullptr;
+  cudaError_t ce = cudaSuccess;
+  if (!ptr_on_device(src)) {
+    if ((ce = sc.get(&tmp, n)) != cudaSuccess) return ce;
+    if ((ce = cudaMemcpyAsync(tmp, src, sizeof(float) * n, cudaMemcpyHostToDevice, s)) != cudaSuccess) return ce;
+    dsrc = tmp;
+  }
+  if ((ce = sc.get(out, n)) != cudaSuccess) return ce;
+  k_f32_to_f64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dsrc, *out, n);
+  return cudaGetLastError();
+}
+// n doubles on the device -> floats at a host or device pointer
+cudaError_t stage_out_f32(Scratch& sc, const double* dsrc, float* dst, size_t n, cudaStream_t s) {
+  if (!dst || !n) return cudaSuccess;
+  float* ddst = dst;
+  cudaError_t ce = cudaSuccess;
+  const bool dev = ptr_on_device(dst);
+  if (!dev && (ce = sc.get(&ddst, n)) != cudaSuccess) return ce;
+  k_f64_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dsrc, ddst, n);
+  if ((ce = cudaGetLastError()) != cudaSuccess) return ce;
+  if (!dev) ce = cudaMemcpyAsync(dst, ddst, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
+  return ce;
+}
+}  // namespace
+
+gpis_status gpis_set_candidates_f32(gpis_handle e, const float* pts, const float* tsdf, const float* normals, const float* noise,
+                                    const int64_t* ids, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  Scratch sc;
+  double *dp = nullptr, *dt = nullptr, *dn = nullptr, *dz = nullptr;
+  CU(stage_in_f32(sc, pts, N * e->D, s, &dp));
+  CU(stage_in_f32(sc, tsdf, N, s, &dt));
+  CU(stage_in_f32(sc, normals, N * e->D, s, &dn));
+  CU(stage_in_f32(sc, noise, N, s, &dz));
+  gpis_status rc = gpis_set_candidates(e, pts ? dp : nullptr, tsdf ? dt : nullptr, dn, dz, ids, stream);
+  CU(cudaStreamSynchronize(s));
+  return rc;
+}
+
+gpis_status gpis_set_grid_candidates_f32(gpis_handle e, const int32_t* dims, const double* origin, const double* spacing,
+                                         int32_t z0, int32_t nz_total, const float* tsdf, const float* normals,
+                                         const float* noise, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  Scratch sc;
+  double *dt = nullptr, *dn = nullptr, *dz = nullptr;
+  CU(stage_in_f32(sc, tsdf, N, s, &dt));
+  CU(stage_in_f32(sc, normals, N * e->D, s, &dn));
+  CU(stage_in_f32(sc, noise, N, s, &dz));
+  gpis_status rc = gpis_set_grid_candidates(e, dims, origin, spacing, z0, nz_total, tsdf ? dt : nullptr, dn, dz, stream);
+  CU(cudaStreamSynchronize(s));
+  return rc;
+}
+
+gpis_status gpis_get_active_f32(gpis_handle e, int32_t max_size, float* active_inputs, float* active_targets,
+                                int32_t* n_selected, int32_t* n_in_model, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  cudaStream_t s = (cudaStream_t)stream;
+  gpis_status rc = read_state(e, s);
+  if (rc != GPIS_OK) return rc;
+  const int m = e->host_state.m;
+  if (n_selected) *n_selected = e->host_state.n_sel;
+  if (n_in_model) *n_in_model = m;
+  if (m == 0 || (!active_inputs && !active_targets)) return GPIS_OK;
+  if (max_size < m) return fail(e, GPIS_ERR_INVALID, "max_size smaller than the number of model points");
+  Scratch sc;
+  float *din = nullptr, *dtg = nullptr;
+  CU(sc.get(&din, (size_t)max_size * e->D));
+  CU(sc.get(&dtg, (size_t)max_size));
+  CU(cudaMemsetAsync(din, 0, sizeof(float) * (size_t)max_size * e->D, s));
+  CU(cudaMemsetAsync(dtg, 0, sizeof(float) * (size_t)max_size, s));
+  GPIS_LAUNCH_SMEM(k_active_targets, (unsigned)((m + 7) / 8), 256, 0, s, e->P, m, e->NB, e->D, din, dtg, (int)max_size);
+  CU(cudaGetLastError());
+  e->launches++;
+  if (active_inputs) CU(cudaMemcpyAsync(active_inputs, din, sizeof(float) * (size_t)max_size * e->D, cudaMemcpyDefault, s));
+  if (active_targets) CU(cudaMemcpyAsync(active_targets, dtg, sizeof(float) * (size_t)max_size, cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_predict_f32(gpis_handle e, const float* query, int64_t nq, float* mean, float* var, float* normals, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  if (nq < 0 || (nq && (!query || !mean || !var))) return fail(e, GPIS_ERR_INVALID, "query, mean and var are required");
+  if (nq == 0) return GPIS_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)nq;
+  Scratch sc;
+  double *dq = nullptr, *dout = nullptr;
+  CU(stage_in_f32(sc, query, n * e->D, s, &dq));
+  CU(sc.get(&dout, n * (2 + e->D)));
+  gpis_status rc = gpis_predict(e, dq, nq, dout, dout + n, normals ? dout + 2 * n : nullptr, stream);
+  if (rc != GPIS_OK) return rc;
+  CU(stage_out_f32(sc, dout, mean, n, s));
+  CU(stage_out_f32(sc, dout + n, var, n, s));
+  if (normals) CU(stage_out_f32(sc, dout + 2 * n, normals, n * e->D, s));
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_candidate_posterior_f32(gpis_handle e, float* mean, float* var, void* stream) {
+  if (!e) return GPIS_ERR_INVALID;
+  GUARD(e);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t N = (size_t)e->P.N;
+  if (!N) return GPIS_OK;
+  Scratch sc;
+  double* d = nullptr;
+  CU(sc.get(&d, 2 * N));
+  gpis_status rc = gpis_get_candidate_posterior(e, d, d + N, stream);
+  if (rc != GPIS_OK) return rc;
+  CU(stage_out_f32(sc, d, mean, N, s));
+  CU(stage_out_f32(sc, d + N, var, N, s));
+  CU(cudaStreamSynchronize(s));
+  return GPIS_OK;
+}
+
+gpis_status gpis_build_tsdf(const uint8_t* inside, int32_t rows, int32_t cols, const gpis_tsdf_params* prm, const double* u,
+                            double* tsdf, double* normals, double* noise, int32_t* valid_idx, int32_t* n_valid,
+                            int32_t device, void* stream) {
+  gpis_engine* e = nullptr;             // the CU() macro records messages on a handle; there is none here
+  if (!inside || !prm || rows < 1 || cols < 1 || (long long)rows * cols > 0x7fffffffLL) return fail(e, GPIS_ERR_INVALID, "bad image");
+  if (prm->struct_size != (int32_t)sizeof(gpis_tsdf_params)) return fail(e, GPIS_ERR_INVALID, "gpis_tsdf_params.struct_size");
+  if (prm->edge_win < 0 || prm->noise_grad_mode < 0 || prm->noise_grad_mode > 4 || !(prm->noise_scale > 0.0))
+    return fail(e, GPIS_ERR_INVALID, "edge_win / noise_grad_mode / noise_scale out of range");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return GPIS_ERR_NO_DEVICE; }
+  int dev = -1;
+  CU(cudaGetDevice(&dev));
+  DeviceGuard guard(device >= 0 ? device : dev);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)rows * cols;
+  TsdfParams P;
+  P.rows = rows; P.cols = cols;
+  P.edge_win = prm->edge_win; P.specular = prm->specular_noise; P.grad_mode = prm->noise_grad_mode;
+  P.noise_scale = prm->noise_scale; P.occlusion_scale = prm->occlusion_scale; P.interior_rate = prm->interior_rate;
+  P.sparsity_rate = prm->sparsity_rate; P.horiz_scale = prm->horiz_scale; P.vert_scale = prm->vert_scale;
+  for (int k = 0; k < 3; ++k) {
+    P.y_low[k] = prm->occ_y_low[k]; P.y_high[k] = prm->occ_y_high[k];
+    P.x_low[k] = prm->occ_x_low[k]; P.x_high[k] = prm->occ_x_high[k];
+  }
+  Scratch sc;
+  unsigned char *d_in = nullptr, *d_valid = nullptr;
+  double *d_t = nullptr, *d_nz = nullptr, *d_g = nullptr, *d_u = nullptr;
+  int *d_idx = nullptr, *d_cnt = nullptr;
+  CU(sc.get(&d_in, n));
+  CU(sc.get(&d_valid, n));
+  CU(sc.get(&d_t, n));
+  CU(sc.get(&d_nz, n));
+  CU(sc.get(&d_g, 2 * n));
+  CU(sc.get(&d_idx, n));
+  CU(sc.get(&d_cnt, 1));
+  CU(cudaMemcpyAsync(d_in, inside, n, cudaMemcpyDefault, s));
+  if (u) {
+    CU(sc.get(&d_u, 3 * n));
+    CU(cudaMemcpyAsync(d_u, u, sizeof(double) * 3 * n, cudaMemcpyDefault, s));
+  }
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  GPIS_LAUNCH_SMEM(k_tsdf_levels, blocks, 256, 0, s, d_in, d_t, rows, cols);
+  GPIS_LAUNCH_SMEM(k_tsdf_noise_normals, blocks, 256, 0, s, d_t, d_u, d_nz, d_g, d_g + n, d_valid, P);
+  GPIS_LAUNCH_SMEM(k_tsdf_compact, 1, 1024, 0, s, d_valid, (long long)n, d_idx, d_cnt);
+  CU(cudaGetLastError());
+  if (tsdf) CU(cudaMemcpyAsync(tsdf, d_t, sizeof(double) * n, cudaMemcpyDefault, s));
+  if (normals) CU(cudaMemcpyAsync(normals, d_g, sizeof(double) * 2 * n, cudaMemcpyDefault, s));
+  if (noise) CU(cudaMemcpyAsync(noise, d_nz, sizeof(double) * n, cudaMemcpyDefault, s));
+  if (valid_idx) CU(cudaMemcpyAsync(valid_idx, d_idx, sizeof(int) * n, cudaMemcpyDefault, s));
+  if (n_valid) CU(cudaMemcpyAsync(n_valid, d_cnt, sizeof(int), cudaMemcpyDefault, s));
+  CU(cudaStreamSynchronize(s));         // the scratch is released on return
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_persist_timing(gpis_handle e, double* ms16) {
+  if (!e || !ms16) return GPIS_ERR_INVALID;
+  for (int i = 0; i < 16; ++i) ms16[i] = e->persist_ms[i];
   return GPIS_OK;
 }
 

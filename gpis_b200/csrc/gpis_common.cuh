@@ -116,6 +116,9 @@ struct EngineParams {
   // kernel factor over the tile's box is not below 2^-70 (the others cannot change a double-precision sum)
   int tile_e;
   unsigned short* rlist;   // [tiles][rlist_stride] model-row indices, append order (ascending)
+  double* TT[MAXD];        // transposed axis tables [axis index][ldtt rows] (the winner's covariance with the model rows)
+  long long ldtt;
+  double* rtz;             // [tiles][rlist_stride] the rows' z-axis factor at the tile's slice
   int* rcnt;               // [tiles]
   int rlist_stride;
   unsigned long long* phase_clk;   // persistent selection kernel: CTA 0's phase times (globaltimer ns), [8]

@@ -35,7 +35,10 @@ namespace gpis {
 
 // lap timer of CTA 0 (globaltimer ns): each stamp books the time since the previous stamp
 enum { PCLK_RECWAIT = 0, PCLK_WSETUP = 1, PCLK_WPASS = 2, PCLK_BAR1 = 3, PCLK_FINISH = 4, PCLK_BAR2 = 5, PCLK_PREFIX = 6,
-       PCLK_GEMM = 7, PCLK_EPI = 8, PCLK_BAR3 = 9, PCLK_WINNER = 10, PCLK_STEPS = 11, PCLK_N = 12 };
+       PCLK_GEMM = 7, PCLK_EPI = 8, PCLK_BAR3 = 9, PCLK_WINNER = 10, PCLK_STEPS = 11,
+       // inside PCLK_GEMM (booked twice): coefficient precompute, waits for a filled stage, in-register epilogues; the
+       // (tile, 16-row chunk) units of ALL blocks (a count: x 2 * 64 * 64 * 16 = the flops the MMAs executed)
+       PCLK_PRECOMP = 12, PCLK_WAITFULL = 13, PCLK_EPIREG = 14, PCLK_UNITS = 15, PCLK_N = 16 };
 
 constexpr int QT = 64;                                  // lattice tile edge (jy x jx) of the persistent kernel
 constexpr int QKC = 16;                                 // model rows per pipeline stage
@@ -47,17 +50,28 @@ constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment 
 constexpr int QT_MAX = 2048;                            // most tiles per rank the kernel takes (prefix table in smem)
 // exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2
 constexpr double QCUT = 48.52030263919617;
+constexpr int QBLK = 256;                               // units whose coefficients sit in shared memory at a time
 
 #ifndef GPIS_EMULATE
+#ifndef GPIS_EXP
+#define GPIS_EXP 0
+#endif
 
 constexpr int PB = 3;                                   // rows of W per batch in phase B (3 x 16 + 16 doubles per thread)
 constexpr int PRING_SLOTS_MAX = 24;
 constexpr int PRING_DOUBLES = 5 * GS1_RMAX;             // 160 KB ring (aliases the GEMM stages of phase D)
-constexpr int PCW = GEMM_CWARPS * 32;                   // 256 compute threads (warps 0-7); warp 8 produces
+constexpr int PCW = GEMM_CWARPS * 32;                   // 256 compute threads (warps 0-7)
+// Warps 8..11 produce.  A bulk copy with a per-lane address compiles to a serial elect-one loop (R2UR + UBLKCP per
+// lane, ~40 cycles each), so ONE warp issuing the 32 row copies of a unit cannot keep up with 0.5 us of DMMA work
+// per unit: four producer warps take every fourth unit each.  (Registers are allocated per 4 warps: 12 warps cost
+// the same 168 registers per thread as 9.)
+constexpr int QPROD = 4;
+constexpr int PTHREADS = (GEMM_CWARPS + QPROD) * 32;
 constexpr size_t PERSIST_SMEM =
     sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * QPIPE);
 static_assert((size_t)QPIPE * QSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
+static_assert(QBLK * QKC <= GS1_RMAX, "the coefficients of a block alias the covariance vector");
 
 #define PSTAMP(slot)                                                       \
   do {                                                                     \
@@ -127,8 +141,9 @@ struct PBest {
 };
 
 // posterior update + straddle rule for one accumulator fragment slot (two x-adjacent lattice points)
-__device__ __forceinline__ void persist_pair(const EngineParams& P, long long slot2, double2 v, double2 mu, double2 var, uchar2 fl,
-                                             double sb, double gn1, int nx, int ny, PBest& b) {
+// jl: lattice index (x fastest) of the slot's first point; its x-neighbour is the second
+__device__ __forceinline__ void persist_pair(const EngineParams& P, long long slot2, long long jl0, double2 v, double2 mu, double2 var,
+                                             uchar2 fl, double sb, double gn1, PBest& b) {
   mu.x += v.x * gn1; mu.y += v.y * gn1;
   var.x -= v.x * v.x; var.y -= v.y * v.y;
   __stcg(reinterpret_cast<double2*>(P.mu) + slot2, mu);
@@ -136,12 +151,10 @@ __device__ __forceinline__ void persist_pair(const EngineParams& P, long long sl
   unsigned char f[2] = {fl.x, fl.y};
   if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) return;
   const double mus[2] = {mu.x, mu.y}, vars[2] = {var.x, var.y};
-  int jx, jy, tz;
-  grid_unslot(P, slot2 * 2, jx, jy, tz);
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
-    const long long jl = (long long)(jx + e) + (long long)nx * (jy + (long long)ny * tz);
+    const long long jl = jl0 + e;
     double ve = vars[e];
     if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise ? P.noise[jl] : P.noise_scalar);
     const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
@@ -149,7 +162,7 @@ __device__ __forceinline__ void persist_pair(const EngineParams& P, long long sl
     const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
     if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
     if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
-    if (sc == sc) {
+    if (sc >= b.s) {          // (false for NaN) the id only matters on a tie
       const long long id = cand_id(P, jl);
       if (better(sc, id, b.s, b.id)) { b.s = sc; b.id = id; b.j = jl; }
     }
@@ -157,8 +170,16 @@ __device__ __forceinline__ void persist_pair(const EngineParams& P, long long sl
   if (f[0] != fl.x || f[1] != fl.y) __stcg(reinterpret_cast<uchar2*>(P.flags) + slot2, make_uchar2(f[0], f[1]));
 }
 
+// lattice index of the first point of fragment slot q (0 .. QPAIRS-1) of the tile at (tx, ty, tz)
+__device__ __forceinline__ long long persist_pair_index(int q, int tx, int ty, int tz, int nx, int ny) {
+  const int l = q & 31, j = (q >> 5) & 3, i = (q >> 7) & 1, w = q >> 8;
+  const int jy = ty * QT + (w >> 1) * 16 + i * 8 + (l >> 2);
+  const int jx = tx * QT + (w & 1) * 32 + j * 8 + (l & 3) * 2;
+  return (long long)jx + (long long)nx * (jy + (long long)ny * tz);
+}
+
 template <int D>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P, int iters) {
+__global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, int iters) {
   GPIS_DYN_SMEM_F64A(p_smem);
   double* s_kv = p_smem;                                  // [GS1_RMAX] covariance of the winner with the model rows
   double* ring = p_smem + GS1_RMAX;                       // phase B: rows of W; phase D: GEMM stages
@@ -168,13 +189,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
   unsigned long long* gempty = gfull + QPIPE;
   __shared__ double s_red[2][PB][GEMM_CWARPS];
   __shared__ double s_rec[PAY_HDR];
-  __shared__ double s_gram[GEMM_THREADS / 32][2];
+  __shared__ double s_gram[PTHREADS / 32][2];
   __shared__ double s_fin[3];                             // dinv, g_new, ok
   __shared__ BlockBest s_bb[GEMM_CWARPS];
   __shared__ BlockBest s_next;                            // the winner every CTA reduced at the end of the previous step
   __shared__ int s_win, s_flag;
   __shared__ int s_pref[QT_MAX + 1];                      // exclusive prefix of the tiles' chunk counts
   __shared__ int s_wsum[GEMM_CWARPS];
+  __shared__ unsigned short s_rho[QBLK * QKC];            // model rows of the units of the running block
+  __shared__ int s_uoff[QBLK];                            // their tiles' offsets into the axis-table rows: jy0 | jx0 << 16
   __shared__ unsigned long long s_clk[PCLK_N], s_tk[1];   // CTA 0, thread 0 only: lap timer (globaltimer ns)
 
   DevState* st = P.st;
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
   // a function-only selection started by k_begin: rows == points == generation, so ONE counter (r0) carries
   // the loop state and the barrier count (3 per step) is derived from it
   if (*(volatile int*)&st->r != 0 || *(volatile int*)&st->m != 0 || *(volatile int*)&st->iter != 0) return;
-  for (int i = tid; i < GS1_RMAX; i += GEMM_THREADS) s_kv[i] = 0.0;
+  for (int i = tid; i < GS1_RMAX; i += PTHREADS) s_kv[i] = 0.0;
   if (tid == 0) {
     for (int i = 0; i < QPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
     for (int i = 0; i < PRING_SLOTS_MAX; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS); }
@@ -200,8 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
   if (tid < PCLK_N) s_clk[tid] = 0;
   if (tid == 0) s_tk[0] = gtimer_ns();
   int stop = 0;          // 1: nothing unclassified / capacity (done), 2: not positive definite
-  int gstage = 0;        // GEMM ring position, carried across the steps (the barriers' phases run on)
-  unsigned gphase = 0;
+  unsigned gcount = 0;   // units this CTA has put through the GEMM ring so far (the barriers' phases run on across steps)
   int w_nslots = -1;     // W ring: slots of the current geometry and rows streamed through it so far
   unsigned wseq = 0;
   const bool exchange = P.world > 1;
@@ -279,7 +301,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
     double nxp[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) nxp[d] = s_rec[PAY_X + d];
-    if (warp == GEMM_CWARPS) {
+    if (warp > GEMM_CWARPS) {
+      // producer warps 9..11 have nothing to do in this phase
+    } else if (warp == GEMM_CWARPS) {
       // producer warp, lane 0: one bulk copy per row
       if (lane == 0) {
         for (int i = 0; i < my_rows; ++i) {
@@ -318,6 +342,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
           if (0.5 * d2 * P.inv_ell2 <= QCUT) {
             const int n = __ldcg(P.rcnt + t);
             P.rlist[(size_t)t * P.rlist_stride + n] = (unsigned short)r0;
+            // the row's z-axis factor at this tile's slice (what the axis-2 table holds for it)
+            double tzf = 1.0;
+            if (D > 2) {
+              const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - nxp[D > 2 ? 2 : 0];
+              tzf = exp(-0.5 * df * df * P.inv_ell2);
+            }
+            P.rtz[(size_t)t * P.rlist_stride + n] = tzf;
             __stcg(P.rcnt + t, n + 1);
           }
           P.tile_cnt[t] = 0u;
@@ -342,16 +373,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
             double v = exp(-0.5 * diff * diff * P.inv_ell2);
             if (d == 0) v *= P.sf2;
             P.T[d][(long long)r0 * P.ldt[d] + j] = v;
+            P.TT[d][(long long)j * P.ldtt + r0] = v;
           }
         }
       }
     } else {
       // covariance of the winner with the model rows (entries >= m stay zero)
-      for (int i = tid; i < m; i += PCW) {
-        double d2 = 0.0;
+      // k(x_i, x_w) = sf2 exp(-|x_i - x_w|^2 / 2 ell^2) is the product of row i's three axis-table entries at the
+      // winner's lattice index (the very factors the update GEMM multiplies), read from the transposed tables
+      // TT[d][index][row]: three coalesced loads per row instead of an exp(), all of the thread's rows in flight
+      // together.  Entries >= m stay zero.
+      {
+        int wj[3] = {0, 0, 0};
+        {
+          long long rem = __double_as_longlong(s_rec[PAY_LOCAL]);
+          if (win != P.rank) {      // a peer's pick: its lattice index from the coordinates
 #pragma unroll
-        for (int d = 0; d < D; ++d) { const double df = __ldcg(P.AX[d] + i) - nxp[d]; d2 += df * df; }
-        s_kv[i] = P.sf2 * exp(-0.5 * d2 * P.inv_ell2);
+            for (int d = 0; d < D; ++d) wj[d] = (int)llrint((nxp[d] - P.gorg[d]) / P.gh[d]);
+          } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              const long long len = P.glen[d] > 0 ? P.glen[d] : 1;
+              wj[d] = (int)(rem % len) + (d == 2 ? P.gz0 : 0);
+              rem /= len;
+            }
+          }
+        }
+        for (int i0 = 0; i0 < m; i0 += 8 * PCW) {
+          double tv[8][D];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = i0 + tid + PCW * k;
+#pragma unroll
+            for (int d = 0; d < D; ++d) tv[k][d] = i < m ? __ldcg(P.TT[d] + (long long)wj[d] * P.ldtt + i) : 0.0;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int i = i0 + tid + PCW * k;
+            if (i < m) {
+              double kv = tv[k][0];
+#pragma unroll
+              for (int d = 1; d < D; ++d) kv *= tv[k][d];
+              s_kv[i] = kv;
+            }
+          }
+        }
       }
       named_sync(1, PCW);
       PSTAMP(PCLK_WSETUP);
@@ -431,13 +497,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
     {
       const double* X = P.L + (long long)r0 * P.R_cap;
       double p0 = 0.0, p1 = 0.0;
-      for (int s = tid; s < r0; s += GEMM_THREADS) { const double x = __ldcg(X + s); p0 += x * x; p1 += x * __ldcg(P.g + s); }
+      for (int s0 = 0; s0 < r0; s0 += 8 * PTHREADS) {      // 16 loads in flight per thread
+        double xv[8], gv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int si = s0 + tid + PTHREADS * k;
+          xv[k] = si < r0 ? __ldcg(X + si) : 0.0;
+          gv[k] = si < r0 ? __ldcg(P.g + si) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { p0 += xv[k] * xv[k]; p1 += xv[k] * gv[k]; }
+      }
       for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
       if (lane == 0) { s_gram[warp][0] = p0; s_gram[warp][1] = p1; }
       __syncthreads();
       if (tid == 0) {
         double xx = 0.0, xg = 0.0;
-        for (int w = 0; w < GEMM_THREADS / 32; ++w) { xx += s_gram[w][0]; xg += s_gram[w][1]; }
+        for (int w = 0; w < PTHREADS / 32; ++w) { xx += s_gram[w][0]; xg += s_gram[w][1]; }
         double mf = P.mean_c;
 #pragma unroll
         for (int d = 0; d < D; ++d) mf += P.mean_w[d] * s_rec[PAY_X + d];
@@ -458,23 +534,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
       __syncthreads();
       const double dinv = s_fin[0];
       const int nparts = min(G, r0);
-      const int gw = (cta * GEMM_THREADS + tid) >> 5, nw = (G * GEMM_THREADS) >> 5;
+      const int gw = (cta * PTHREADS + tid) >> 5, nw = (G * PTHREADS) >> 5;
       const int sub = lane >> 2, cq = lane & 3;
       for (int c0 = gw * 4; c0 < r0; c0 += nw * 4) {
         const int c = c0 + cq;
         double y = 0.0;
         if (c < r0) {
           const double* yp = P.ypart + c;
-          int part = sub;
-          for (; part + 32 < nparts; part += 40) {
-            const double a0 = __ldcg(yp + (long long)part * GS1_RMAX);
-            const double a1 = __ldcg(yp + (long long)(part + 8) * GS1_RMAX);
-            const double a2 = __ldcg(yp + (long long)(part + 16) * GS1_RMAX);
-            const double a3 = __ldcg(yp + (long long)(part + 24) * GS1_RMAX);
-            const double a4 = __ldcg(yp + (long long)(part + 32) * GS1_RMAX);
-            y += a0; y += a1; y += a2; y += a3; y += a4;
+          // the CTAs' partials in a fixed order (bit-identical on every rank), 24 loads in flight
+          double a[24];
+#pragma unroll
+          for (int q = 0; q < 24; ++q) {
+            const int part = sub + 8 * q;
+            a[q] = part < nparts ? __ldcg(yp + (long long)part * GS1_RMAX) : 0.0;
           }
-          for (; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
+#pragma unroll
+          for (int q = 0; q < 24; ++q) y += a[q];
+          for (int part = sub + 8 * 24; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
         }
         y += __shfl_xor_sync(0xffffffffu, y, 4);
         y += __shfl_xor_sync(0xffffffffu, y, 8);
@@ -535,73 +611,114 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
     PSTAMP(PCLK_PREFIX);
     PBest best;
     best.s = NEG_INF; best.id = 0x7fffffffffffffffLL; best.j = -1;
-    if (warp == GEMM_CWARPS) {
-      // ------------------------------- producer -------------------------------
-      const double* wrow = P.W + (long long)r0 * P.ldW;
-      int t = tile0, c = c0;
-      int cnt = 0, Ct = 1, tz = 0, ty = 0, tx = 0;
-      const unsigned short* rl = P.rlist;
-      bool fresh = true;
-      for (int ul = 0; ul < n_units; ++ul) {
-        if (fresh) {
-          cnt = __ldcg(P.rcnt + t);
-          Ct = s_pref[t + 1] - s_pref[t];
-          tz = t / txy; ty = (t / tiles_x) % tiles_y; tx = t % tiles_x;
-          rl = P.rlist + (size_t)t * P.rlist_stride;
-          fresh = false;
+    // The units of this CTA go through the ring in blocks of QBLK: before a block starts, every thread
+    // takes one unit and leaves its 16 row indices and coefficients W[r,rho] Tz[rho][jz] in shared memory
+    // (two dependent rounds of L2 loads, all of a block's in flight together), so that neither the producer
+    // nor the MMA warps ever wait on global memory for them.
+    double* s_cs = s_kv;                                  // [QBLK][QKC], aliases the winner's covariance vector (phase B only)
+    const double sb = [&]() {
+      double beta = P.beta;
+      if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
+      else if (P.beta_mode == 2) { const double k1 = (double)(gen + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
+      return sqrt(beta);
+    }();
+    const double gn1 = s_fin[1];
+    const int wm = warp >> 1, wn = warp & 1;
+    // walking state of the consumers: tile, chunk inside it, its chunk count
+    int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0];
+    int seg_c0 = c0;                                      // first chunk of the running segment
+    int def_t[2], ndef = 0;
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int b0 = 0; b0 < n_units; b0 += QBLK) {
+      const int bn = min(QBLK, n_units - b0);
+      __syncthreads();                                    // the previous block's coefficients are no longer read
+      unsigned long long tk0 = 0;
+      if (cta == 0 && tid == 0) tk0 = gtimer_ns();
+      {
+        const double* wrow = P.W + (long long)r0 * P.ldW;
+        for (int ul = tid; ul < bn; ul += PTHREADS) {
+          const long long u = u0 + b0 + ul;
+          int lo = tile0, hi = T - 1;
+          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_pref[mid] <= u) lo = mid; else hi = mid - 1; }
+          const int t = lo, c = (int)(u - s_pref[t]);
+          const int cnt = __ldcg(P.rcnt + t);
+          const uint4* rl4 = reinterpret_cast<const uint4*>(P.rlist + (size_t)t * P.rlist_stride + c * QKC);
+          const uint4 ra = __ldcg(rl4), rb = __ldcg(rl4 + 1);
+          const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+          int rho[QKC];
+          double wv[QKC], tv[QKC];
+          const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
+#pragma unroll
+          for (int k = 0; k < QKC; k += 2) { const double2 z2 = __ldcg(tz2 + (k >> 1)); tv[k] = z2.x; tv[k + 1] = z2.y; }
+#pragma unroll
+          for (int k = 0; k < QKC; ++k) {
+            const int rr = (int)((rw[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+            rho[k] = (c * QKC + k < cnt) ? rr : 0;
+          }
+          // row r0 of W is new this step: no line of it can be stale in L1, so these loads may be cached there
+#pragma unroll
+          for (int k = 0; k < QKC; ++k) wv[k] = wrow[rho[k]];
+#pragma unroll
+          for (int k = 0; k < QKC; ++k) {
+            s_cs[ul * QKC + k] = (c * QKC + k < cnt) ? wv[k] * tv[k] : 0.0;
+            s_rho[ul * QKC + k] = (unsigned short)rho[k];
+          }
+          s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
         }
-        mbar_wait(&gempty[gstage], gphase ^ 1u);
-        double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
-        double* Bs = As + QKC * QLD;
-        double* cs = Bs + QKC * QLD;
-        const int k = c * QKC + (lane & (QKC - 1));
-        const int rho = k < cnt ? (int)__ldcg(rl + k) : 0;
-        if (lane < QKC) {
-          double cv = 0.0;
-          if (k < cnt) cv = __ldcg(wrow + rho) * __ldcg(P.T[2] + (long long)rho * P.ldt[2] + P.gz0 + tz);
-          cs[lane] = cv;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&gfull[gstage], 2 * QKC * QT * (unsigned)sizeof(double));
-        __syncwarp();
-        if (lane < QKC)
-          bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + ty * QT, QT * sizeof(double), &gfull[gstage]);
-        else
-          bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + tx * QT, QT * sizeof(double), &gfull[gstage]);
-        if (++c == Ct) { c = 0; ++t; fresh = true; }
-        if (++gstage == QPIPE) { gstage = 0; gphase ^= 1u; }
       }
-    } else {
-      // --------------------------------- consumers ---------------------------------
-      const double sb = [&]() {
-        double beta = P.beta;
-        if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
-        else if (P.beta_mode == 2) { const double k1 = (double)(gen + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
-        return sqrt(beta);
-      }();
-      const double gn1 = s_fin[1];
-      const int wm = warp >> 1, wn = warp & 1;
-      int ul = 0, t = tile0, c = c0;
-      int def_t[2], ndef = 0;
-      while (ul < n_units) {
-        const int Ct = s_pref[t + 1] - s_pref[t];
-        const int seg_units = min(n_units - ul, Ct - c);
-        const bool whole = (c == 0) && (seg_units == Ct);
-        const long long tbase = (long long)t * QPAIRS;
-        double acc[2][4][2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int q = 0; q < seg_units; ++q) {
-          mbar_wait(&gfull[gstage], gphase);
+      __syncthreads();
+      if (cta == 0 && tid == 0) { s_clk[PCLK_PRECOMP] += gtimer_ns() - tk0; if (b0 == 0) s_clk[PCLK_UNITS] += (unsigned long long)U; }
+      if (warp >= GEMM_CWARPS) {
+        // ------------------------------- producers: every QPROD-th unit each -------------------------------
+        for (int ul = warp - GEMM_CWARPS; ul < bn; ul += QPROD) {
+          const unsigned q = gcount + (unsigned)(b0 + ul);
+          const int stage = (int)(q % QPIPE);
+          mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
+          double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
+          double* Bs = As + QKC * QLD;
+          const int rho = (int)s_rho[ul * QKC + (lane & (QKC - 1))];
+          const int uo = s_uoff[ul];
+          if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
+          __syncwarp();
+#if GPIS_EXP == 2      // experiment: every copy issued twice (same destination): the rise in time is the copies' cost
+          if (lane == 0) asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&gfull[stage])), "r"(2 * QKC * QT * 8) : "memory");
+          __syncwarp();
+          if (lane < QKC)
+            bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
+          else
+            bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+#endif
+          if (lane < QKC)
+            bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
+          else
+            bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+        }
+      } else {
+        // --------------------------------- consumers ---------------------------------
+        for (int ul = 0; ul < bn; ++ul) {
+          const unsigned q = gcount + (unsigned)(b0 + ul);
+          const int gstage = (int)(q % QPIPE);
+          if (cta == 0 && tid == 0) tk0 = gtimer_ns();
+          mbar_wait(&gfull[gstage], (q / QPIPE) & 1u);
+          if (cta == 0 && tid == 0) s_clk[PCLK_WAITFULL] += gtimer_ns() - tk0;
           const double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
           const double* Bs = As + QKC * QLD;
-          const double* cs = Bs + QKC * QLD;
+          const double* cs = s_cs + ul * QKC;
+#if GPIS_EXP == 1      // experiment: the MMA loop runs twice (second time with zero coefficients): the rise is its cost
+          for (int rep = 0; rep < 2; ++rep)
+#endif
 #pragma unroll
           for (int k4 = 0; k4 < QKC / 4; ++k4) {
             const int kb = k4 * 4 + (lane & 3);
+#if GPIS_EXP == 1
+            const double cv = rep ? 0.0 : cs[kb];
+#else
             const double cv = cs[kb];
+#endif
             double af[2], bf[4];
 #pragma unroll
             for (int i = 0; i < 2; ++i) af[i] = As[kb * QLD + wm * 16 + i * 8 + (lane >> 2)] * cv;
@@ -614,44 +731,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&gempty[gstage]);
-          if (++gstage == QPIPE) { gstage = 0; gphase ^= 1u; }
+          ++wc;
+          if (wc < wCt && b0 + ul + 1 < n_units) continue;
+          // ---- the running segment of tile wt ends here
+          const bool whole = (seg_c0 == 0) && (wc == wCt);
+          const long long tbase = (long long)wt * QPAIRS;
+          if (cta == 0 && tid == 0) tk0 = gtimer_ns();
+          if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
+            double2 pmu[2][4], pvar[2][4];
+            uchar2 pfl[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const long long s2 = tbase + ((warp * 2 + i) * 4 + j) * 32 + lane;
+                pmu[i][j] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+                pvar[i][j] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+                pfl[i][j] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
+              }
+            const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int q = ((warp * 2 + i) * 4 + j) * 32 + lane;
+                persist_pair(P, tbase + q, persist_pair_index(q, etx, ety, etz, nx, ny), make_double2(acc[i][j][0], acc[i][j][1]),
+                             pmu[i][j], pvar[i][j], pfl[i][j], sb, gn1, best);
+              }
+          } else {
+            // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
+            // first tile, 1: its last), then arrive on the tile
+            double2* ws = reinterpret_cast<double2*>(P.gws) + ((size_t)cta * 2 + (wt == tile0 ? 0 : 1)) * QPAIRS;
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                __stcg(&ws[((warp * 2 + i) * 4 + j) * 32 + lane], make_double2(acc[i][j][0], acc[i][j][1]));
+            __threadfence();
+            named_sync(1, PCW);
+            if (tid == 0) atomicAdd(&P.tile_cnt[wt], 1u);
+            def_t[ndef++] = wt;
+          }
+          if (cta == 0 && tid == 0) s_clk[PCLK_EPIREG] += gtimer_ns() - tk0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+          ++wt;
+          wc = 0;
+          seg_c0 = 0;
+          if (wt < T) wCt = s_pref[wt + 1] - s_pref[wt];
         }
-        ul += seg_units;
-        if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
-          double2 pmu[2][4], pvar[2][4];
-          uchar2 pfl[2][4];
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const long long s2 = tbase + ((warp * 2 + i) * 4 + j) * 32 + lane;
-              pmu[i][j] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
-              pvar[i][j] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
-              pfl[i][j] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
-            }
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              persist_pair(P, tbase + ((warp * 2 + i) * 4 + j) * 32 + lane, make_double2(acc[i][j][0], acc[i][j][1]),
-                           pmu[i][j], pvar[i][j], pfl[i][j], sb, gn1, nx, ny, best);
-        } else {
-          // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
-          // first tile, 1: its last), then arrive on the tile
-          double2* ws = reinterpret_cast<double2*>(P.gws) + ((size_t)cta * 2 + (t == tile0 ? 0 : 1)) * QPAIRS;
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              __stcg(&ws[((warp * 2 + i) * 4 + j) * 32 + lane], make_double2(acc[i][j][0], acc[i][j][1]));
-          __threadfence();
-          named_sync(1, PCW);
-          if (tid == 0) atomicAdd(&P.tile_cnt[t], 1u);
-          def_t[ndef++] = t;
-        }
-        ++t;
-        c = 0;
       }
+    }
+    gcount += (unsigned)n_units;
+    if (warp < GEMM_CWARPS) {
       PSTAMP(PCLK_GEMM);
 
       // ---- tiles shared with neighbouring CTAs: wait for all segments, split the epilogue by segment index
@@ -699,7 +833,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_persist(EngineParams P
 #pragma unroll
           for (int k = 0; k < GEPI_SPT; ++k) {
             if (ub + k >= un1) continue;
-            persist_pair(P, tbase + (ub + k) * PCW + tid, v[k], mu[k], var[k], fl[k], sb, gn1, nx, ny, best);
+            const int q = (ub + k) * PCW + tid;
+            persist_pair(P, tbase + q, persist_pair_index(q, t2 % tiles_x, (t2 / tiles_x) % tiles_y, t2 / txy, nx, ny), v[k], mu[k],
+                         var[k], fl[k], sb, gn1, best);
           }
         }
       }

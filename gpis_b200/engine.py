@@ -286,11 +286,11 @@ class GpisEngine:
                 "append_ms": p.value, "main_ms": q.value, "epilogue_ms": r.value}
 
     PERSIST_SLOTS = ("record_wait", "w_setup", "w_pass", "barrier1", "new_row", "barrier2", "prefix", "gemm", "epilogue",
-                     "barrier3", "winner", "steps")
+                     "barrier3", "winner", "steps", "gemm_precompute", "gemm_wait_full", "gemm_epilogue_regs", "units")
 
     def persist_timing(self):
         """Lap times (ms, block 0's clock) of the persistent selection kernel in the last select()."""
-        a = np.zeros(12)
+        a = np.zeros(16)
         self._ck(self.lib.gpis_get_persist_timing(self.h, _ptr(a)))
         return dict(zip(self.PERSIST_SLOTS, a.tolist()))
 

@@ -232,6 +232,51 @@ gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const
                               int32_t* n_in_model, double* mean, double* var, uint8_t* flags,
                               double* device_ms, void* stream);
 
+/* float entry points.  The reference's ABI is fp32 throughout (SelectChol(maxSize, float* inputPoints, float* targetPoints,
+ * .., float* activeInputs, float* activeTargets), include/gpu_active_set_selector.hpp:41-46; the float* members of
+ * ActiveSetBuffers / MaxSubsetBuffers, include/active_set_selection_types.h:16-41).  These take and return float arrays
+ * with the same layouts as their double counterparts above (host or device pointers); the engine converts on the device
+ * and computes in fp64.
+ *   gpis_get_active_f32 fills what SelectChol's activeInputs / activeTargets were meant to receive
+ *   (gpu_active_set_selector.cpp:584-586 never writes them): active_inputs[a + d*max_size], active_targets[a] for the
+ *   n_in_model model points in selection order (max_size >= n_in_model; the rest is zeroed); the targets are read back
+ *   from the replicated factor (y = m + L g), so every rank of a sharded run returns all of them. */
+gpis_status gpis_set_candidates_f32(gpis_handle h, const float* pts, const float* tsdf, const float* normals,
+                                    const float* noise, const int64_t* ids, void* stream);
+gpis_status gpis_set_grid_candidates_f32(gpis_handle h, const int32_t* dims, const double* origin, const double* spacing,
+                                         int32_t z0, int32_t nz_total, const float* tsdf, const float* normals,
+                                         const float* noise, void* stream);
+gpis_status gpis_get_active_f32(gpis_handle h, int32_t max_size, float* active_inputs, float* active_targets,
+                                int32_t* n_selected, int32_t* n_in_model, void* stream);
+gpis_status gpis_predict_f32(gpis_handle h, const float* query, int64_t nq, float* mean, float* var, float* normals,
+                             void* stream);
+gpis_status gpis_get_candidate_posterior_f32(gpis_handle h, float* mean, float* var, void* stream);
+
+/* matlab/core/auto_tsdf.m:133-262, the step BEFORE the selection path: from the rasterised shape to shapeParams.
+ *   inside[i + j*rows] != 0: pixel (row i, column j) is inside the shape (the reference's image value 102; 255 outside).
+ *   :133-157  3x3 imdilate / imerode masks (the 5x5 window for the double dilation) -> TSDF in {-1, -0.5, 0, 0.5, 1};
+ *   :159-218  measurement noise per pixel: occlusionScale inside the three occlusion rectangles (1-based, low < i <= high)
+ *             where tsdf < 0.6; interior points (tsdf < -0.5) measured with probability interiorRate; elsewhere noiseScale,
+ *             scaled by a specular factor near the surface (edgeWin window) and by the image position (noiseGradMode);
+ *   :221      imgradientxy 'CentralDifference' normals;   :229-236  validIndices = find(noise < occlusionScale).
+ * The reference draws rand() in a data-dependent order that cannot be reproduced: the uniform draws are the input
+ * u[3][rows*cols] (interior, specular scale, sparsity; NULL = 0.5 everywhere).  The first stage of auto_tsdf.m
+ * (vision.ShapeInserter, :129-131) needs MATLAB's Computer Vision toolbox and is not part of this call.
+ * Outputs (host or device pointers, any may be NULL), all column-major like the reference's tsdf(:):
+ *   tsdf[n], normals[2][n] (Gx then Gy), noise[n], valid_idx[n] (first *n_valid entries: 0-based linear indices of the
+ *   measured pixels, ascending).  device: CUDA ordinal or -1 = current.  Synchronises `stream` before returning. */
+typedef struct gpis_tsdf_params {
+  int32_t struct_size;          /* = sizeof(gpis_tsdf_params) */
+  int32_t edge_win;             /* varParams.edgeWin */
+  int32_t specular_noise;       /* varParams.specularNoise */
+  int32_t noise_grad_mode;      /* varParams.noiseGradMode: 0 none, 1 TLBR, 2 TRBL, 3 BLTR, 4 BRTL */
+  double noise_scale, occlusion_scale, interior_rate, sparsity_rate, horiz_scale, vert_scale;
+  double occ_y_low[3], occ_y_high[3], occ_x_low[3], occ_x_high[3];   /* varParams.{y,x}_thresh{1,2,3}_{low,high} */
+} gpis_tsdf_params;
+gpis_status gpis_build_tsdf(const uint8_t* inside, int32_t rows, int32_t cols, const gpis_tsdf_params* prm, const double* u,
+                            double* tsdf, double* normals, double* noise, int32_t* valid_idx, int32_t* n_valid,
+                            int32_t device, void* stream);
+
 /* Level-set state of the candidates after selection: last ambiguity each candidate was
  * scored with, and the high / low masks (straddle.m:121-125; ClassificationBuffers). */
 gpis_status gpis_get_levelset(gpis_handle h, double* ambiguity, uint8_t* high, uint8_t* low,
@@ -255,8 +300,11 @@ gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main
  * last gpis_select, ms: [0] winner / wait for the exchange records, [1] covariance of the winner with the model
  * rows, [2] W pass of the factor append, [3] grid barrier, [4] new row of W, [5] grid barrier, [6] unit prefix,
  * [7] update GEMM with the in-register epilogues of whole tiles, [8] epilogues of tiles shared between blocks,
- * [9] grid barrier, [10] winner reduction (+ record publication when sharded), [11] = number of steps (a count). */
-gpis_status gpis_get_persist_timing(gpis_handle h, double* ms12);
+ * [9] grid barrier, [10] winner reduction (+ record publication when sharded), [11] = number of steps (a count);
+ * inside [7]: [12] coefficient precompute, [13] waits for a filled pipeline stage, [14] in-register epilogues,
+ * [15] = number of (tile, 16-row chunk) units all blocks processed (a count; x 2*64*64*16 = executed MMA flops).
+ * 16 doubles. */
+gpis_status gpis_get_persist_timing(gpis_handle h, double* ms16);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
  * stream (plain launches instead of the captured graph). */
 gpis_status gpis_set_profiling(gpis_handle h, int32_t on);

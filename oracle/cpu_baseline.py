@@ -119,3 +119,77 @@ def dense_model(X, y, hyp):
     L = np.linalg.cholesky(Q)
     alpha = sla.cho_solve((L, True), y - (X @ hm[:D] + hm[D]))
     return L, alpha
+
+
+def select_separable(dims, tsdf, hyp, train, first_index, max_steps=None, checkpoint=None, time_budget_s=None):
+    """The same greedy selection for candidates on the integer lattice 0..dims-1 (x fastest), restated so that
+    the CPU can hold BASELINE config 3 in memory: V = L^-1 K(active, candidates) is never stored (at 128^3 /
+    4000 rows it is 60+ GB and select_compact above runs out of memory near step 3900).  The new row of V is
+    formed from W = L^-1 directly,
+        v_new[z, y, x] = sum_rho W[r, rho] Tz[rho, z] Ty[rho, y] Tx[rho, x],
+    with the separable SE factors T_d[rho, j] = exp(-(j - p_rho,d)^2 / (2 ell^2)) -- one dense matrix product per
+    step.  Same rule (select_active_set_straddle.m:62-126: variance-scaled bounds, lowest index on ties, flags
+    only ever set), same order of the model rows.  tests/golden/make_sequence_fixtures.py checks its picks against
+    select_compact's on the steps the latter completes."""
+    nx, ny, nz = (int(d) for d in dims)
+    N = nx * ny * nz
+    y = np.asarray(tsdf, np.float64).reshape(-1)
+    ell2 = float(np.exp(np.float64(hyp["cov"][0])) ** 2)
+    sf2 = float(np.exp(2.0 * np.float64(hyp["cov"][1])))
+    noise = float(np.exp(2.0 * hyp["lik"]))
+    hm = np.asarray(hyp["mean"], np.float64).reshape(-1)
+    h, s, eps, K = float(train["levelSet"]), np.sqrt(float(train["beta"])), float(train["eps"]), int(train["activeSetSize"])
+    steps = K - 1 if max_steps is None else min(K - 1, int(max_steps))
+    ax = [np.arange(n, dtype=np.float64) for n in (nx, ny, nz)]
+    idx = np.arange(N)
+    coords = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)], axis=1).astype(np.float64)
+    mu = coords @ hm[:3] + hm[3]
+    var = np.full(N, sf2)
+    live = np.ones(N, bool)
+    T = [np.zeros((steps + 1, n)) for n in (nx, ny, nz)]
+    W = np.zeros((steps + 1, steps + 1))
+    X = np.zeros((steps + 1, 3))
+    g = np.zeros(steps + 1)
+    order = [int(first_index)]
+    pending = int(first_index)
+    live[pending] = False
+    scored, step_times = [], []
+    t0 = time.perf_counter()
+    r = 0
+    for it in range(steps):
+        ts = time.perf_counter()
+        p = coords[pending]
+        diff = X[:r] - p[None, :]
+        kvec = sf2 * np.exp(-np.einsum("ij,ij->i", diff, diff) / (2.0 * ell2))
+        ell = W[:r, :r] @ kvec
+        d = np.sqrt(sf2 + noise - ell @ ell)
+        W[r, :r] = -(ell @ W[:r, :r]) / d
+        W[r, r] = 1.0 / d
+        g[r] = (y[pending] - (p @ hm[:3] + hm[3]) - ell @ g[:r]) / d
+        X[r] = p
+        for a in range(3):
+            T[a][r] = np.exp(-(ax[a] - p[a]) ** 2 / (2.0 * ell2))
+        w = W[r, :r + 1] * sf2
+        B = ((w[:, None] * T[2][:r + 1])[:, :, None] * T[1][:r + 1][:, None, :]).reshape(r + 1, nz * ny)
+        vnew = (B.T @ T[0][:r + 1]).reshape(-1)                      # [(z, y), x] = lattice order, x fastest
+        var -= vnew * vnew
+        mu += vnew * g[r]
+        r += 1
+        if not live.any():
+            break
+        hi = mu + s * var
+        lo = mu - s * var
+        amb = np.where(live, np.minimum(hi - h, h - lo), -np.inf)
+        scored.append(int(live.sum()))
+        b = int(np.flatnonzero(amb == amb.max())[0])                  # lowest index among exact ties
+        pending = b
+        order.append(b)
+        live[live & ((lo + eps > h) | (hi - eps < h))] = False
+        live[b] = False
+        step_times.append(time.perf_counter() - ts)
+        if checkpoint is not None and (it + 1) % 100 == 0:
+            checkpoint(order, it + 1)
+        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
+            break
+    return {"order": np.asarray(order), "n_in_model": r, "seconds": time.perf_counter() - t0,
+            "step_seconds": np.asarray(step_times), "scored": np.asarray(scored), "X": X[:r], "mu": mu, "var": var}

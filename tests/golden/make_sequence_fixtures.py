@@ -3,14 +3,15 @@ incremental form of select_active_set_straddle.m:62-126 that tests/test_oracle_s
 literal loop) at BASELINE.json's full sizes, plus -- from a dense refit (create_gpis.m / gp_mean.m /
 gp_cov.m restated in oracle/cpu_baseline.py::dense_model, predict_dense) on the model points -- the posterior
 at a seeded sample of lattice points.  Test infrastructure: the -m gpu tests compare the engine's picks and
-its posterior grid with these files.  CPU only; config 3 takes ~1 h on 8 cores and ~35 GB.
+its posterior grid with these files.  CPU only.  Config 3: oracle/cpu_baseline.py::select_separable (V never stored; minutes on 8 cores), checked against
+the picks select_compact reaches before it runs out of memory (3801 of 4000 on the 62 GB box, 45 minutes).
 
   python tests/golden/make_sequence_fixtures.py c2|c3|c4s [--steps K]
 
 c4s is BASELINE config 4's CODE PATH at a size the CPU finishes (config 4 itself, 256^3 with 32 000 model rows, is
-beyond it): 48^3 sphere WITH gradient observations, 1100 points = 4396 model rows -- above the 4096 rows up to
-which function-only models use the one-pass append, so the engine runs the two-pass gradient append
-(k_grid_point / k_grid_solve<4,3> / k_grid_wrow<4>) exactly as at 256^3.  Oracle:
+beyond it): 48^3 sphere WITH gradient observations, K = 1100 -- the selection stops by itself after 719 points
+(2876 model rows) because nothing is left unclassified.  Gradient models always take the two-pass append
+(k_grid_point / k_grid_solve<4,3> / k_grid_wrow<4>) and the NB = 4 update GEMM, exactly as at 256^3.  Oracle:
 oracle/gpis_oracle.py::select_straddle_incremental (se_cov_derivative.m:41-92 blocks, noise leak included).
 """
 import argparse
@@ -33,6 +34,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("case", choices=sorted(CASES) + ["c4s"])
 ap.add_argument("--steps", type=int, default=None)
 ap.add_argument("--sample", type=int, default=20000)
+ap.add_argument("--compact", action="store_true", help="c3: run select_compact (as far as memory allows) instead of select_separable")
 a = ap.parse_args()
 if a.case == "c4s":
     from oracle import gpis_oracle as O
@@ -67,7 +69,25 @@ def checkpoint(order, step):
 
 
 t0 = time.perf_counter()
-res = B.select_compact(pts, tsdf, HYP, train, first_index(N), max_steps=a.steps, checkpoint=checkpoint)
+prefix_checked = 0
+if a.case == "c3":
+    # select_compact keeps V = L^-1 K for the unclassified candidates: at 128^3 it runs out of memory near step 3900
+    # of 3999 on this 62 GB box (its picks up to there are kept in build/seq_c3_checkpoint.npy by an earlier run of this
+    # script with --compact).  The whole sequence comes from select_separable (same rule, V never stored) and is
+    # checked against that prefix.
+    if a.compact:
+        res = B.select_compact(pts, tsdf, HYP, train, first_index(N), max_steps=a.steps, checkpoint=checkpoint)
+    else:
+        res = B.select_separable((g, g, g), tsdf, HYP, train, first_index(N), max_steps=a.steps,
+                                 checkpoint=lambda o, s: print(f"step {s}: {time.perf_counter() - t0:.0f} s", flush=True))
+        if os.path.exists(ck_path):
+            ck = np.load(ck_path)
+            n = min(len(ck), len(res["order"]))
+            assert np.array_equal(ck[:n], res["order"][:n]), "select_separable and select_compact disagree"
+            prefix_checked = int(n)
+            print("picks equal to select_compact's on its first", n, flush=True)
+else:
+    res = B.select_compact(pts, tsdf, HYP, train, first_index(N), max_steps=a.steps, checkpoint=checkpoint)
 order = res["order"]
 n_model = int(res["n_in_model"])
 print("picks", len(order), "in model", n_model, "seconds", round(res["seconds"], 1), flush=True)
@@ -85,5 +105,5 @@ out = os.path.join(HERE, f"seq_{a.case}.npz")
 np.savez_compressed(out, order=order.astype(np.int32), n_in_model=n_model, scored=res["scored"].astype(np.int32),
                     sample=sample.astype(np.int32), mean=mu, var=var, alpha_head=alpha[:64],
                     cpu_seconds=res["seconds"], cpu_cores=os.cpu_count(), grid=g, K=K,
-                    step_seconds=res["step_seconds"].astype(np.float32))
+                    step_seconds=res["step_seconds"].astype(np.float32), prefix_checked_against_select_compact=prefix_checked)
 print("wrote", out, os.path.getsize(out), "bytes")

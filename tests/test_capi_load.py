@@ -19,7 +19,7 @@ def lib():
 def header_symbols():
     src = open(os.path.join(ROOT, "include", "gpis_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(gpis_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(gpis_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported(lib):

@@ -271,3 +271,51 @@ def test_engine_reuse_across_backends_and_calls(G):
     with pytest.raises(G._lib.GpisError):
         eng.select(g ** 3 + 7, K)
     eng.close()
+
+
+def test_float_entry_points_match_the_double_ones(G):
+    """The fp32 ABI of the reference (gpu_active_set_selector.hpp:41-46): float candidates in, float active set and
+    posterior out -- the same selection as the double entry points on the float-rounded inputs."""
+    import ctypes as C
+    from gpis_b200 import _lib
+    lib = _lib.load()
+    g, K = 14, 40
+    shape, hyp = sphere(g, ell=2.5)
+    pts32 = np.ascontiguousarray(shape["points"].T.astype(np.float32))          # SoA like the reference
+    t32 = shape["tsdf"].astype(np.float32)
+    N = g ** 3
+    ref = G.GpisEngine(3, N, K, ell=2.5, noise=0.05, eps=1e-2, beta=10.0)
+    ref.set_candidates(pts32.astype(np.float64), t32.astype(np.float64), soa=True)
+    ref.select(100, K)
+    ids_ref, nm_ref = ref.active()
+    mu_ref, var_ref, _ = ref.predict(shape["points"][:500])
+    for lattice in (False, True):
+        eng = G.GpisEngine(3, N, K, ell=2.5, noise=0.05, eps=1e-2, beta=10.0)
+        if lattice:
+            dims = np.array([g, g, g], np.int32)
+            org, sp = np.zeros(3), np.ones(3)
+            eng._ck(lib.gpis_set_grid_candidates_f32(eng.h, dims.ctypes.data, org.ctypes.data, sp.ctypes.data, 0, g,
+                                                     t32.ctypes.data, None, None, None))
+        else:
+            eng._ck(lib.gpis_set_candidates_f32(eng.h, pts32.ctypes.data, t32.ctypes.data, None, None, None, None))
+        eng.select(100, K)
+        ids, nm = eng.active()
+        assert np.array_equal(ids, ids_ref) and nm == nm_ref
+        ain = np.full(3 * K, -1, np.float32)
+        atg = np.full(K, -1, np.float32)
+        ns, nmm = C.c_int32(), C.c_int32()
+        eng._ck(lib.gpis_get_active_f32(eng.h, K, ain.ctypes.data, atg.ctypes.data, C.byref(ns), C.byref(nmm), None))
+        assert ns.value == len(ids) and nmm.value == nm
+        assert np.array_equal(ain.reshape(3, K)[:, :nm], pts32[:, ids[:nm]])           # active_inputs[a + d*maxSize]
+        assert np.array_equal(atg[:nm], t32[ids[:nm]]) and np.all(atg[nm:] == 0)
+        q32 = np.ascontiguousarray(shape["points"][:500].T.astype(np.float32))
+        m32, v32 = np.empty(500, np.float32), np.empty(500, np.float32)
+        eng._ck(lib.gpis_predict_f32(eng.h, q32.ctypes.data, 500, m32.ctypes.data, v32.ctypes.data, None, None))
+        assert np.array_equal(m32, np.asarray(mu_ref).astype(np.float32)) or np.max(np.abs(m32 - mu_ref)) < 1e-6
+        assert np.max(np.abs(v32 - var_ref)) < 1e-6
+        if lattice:
+            pm, pv = np.empty(N, np.float32), np.empty(N, np.float32)
+            eng._ck(lib.gpis_get_candidate_posterior_f32(eng.h, pm.ctypes.data, pv.ctypes.data, None))
+            mu, var = eng.candidate_posterior()
+            assert np.array_equal(pm, mu.astype(np.float32)) and np.array_equal(pv, var.astype(np.float32))
+        eng.close()
