@@ -558,12 +558,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * dinv;
       }
     }
-    if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
-    PSTAMP(PCLK_FINISH);
-    if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
-    PSTAMP(PCLK_BAR2);
-
-    // ------------------------------------------------------------------ D: update GEMM + epilogue
+    // (the row lists are final since the first barrier: the unit prefix of phase D is formed here, off its critical path)
     // exclusive prefix of the tiles' chunk counts (every tile has at least one chunk: its candidates are
     // scored every step even when no model row reaches it)
     {
@@ -596,6 +591,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       }
       __syncthreads();
     }
+    if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
+    PSTAMP(PCLK_FINISH);
+    if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
+    PSTAMP(PCLK_BAR2);
+
+    // ------------------------------------------------------------------ D: update GEMM + epilogue
     const long long U = s_pref[T];
     const int Gw = (int)min((long long)G, U);
     const bool working = cta < Gw;
