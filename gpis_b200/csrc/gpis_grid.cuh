@@ -37,8 +37,9 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 // warp tile (TE/4) x (TE/2) in 8 x 8 DMMA blocks -- so that the epilogue streams it with fully coalesced
 // 16-byte accesses.
 __host__ __device__ inline int grid_tile_edge(const EngineParams& P) { return P.tile_e > 0 ? P.tile_e : GT; }
-__host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, int jy, int tz) {
-  const int TE = grid_tile_edge(P), WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
+template <int TE>
+__host__ __device__ inline long long grid_slot_te(const EngineParams& P, int jx, int jy, int tz) {
+  constexpr int WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
   const int tiles_x = (P.glen[0] + TE - 1) / TE, tiles_y = (P.glen[1] + TE - 1) / TE;
   const long long tile = ((long long)tz * tiles_y + jy / TE) * tiles_x + jx / TE;
   const int my = jy % TE, mx = jx % TE;
@@ -46,13 +47,17 @@ __host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, in
   const int frag = ((gwarp * NI + (my % WY) / 8) * NJ + (mx % WX) / 8) * 32 + (my % 8) * 4 + (mx % 8) / 2;
   return tile * (TE * TE) + frag * 2 + (mx & 1);
 }
+__host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, int jy, int tz) {
+  return grid_tile_edge(P) == 64 ? grid_slot_te<64>(P, jx, jy, tz) : grid_slot_te<GT>(P, jx, jy, tz);
+}
 __host__ __device__ inline long long grid_slot_of_local(const EngineParams& P, long long jl) {
   const int nx = P.glen[0], ny = P.glen[1];
   return grid_slot(P, (int)(jl % nx), (int)((jl / nx) % ny), (int)(jl / ((long long)nx * ny)));
 }
 // inverse: slot -> (jx, jy, tz); returns false for padding slots
-__host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
-  const int TE = grid_tile_edge(P), WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
+template <int TE>
+__host__ __device__ inline bool grid_unslot_te(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
+  constexpr int WY = TE / 4, WX = TE / 2, NI = WY / 8, NJ = WX / 8;
   const int tiles_x = (P.glen[0] + TE - 1) / TE, tiles_y = (P.glen[1] + TE - 1) / TE;
   const long long tile = slot / (TE * TE);
   const int w = (int)(slot % (TE * TE));
@@ -65,6 +70,9 @@ __host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slo
   jy = (int)((tile / tiles_x) % tiles_y) * TE + my;
   jx = (int)(tile % tiles_x) * TE + mx;
   return jx < P.glen[0] && jy < P.glen[1];
+}
+__host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
+  return grid_tile_edge(P) == 64 ? grid_unslot_te<64>(P, slot, jx, jy, tz) : grid_unslot_te<GT>(P, slot, jx, jy, tz);
 }
 // slots of the whole (tile-padded) lattice in the layout of this selection
 __host__ __device__ inline long long grid_slot_count(const EngineParams& P) {
@@ -1085,7 +1093,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
     if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) continue;
     const double mus[2] = {mu[k].x, mu[k].y}, vars[2] = {var[k].x, var[k].y};
     int jx, jy, tz;
-    grid_unslot(P, slot2 * 2, jx, jy, tz);
+    grid_unslot_te<GT>(P, slot2 * 2, jx, jy, tz);       // the per-step kernels work on 128 x 128 tiles
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
