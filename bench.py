@@ -311,7 +311,7 @@ def run_ours(args):
         ms_inst, acc = timed(False, args.steps)
     else:
         _, acc = timed(False, 1)
-        acc = {k: v * args.steps for k, v in acc.items()}
+        acc = {k: (v * args.steps if isinstance(v, (int, float)) else v) for k, v in acc.items()}
     clocks = sampler.stop() if rank == 0 else None
     ids, n_model = eng.active()
     # (4) optional: the same job in TF32 mode (update GEMM on tcgen05, 3xTF32), reported beside the

@@ -25,7 +25,7 @@ constexpr size_t TF32_SMEM = 0;
 template <int NB>
 void k_grid_gemm_tf32(EngineParams) {}
 constexpr size_t PERSIST_SMEM = 0;      // in-kernel grid barriers are not emulated either: the per-step path runs
-constexpr int PTHREADS = 32;
+constexpr int PTHREADS = 32, PLL_WORLD_MAX = 16;
 template <int D>
 void k_grid_persist(EngineParams, int) {}
 }  // namespace gpis
@@ -756,7 +756,9 @@ gpis_status gpis_peer_export(gpis_handle e, void* handle64) {
   EngineParams& P = e->P;
   if (!e->xchg_base) {
     const size_t rec = sizeof(double) * 2 * (size_t)P.world * P.pay_stride;
-    e->xchg_bytes = rec + sizeof(unsigned long long) * 3 * P.world;     // records, generation flags [2][world], done [world]
+    // records, generation flags [2][world], done [world], tagged per-step slots [2][world][16]
+    P.xll_off = (long long)(rec + sizeof(unsigned long long) * 3 * P.world);
+    e->xchg_bytes = (size_t)P.xll_off + sizeof(unsigned long long) * 2 * P.world * 16;
     CU(dalloc(e, reinterpret_cast<char**>(&e->xchg_base), e->xchg_bytes));
     CU(cudaMemset(e->xchg_base, 0, e->xchg_bytes));
     P.xchg = static_cast<double*>(e->xchg_base);
@@ -815,7 +817,8 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaEventRecord(e->ev0, s));
   // one persistent cooperative kernel for the whole greedy loop (lattice candidates, function values, fp64)
-  const bool persist = e->persist && e->backend == 2 && e->persist_grid_ok && !e->profiling && e->P.peer_mode && e->P.tile_cnt;
+  const bool persist = e->persist && e->backend == 2 && e->persist_grid_ok && !e->profiling && e->P.peer_mode && e->P.tile_cnt &&
+                       e->P.world <= PLL_WORLD_MAX;
   gpis_status rc = select_begin_impl(e, first_local, stream, persist ? QT : GT);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;

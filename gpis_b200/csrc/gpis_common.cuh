@@ -87,6 +87,10 @@ struct EngineParams {
   unsigned long long** peer_xflag;
   // selection fence: xdone[p] = last selection (epoch) rank p has finished reading records of; a rank
   // publishes nothing of selection e + 1 into a peer's region before every peer has finished e
+  // persistent selection kernel, sharded: per-step records as 8-byte {data half, tag} slots (no fence, no separate
+  // flag: a slot is valid when its tag is this step's) [2 parities][world][16 slots], at byte offset xll_off of
+  // every rank's exchange region
+  long long xll_off;
   unsigned long long* xdone;       // [world], written by the peers
   unsigned long long** peer_xdone;
   int ell_chunk;           // factor rows staged in shared memory per pass

@@ -135,6 +135,13 @@ __device__ __forceinline__ bool grid_barrier(const EngineParams& P, DevState* st
   return *s_flag != 0;
 }
 
+// tagged-slot records of the sharded persistent loop: 8 doubles per rank
+enum { PLL_SCORE = 0, PLL_ID = 1, PLL_LOCAL = 2, PLL_TSDF = 3, PLL_NOISE = 4, PLL_X = 5 };
+constexpr int PLL_WORLD_MAX = 16;
+__device__ __forceinline__ unsigned ll_tag(unsigned epoch, int gen) {
+  return 0x80000000u | ((epoch & 0x7fu) << 24) | ((unsigned)(gen + 1) & 0xffffffu);
+}
+
 struct PBest {
   double s;
   long long id, j;
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   __shared__ int s_pref[QT_MAX + 1];                      // exclusive prefix of the tiles' chunk counts
   __shared__ int s_wsum[GEMM_CWARPS];
   __shared__ unsigned short s_rho[QBLK * QKC];            // model rows of the units of the running block
+  __shared__ __align__(8) unsigned s_ll[16 * PLL_WORLD_MAX];   // sharded: the ranks' records of this step, 8 doubles each
   __shared__ int s_uoff[QBLK];                            // their tiles' offsets into the axis-table rows: jy0 | jx0 << 16
   __shared__ unsigned long long s_clk[PCLK_N], s_tk[1];   // CTA 0, thread 0 only: lap timer (globaltimer ns)
 
@@ -233,7 +241,50 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     const int m = r0, gen = r0;
     unsigned passed = 3u * (unsigned)r0;
     // ------------------------------------------------------------------ A: the winner
-    if (exchange || r0 == 0) {
+    if (exchange && r0 > 0) {
+      // sharded: every rank stored its record of this generation into our region as 16 tagged 8-byte slots
+      // ({low or high half of a double, tag}): a slot is valid as soon as its tag is this generation's -- no
+      // fence, no separate flag.  Every CTA polls the slots itself and picks the same winner.
+      const unsigned tag = ll_tag(st->epoch, gen);
+      const volatile unsigned long long* ll = reinterpret_cast<const volatile unsigned long long*>(
+          reinterpret_cast<const char*>(P.xchg) + P.xll_off) + (size_t)(gen & 1) * P.world * 16;
+      if (tid == 0) s_flag = 1;
+      __syncthreads();
+      if (tid < 16 * P.world && tid < 16 * PLL_WORLD_MAX) {
+        const long long t0 = clock64();
+        unsigned long long v = ll[tid];
+        unsigned n = 0;
+        while ((unsigned)(v >> 32) != tag) {
+          if ((++n & 63u) == 0u && (clock64() - t0 > P.spin_cycles || *(volatile int*)&st->err != 0)) { s_flag = 0; break; }
+          v = ll[tid];
+        }
+        s_ll[tid] = (unsigned)v;
+      }
+      __syncthreads();
+      if (!s_flag) { if (tid == 0) persist_fail(st); return; }
+      if (tid == 0) {
+        int win = -1;
+        double bs = 0.0;
+        long long bid = 0;
+        const double* recd = reinterpret_cast<const double*>(s_ll);
+        for (int w = 0; w < P.world; ++w) {
+          const double* pay = recd + w * 8;
+          const long long loc = __double_as_longlong(pay[PLL_LOCAL]);
+          if (loc < 0) continue;
+          const long long id = __double_as_longlong(pay[PLL_ID]);
+          if (win < 0 || better(pay[PLL_SCORE], id, bs, bid)) { win = w; bs = pay[PLL_SCORE]; bid = id; }
+        }
+        if (win >= 0 && m >= P.M_cap) win = -1;
+        s_win = win;
+        if (win >= 0) {
+          const double* pay = recd + win * 8;
+          s_rec[PAY_SCORE] = pay[PLL_SCORE]; s_rec[PAY_ID] = pay[PLL_ID]; s_rec[PAY_LOCAL] = pay[PLL_LOCAL];
+          s_rec[PAY_TSDF] = pay[PLL_TSDF]; s_rec[PAY_NOISE] = pay[PLL_NOISE];
+          for (int d = 0; d < MAXD; ++d) s_rec[PAY_X + d] = pay[PLL_X + d];
+        }
+      }
+    } else if (r0 == 0) {
+      // the first point: k_begin's record(s), in the record format of the per-step kernels
       if (!wait_records(P, st, gen)) return;
       const double* recs = records_ptr(P, gen);
       if (tid == 0) {
@@ -896,9 +947,38 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
 #pragma unroll
         for (int d = 0; d < D; ++d) st->nx[d] = s_rec[PAY_X + d];
       }
-      // sharded: this rank's record of every step goes to all peers; one GPU: only the last winner is
-      // published (the finalize kernel reads it)
-      if (exchange || r0 + 1 == iters) {
+      // sharded: this rank's record of every step goes to all peers as tagged slots; the last winner is also
+      // published in the record format of the per-step kernels (the finalize kernel reads it)
+      if (exchange && r0 + 1 < iters) {
+        const BlockBest b = s_next;
+        if (tid == 0) {
+          double* pay = reinterpret_cast<double*>(s_ll);
+          const long long jl = b.local;
+          pay[PLL_SCORE] = b.score;
+          pay[PLL_ID] = __longlong_as_double(jl >= 0 ? cand_id(P, jl) : -1);
+          pay[PLL_LOCAL] = __longlong_as_double(jl);
+          pay[PLL_TSDF] = jl >= 0 ? P.tsdf[jl] : 0.0;
+          pay[PLL_NOISE] = jl >= 0 ? (P.noise ? P.noise[jl] : P.noise_scalar) : 0.0;
+          long long rem = jl >= 0 ? jl : 0;
+#pragma unroll
+          for (int d = 0; d < MAXD; ++d) {
+            const long long len = P.glen[d] > 0 ? P.glen[d] : 1;
+            const long long jd = rem % len + (d == 2 ? P.gz0 : 0);
+            rem /= len;
+            pay[PLL_X + d] = P.gorg[d] + P.gh[d] * (double)jd;
+          }
+        }
+        __syncthreads();
+        const unsigned tag = ll_tag(st->epoch, r0 + 1);
+        for (int q = tid; q < 16 * P.world; q += PTHREADS) {
+          const int p = q >> 4, k = q & 15;
+          volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(
+              reinterpret_cast<char*>(P.peer_xchg[p]) + P.xll_off) + ((size_t)((r0 + 1) & 1) * P.world + P.rank) * 16 + k;
+          *dst = ((unsigned long long)tag << 32) | (unsigned long long)s_ll[k];
+        }
+        __syncthreads();
+      }
+      if (r0 + 1 == iters) {
         __syncthreads();
         const BlockBest b = s_next;
         write_record(P, b.score, b.local, 0);
