@@ -465,9 +465,83 @@ def run_ours(args):
             out["shape_sampling"] = sampling_block(eng, g, dev)
         except Exception as e:          # an extra must never cost the bench line
             out["shape_sampling"] = {"error": repr(e)}
+    if world == 1 and not args.no_extras:
+        for name, fn in (("config5_batch", lambda: config5_block(dev)), ("config2_arbitrary_points", lambda: config2_panel_block(dev, peaks))):
+            try:
+                out[name] = fn()
+            except Exception as e:      # an extra must never cost the bench line
+                out[name] = {"error": repr(e)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_block(dev, n_objects=512, g=32, K=256):
+    """BASELINE config 5: 512 independent 32^3 object fits, 256 points each, through gpis_batch_select (one thread
+    block runs the whole selection of an object, one launch for the batch).  Reported beside the headline."""
+    import torch
+    from gpis_b200.batch import select_batch_fused, superellipsoid_tsdf
+    stack = np.ascontiguousarray(np.stack([superellipsoid_tsdf(g, k) for k in range(n_objects)]))
+    cfg = dict(ell=2.5, noise=0.05, level=0.0, eps=1e-2, beta=10.0)
+    select_batch_fused(stack[:8], (g, g, g), K, 3254, keep_posterior=False, **cfg)              # warm-up
+    best, res = None, None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = select_batch_fused(stack, (g, g, g), K, 3254, **cfg)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    dev_s = res[0]["device_ms"] / 1e3
+    flops = sum(2.0 * g ** 3 * r["n_in_model"] * (r["n_in_model"] + 1) / 2 for r in res)
+    npts = sum(len(r["ids"]) for r in res)
+    return {"workload": f"{n_objects} x {g}^3 objects, {K}-pt active set each (gpis_batch_select, default inner loops = DMMA)",
+            "device_seconds": dev_s, "e2e_seconds": best, "objects_per_s_device": n_objects / dev_s, "objects_per_s_e2e": n_objects / best,
+            "pts_selected_per_s_e2e": npts / best, "h2d_bytes": int(stack.nbytes),
+            "d2h_bytes": int(stack.nbytes * 2 + stack.size + n_objects * K * 8),
+            "fp64_tflops_device": flops / dev_s / 1e12, "frac_of_fp64_peak": flops / dev_s / 1e12 / 37.18,
+            "ids_crc32": int(__import__("zlib").crc32(np.concatenate([np.asarray(r["ids"], np.int64) for r in res]).tobytes())),
+            "dtype": "f64"}
+
+
+def config2_panel_block(dev, peaks, g=64, K=1000):
+    """BASELINE config 2 through the ARBITRARY-POINT path: panel backend (V = L^-1 K kept in HBM, the update kernel
+    streams it: HBM-bound) and the dense prediction kernel over the 64^3 grid (fp64 tensor pipe)."""
+    import torch
+    from gpis_b200 import GpisEngine
+    from gpis_b200.synth import first_index, sphere_tsdf
+    pts, tsdf = sphere_tsdf(g)
+    N = g ** 3
+    d_pts = torch.as_tensor(np.ascontiguousarray(pts.T), device=dev)
+    d_tsdf = torch.as_tensor(tsdf, device=dev)
+    mean = torch.empty(N, dtype=torch.float64, device=dev)
+    var = torch.empty(N, dtype=torch.float64, device=dev)
+    eng = GpisEngine(3, N, K, ell=HYP_ELL, noise=NOISE, level=LEVEL, eps=EPS, beta=BETA)
+    eng.set_profiling(True)
+    best = None
+    for _ in range(2):
+        eng.set_candidates(d_pts, d_tsdf, soa=True)
+        eng.select(first_index(N), K)
+        eng.predict_into(d_pts, mean, var)
+        torch.cuda.synchronize()
+        t, h = eng.timing(), eng.history()
+        r, u = h["rows"].astype(np.float64), h["scored"].astype(np.float64)
+        alg = float(np.sum(8.0 * u * (r + 1) + u * 18.0))                        # SURVEY 8(d): bytes per step
+        cur = {"select_ms": t["select_ms"], "update_kernel_ms": t["update_ms"], "predict_ms": t["predict_ms"], "alg_bytes": alg}
+        best = cur if best is None or cur["select_ms"] < best["select_ms"] else best
+    ids, nm = eng.active()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = best["alg_bytes"] / (best["update_kernel_ms"] / 1e3) / 1e9
+    ptf = (N * float(nm) * nm + 2.0 * N * nm) / (best["predict_ms"] / 1e3) / 1e12
+    eng.close()
+    return {"workload": f"sphere TSDF {g}^3 as {N} arbitrary points, {K}-pt active set (panel backend) + dense prediction of all {N} points",
+            "select_ms": best["select_ms"], "predict_ms": best["predict_ms"], "n_selected": int(len(ids)),
+            "ids_crc32": int(__import__("zlib").crc32(np.asarray(ids, np.int64).tobytes())),
+            "update_kernel": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                              "note": "k_update: algorithmic bytes 8 U (r + 1) + 18 U per step / summed launch time (CUDA events per launch)"},
+            "predict_kernel": {"bound": "tensor", "achieved": ptf, "peak": 37.18, "unit": "TFLOP/s", "frac": ptf / 37.18,
+                               "note": "k_predict_f64: N R^2 + 2 N R flops / device time of gpis_predict"},
+            "dtype": "f64"}
 
 
 def sampling_block(eng, g, dev, per_axis=24, n_samples=8, jitter=1e-8):
@@ -569,6 +643,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tf32", action="store_true", help="skip the extra TF32-mode measurement")
     ap.add_argument("--no-sampling", action="store_true", help="skip the extra shape-sampling measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-5 batch and config-2 arbitrary-point extras")
     ap.add_argument("--no-profile", action="store_true", help="CUDA-graph launches, no per-launch events (no roofline)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")

@@ -1304,8 +1304,10 @@ gpis_status gpis_batch_select(const gpis_config* cfg_in, const int32_t* dims, co
   P.n_sel = d_cnt;
   P.n_model = d_cnt + n_objects;
   P.err = d_cnt + 2 * (size_t)n_objects;
-  // inner loops of the kernel (gpis_batch.cuh): cfg->batch_kernel, GPIS_BATCH_AUTO = the tuned DFMA form
-  const int fast = cfg->batch_kernel == GPIS_BATCH_PLAIN ? 0 : cfg->batch_kernel == GPIS_BATCH_DMMA ? 2 : 1;
+  // inner loops of the kernel (gpis_batch.cuh): cfg->batch_kernel; GPIS_BATCH_AUTO = the tensor-pipe (DMMA) form,
+  // the fastest of the three on a B200 (512 x 32^3 x 256: 93 ms against 126 ms DFMA-tuned and 169 ms plain,
+  // profiles/r02_batch_variants.json; same picks in all)
+  const int fast = cfg->batch_kernel == GPIS_BATCH_PLAIN ? 0 : cfg->batch_kernel == GPIS_BATCH_DFMA ? 1 : 2;
   CU(cudaFuncSetAttribute((const void*)k_batch_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
   CU(cudaFuncSetAttribute((const void*)k_batch_select_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));

@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     // takes one unit and leaves its 16 row indices and coefficients W[r,rho] Tz[rho][jz] in shared memory
     // (two dependent rounds of L2 loads, all of a block's in flight together), so that neither the producer
     // nor the MMA warps ever wait on global memory for them.
-    double* s_cs = s_kv;                                  // [QBLK][QKC], aliases the winner's covariance vector (phase B only)
+    double* s_cs = s_kv;                                  // [QKC][QBLK], aliases the winner's covariance vector (phase B only)
     const double sb = [&]() {
       double beta = P.beta;
       if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
@@ -716,8 +716,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           for (int k = 0; k < QKC; ++k) wv[k] = wrow[rho[k]];
 #pragma unroll
           for (int k = 0; k < QKC; ++k) {
-            s_cs[ul * QKC + k] = (c * QKC + k < cnt) ? wv[k] * tv[k] : 0.0;
-            s_rho[ul * QKC + k] = (unsigned short)rho[k];
+            s_cs[k * QBLK + ul] = (c * QKC + k < cnt) ? wv[k] * tv[k] : 0.0;      // [k][unit]: conflict-free stores
+            s_rho[k * QBLK + ul] = (unsigned short)rho[k];
           }
           s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
         }
@@ -732,7 +732,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
           double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
           double* Bs = As + QKC * QLD;
-          const int rho = (int)s_rho[ul * QKC + (lane & (QKC - 1))];
+          const int rho = (int)s_rho[(lane & (QKC - 1)) * QBLK + ul];
           const int uo = s_uoff[ul];
           if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
           __syncwarp();
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           if (cta == 0 && tid == 0) s_clk[PCLK_WAITFULL] += gtimer_ns() - tk0;
           const double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
           const double* Bs = As + QKC * QLD;
-          const double* cs = s_cs + ul * QKC;
+          const double* cs = s_cs + ul;
 #if GPIS_EXP == 1      // experiment: the MMA loop runs twice (second time with zero coefficients): the rise is its cost
           for (int rep = 0; rep < 2; ++rep)
 #endif
@@ -767,9 +767,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           for (int k4 = 0; k4 < QKC / 4; ++k4) {
             const int kb = k4 * 4 + (lane & 3);
 #if GPIS_EXP == 1
-            const double cv = rep ? 0.0 : cs[kb];
+            const double cv = rep ? 0.0 : cs[kb * QBLK];
 #else
-            const double cv = cs[kb];
+            const double cv = cs[kb * QBLK];
 #endif
             double af[2], bf[4];
 #pragma unroll

@@ -224,7 +224,7 @@ gpis_status gpis_get_sampling_timing(gpis_handle h, double* cov_ms, double* chol
  * variance of every lattice point and the level-set flags (bit 0 active, bit 1 high, bit 2 low),
  * [n_objects][N].  device_ms (NULL allowed): CUDA-event time of the launch.  cfg->batch_kernel selects
  * the form of the kernel's inner loops (GPIS_BATCH_PLAIN: untuned, GPIS_BATCH_DMMA: the update on the fp64
- * tensor pipe, GPIS_BATCH_DFMA / AUTO: the tuned register-tile form; same picks in all).  Returns
+ * tensor pipe -- the fastest, and what AUTO selects --, GPIS_BATCH_DFMA: the tuned register-tile form; same picks in all).  Returns
  * GPIS_ERR_NOT_PD if any object's factor lost positive definiteness (its counts tell where). */
 gpis_status gpis_batch_select(const gpis_config* cfg, const int32_t* dims, const double* origin,
                               const double* spacing, int32_t n_objects, const double* tsdf,

@@ -27,7 +27,7 @@ def _bench(n, *extra):
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                 "--master-port", "29571"]
     cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--grid", "48", "--active", "300", "--steps", "1",
-            "--warmup", "1", "--no-cpu-baseline", "--no-tf32", "--no-profile", *extra]
+            "--warmup", "1", "--no-cpu-baseline", "--no-tf32", "--no-profile", "--no-sampling", "--no-extras", *extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
