@@ -24,7 +24,7 @@ SYMBOLS = [
     "gpis_predict", "gpis_get_levelset", "gpis_get_candidate_posterior", "gpis_get_stats", "gpis_get_timing",
     "gpis_set_profiling", "gpis_get_history", "gpis_peer_export", "gpis_peer_import", "gpis_get_phase_timing",
     "gpis_posterior_cov", "gpis_sample_shapes", "gpis_get_sampling_timing", "gpis_batch_select",
-    "gpis_get_persist_timing", "gpis_build_tsdf", "gpis_set_candidates_f32", "gpis_set_grid_candidates_f32",
+    "gpis_get_persist_timing", "gpis_get_persist_balance", "gpis_build_tsdf", "gpis_set_candidates_f32", "gpis_set_grid_candidates_f32",
     "gpis_get_active_f32", "gpis_predict_f32", "gpis_get_candidate_posterior_f32",
 ]
 
@@ -107,6 +107,7 @@ def load():
         "gpis_get_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), i64p],
         "gpis_set_profiling": [vp, C.c_int32],
         "gpis_get_persist_timing": [vp, vp],
+        "gpis_get_persist_balance": [vp, vp, C.c_int32, i32p],
         "gpis_get_phase_timing": [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "gpis_peer_export": [vp, vp],
         "gpis_peer_import": [vp, vp, C.c_int32],

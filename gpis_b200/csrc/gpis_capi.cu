@@ -450,8 +450,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
 #endif
       e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
       CU(dalloc(e, &P.ypart, (size_t)std::max(e->solve1_ctas, e->num_sms) * GS1_RMAX));
-      CU(dalloc(e, &e->d_phase_clk, (size_t)16));
-      CU(cudaMemset(e->d_phase_clk, 0, 16 * sizeof(unsigned long long)));
+      CU(dalloc(e, &e->d_phase_clk, (size_t)16 + 2 * (size_t)e->num_sms));
+      CU(cudaMemset(e->d_phase_clk, 0, (16 + 2 * (size_t)e->num_sms) * sizeof(unsigned long long)));
       P.phase_clk = e->d_phase_clk;
     }
     if (e->fused_solve)
@@ -1684,6 +1684,18 @@ gpis_status gpis_build_tsdf(const uint8_t* inside, int32_t rows, int32_t cols, c
   if (valid_idx) CU(cudaMemcpyAsync(valid_idx, d_idx, sizeof(int) * n, cudaMemcpyDefault, s));
   if (n_valid) CU(cudaMemcpyAsync(n_valid, d_cnt, sizeof(int), cudaMemcpyDefault, s));
   CU(cudaStreamSynchronize(s));         // the scratch is released on return
+  return GPIS_OK;
+}
+
+gpis_status gpis_get_persist_balance(gpis_handle e, double* ms, int32_t capacity, int32_t* n_blocks) {
+  if (!e || !n_blocks) return GPIS_ERR_INVALID;
+  GUARD(e);
+  *n_blocks = e->d_phase_clk ? e->num_sms : 0;
+  if (!ms || !e->d_phase_clk) return GPIS_OK;
+  if (capacity < 2 * e->num_sms) return fail(e, GPIS_ERR_INVALID, "capacity smaller than 2 * blocks");
+  std::vector<unsigned long long> clk(2 * (size_t)e->num_sms);
+  CU(cudaMemcpy(clk.data(), e->d_phase_clk + 16, sizeof(unsigned long long) * clk.size(), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < clk.size(); ++i) ms[i] = (double)clk[i] * 1e-6;
   return GPIS_OK;
 }
 

@@ -50,6 +50,9 @@ constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment 
 constexpr int QT_MAX = 2048;                            // most tiles per rank the kernel takes (prefix table in smem)
 // exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2
 constexpr double QCUT = 48.52030263919617;
+// Stream-K splits the COST of a step evenly: a tile costs its chunks plus QEPI unit times for its epilogue (a chunk is
+// 0.52 us of MMAs, an epilogue about 2 us), so blocks with many short tiles are not the last to arrive.
+constexpr int QEPI = 4;
 constexpr int QBLK = 256;                               // units whose coefficients sit in shared memory at a time
 
 #ifndef GPIS_EMULATE
@@ -230,6 +233,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   const int T = txy * P.glen[2];
   if (tid < PCLK_N) s_clk[tid] = 0;
   if (tid == 0) s_tk[0] = gtimer_ns();
+  unsigned long long d_ns = 0, dwait_ns = 0, dt0 = 0;      // thread 0 of every CTA: its time in phase D / waiting for a filled stage
   int stop = 0;          // 1: nothing unclassified / capacity (done), 2: not positive definite
   unsigned gcount = 0;   // units this CTA has put through the GEMM ring so far (the barriers' phases run on across steps)
   int w_nslots = -1;     // W ring: slots of the current geometry and rows streamed through it so far
@@ -610,8 +614,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       }
     }
     // (the row lists are final since the first barrier: the unit prefix of phase D is formed here, off its critical path)
-    // exclusive prefix of the tiles' chunk counts (every tile has at least one chunk: its candidates are
-    // scored every step even when no model row reaches it)
+    // exclusive prefix of the tiles' COSTS in unit times: their 16-row chunks (at least one: a tile's candidates are
+    // scored every step even when no model row reaches it) + QEPI for the tile's epilogue
     {
       const int per = (T + PCW - 1) / PCW;             // <= QT_MAX / 256 = 8
       int cbuf[QT_MAX / PCW], loc = 0;
@@ -620,7 +624,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         for (int k = 0; k < QT_MAX / PCW; ++k) {
           const int t = tid * per + k;
           int c = 0;
-          if (k < per && t < T) { c = (__ldcg(P.rcnt + t) + QKC - 1) / QKC; c = c > 0 ? c : 1; }
+          if (k < per && t < T) { c = (__ldcg(P.rcnt + t) + QKC - 1) / QKC; c = (c > 0 ? c : 1) + QEPI; }
           cbuf[k] = c;
           loc += c;
         }
@@ -642,32 +646,108 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       }
       __syncthreads();
     }
-    if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
-    PSTAMP(PCLK_FINISH);
-    if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
-    PSTAMP(PCLK_BAR2);
-
-    // ------------------------------------------------------------------ D: update GEMM + epilogue
+    // This CTA's share [u0, u1) of the cost line; inside tile t the positions [0, C_t) are its chunks and
+    // [C_t, C_t + QEPI) stand for its epilogue.  cpref(t) = s_pref[t] - QEPI t is the prefix of the chunks alone.
     const long long U = s_pref[T];
     const int Gw = (int)min((long long)G, U);
     const bool working = cta < Gw;
     const long long u0 = working ? (long long)cta * U / Gw : 0, u1 = working ? (long long)(cta + 1) * U / Gw : 0;
-    const int n_units = (int)(u1 - u0);
-    int tile0 = 0;
-    {   // last tile whose first unit is <= u0
-      int lo = 0, hi = T - 1;
+    int tile0 = 0, c0 = 0, n_units = 0;
+    if (working) {
+      int lo = 0, hi = T - 1;      // last tile whose first position is <= u0
       while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_pref[mid] <= u0) lo = mid; else hi = mid - 1; }
       tile0 = lo;
+      c0 = (int)(u0 - s_pref[tile0]);
+      if (c0 >= s_pref[tile0 + 1] - s_pref[tile0] - QEPI) { ++tile0; c0 = 0; }      // u0 falls into the epilogue part
+      // chunks up to u1: those of the tile holding u1 - 1 count up to that position
+      lo = 0; hi = T - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_pref[mid] <= u1 - 1) lo = mid; else hi = mid - 1; }
+      const int tl = lo, Cl = s_pref[tl + 1] - s_pref[tl] - QEPI;
+      const long long q1 = ((long long)s_pref[tl] - (long long)QEPI * tl) + min((long long)Cl, u1 - s_pref[tl]);
+      const long long q0 = tile0 < T ? ((long long)s_pref[tile0] - (long long)QEPI * tile0) + c0 : q1;
+      n_units = (int)max(0LL, q1 - q0);
+      if (tile0 >= T) tile0 = T - 1;
     }
-    const int c0 = (int)(u0 - s_pref[tile0]);
+    const long long q_first = ((long long)s_pref[tile0] - (long long)QEPI * tile0) + c0;      // first chunk, in chunk space
+    double* s_cs = s_kv;                                  // [QKC][QBLK], aliases the winner's covariance vector (phase B only)
+    // The units of this CTA go through the ring in blocks of QBLK.  Before a block starts every thread takes one
+    // unit and leaves, in shared memory, its 16 model-row indices, its tile's offsets into the axis-table rows and
+    // the rows' z factors (part A: nothing of it depends on this step's row of W) and then multiplies the
+    // coefficients W[r, rho] in (part B), so that neither the producers nor the MMA warps ever wait on global
+    // memory for them.
+    auto stage_part_a = [&](int b0, int bn) {
+      for (int ul = tid; ul < bn; ul += PTHREADS) {
+        const long long u = q_first + b0 + ul;      // chunk-space index of this unit
+        int lo = tile0, hi = T - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((long long)s_pref[mid] - (long long)QEPI * mid <= u) lo = mid; else hi = mid - 1;
+        }
+        const int t = lo, c = (int)(u - ((long long)s_pref[t] - (long long)QEPI * t));
+        const int cnt = __ldcg(P.rcnt + t);
+        const uint4* rl4 = reinterpret_cast<const uint4*>(P.rlist + (size_t)t * P.rlist_stride + c * QKC);
+        const uint4 ra = __ldcg(rl4), rb = __ldcg(rl4 + 1);
+        const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
+        double tv[QKC];
+#pragma unroll
+        for (int k = 0; k < QKC; k += 2) { const double2 z2 = __ldcg(tz2 + (k >> 1)); tv[k] = z2.x; tv[k + 1] = z2.y; }
+#pragma unroll
+        for (int k = 0; k < QKC; ++k) {
+          const bool live = c * QKC + k < cnt;
+          const int rr = (int)((rw[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+          s_rho[k * QBLK + ul] = (unsigned short)(live ? rr : 0);      // [k][unit]: conflict-free stores
+          s_cs[k * QBLK + ul] = live ? tv[k] : 0.0;
+        }
+        s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
+      }
+    };
+    auto stage_part_b = [&](int bn) {
+      // row r0 of W is new this step: no line of it can be stale in L1, so these loads may be cached there
+      const double* wrow = P.W + (long long)r0 * P.ldW;
+      for (int ul = tid; ul < bn; ul += PTHREADS) {
+        double wv[QKC];
+#pragma unroll
+        for (int k = 0; k < QKC; ++k) wv[k] = wrow[s_rho[k * QBLK + ul]];
+#pragma unroll
+        for (int k = 0; k < QKC; ++k) s_cs[k * QBLK + ul] *= wv[k];
+      }
+    };
+    // producers: the 32 row copies of unit ul of the block at b0 (the unit's stage and phase follow from the
+    // running unit count)
+    auto issue_unit = [&](int b0, int ul) {
+      const unsigned q = gcount + (unsigned)(b0 + ul);
+      const int stage = (int)(q % QPIPE);
+      mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
+      double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
+      double* Bs = As + QKC * QLD;
+      const int rho = (int)s_rho[(lane & (QKC - 1)) * QBLK + ul];
+      const int uo = s_uoff[ul];
+      if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
+      __syncwarp();
+      if (lane < QKC)
+        bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
+      else
+        bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+    };
+    if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
+    PSTAMP(PCLK_FINISH);
+    if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
+    PSTAMP(PCLK_BAR2);
+    // Block 0's part A, then the first QPIPE units' copies go out while part B multiplies the coefficients in.
+    // (Measured: doing part A and these copies BEFORE the barrier gains nothing -- the wait-for-data time of the MMA
+    // warps is the cost of polling a completed barrier once per unit, not a pipeline-fill stall.)
+    const int bn0 = min(QBLK, n_units), npre = min(QPIPE, bn0);
+    stage_part_a(0, bn0);
+    __syncthreads();
+    if (warp >= GEMM_CWARPS)
+      for (int ul = warp - GEMM_CWARPS; ul < npre; ul += QPROD) issue_unit(0, ul);
+
+    // ------------------------------------------------------------------ D: update GEMM + epilogue
     PSTAMP(PCLK_PREFIX);
+    if (tid == 0) dt0 = gtimer_ns();
     PBest best;
     best.s = NEG_INF; best.id = 0x7fffffffffffffffLL; best.j = -1;
-    // The units of this CTA go through the ring in blocks of QBLK: before a block starts, every thread
-    // takes one unit and leaves its 16 row indices and coefficients W[r,rho] Tz[rho][jz] in shared memory
-    // (two dependent rounds of L2 loads, all of a block's in flight together), so that neither the producer
-    // nor the MMA warps ever wait on global memory for them.
-    double* s_cs = s_kv;                                  // [QKC][QBLK], aliases the winner's covariance vector (phase B only)
     const double sb = [&]() {
       double beta = P.beta;
       if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
@@ -677,7 +757,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     const double gn1 = s_fin[1];
     const int wm = warp >> 1, wn = warp & 1;
     // walking state of the consumers: tile, chunk inside it, its chunk count
-    int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0];
+    int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0] - QEPI;
     int seg_c0 = c0;                                      // first chunk of the running segment
     int def_t[2], ndef = 0;
     double acc[2][4][2];
@@ -687,76 +767,25 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int b0 = 0; b0 < n_units; b0 += QBLK) {
       const int bn = min(QBLK, n_units - b0);
-      __syncthreads();                                    // the previous block's coefficients are no longer read
       unsigned long long tk0 = 0;
       if (cta == 0 && tid == 0) tk0 = gtimer_ns();
-      {
-        const double* wrow = P.W + (long long)r0 * P.ldW;
-        for (int ul = tid; ul < bn; ul += PTHREADS) {
-          const long long u = u0 + b0 + ul;
-          int lo = tile0, hi = T - 1;
-          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_pref[mid] <= u) lo = mid; else hi = mid - 1; }
-          const int t = lo, c = (int)(u - s_pref[t]);
-          const int cnt = __ldcg(P.rcnt + t);
-          const uint4* rl4 = reinterpret_cast<const uint4*>(P.rlist + (size_t)t * P.rlist_stride + c * QKC);
-          const uint4 ra = __ldcg(rl4), rb = __ldcg(rl4 + 1);
-          const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-          int rho[QKC];
-          double wv[QKC], tv[QKC];
-          const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
-#pragma unroll
-          for (int k = 0; k < QKC; k += 2) { const double2 z2 = __ldcg(tz2 + (k >> 1)); tv[k] = z2.x; tv[k + 1] = z2.y; }
-#pragma unroll
-          for (int k = 0; k < QKC; ++k) {
-            const int rr = (int)((rw[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-            rho[k] = (c * QKC + k < cnt) ? rr : 0;
-          }
-          // row r0 of W is new this step: no line of it can be stale in L1, so these loads may be cached there
-#pragma unroll
-          for (int k = 0; k < QKC; ++k) wv[k] = wrow[rho[k]];
-#pragma unroll
-          for (int k = 0; k < QKC; ++k) {
-            s_cs[k * QBLK + ul] = (c * QKC + k < cnt) ? wv[k] * tv[k] : 0.0;      // [k][unit]: conflict-free stores
-            s_rho[k * QBLK + ul] = (unsigned short)rho[k];
-          }
-          s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
-        }
+      if (b0 > 0) {
+        __syncthreads();                                  // the previous block's coefficients are no longer read
+        stage_part_a(b0, bn);
+        __syncthreads();
       }
+      stage_part_b(bn);
       __syncthreads();
-      if (cta == 0 && tid == 0) { s_clk[PCLK_PRECOMP] += gtimer_ns() - tk0; if (b0 == 0) s_clk[PCLK_UNITS] += (unsigned long long)U; }
+      if (cta == 0 && tid == 0) { s_clk[PCLK_PRECOMP] += gtimer_ns() - tk0; if (b0 == 0) s_clk[PCLK_UNITS] += (unsigned long long)(U - (long long)QEPI * T); }
       if (warp >= GEMM_CWARPS) {
         // ------------------------------- producers: every QPROD-th unit each -------------------------------
-        for (int ul = warp - GEMM_CWARPS; ul < bn; ul += QPROD) {
-          const unsigned q = gcount + (unsigned)(b0 + ul);
-          const int stage = (int)(q % QPIPE);
-          mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
-          double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
-          double* Bs = As + QKC * QLD;
-          const int rho = (int)s_rho[(lane & (QKC - 1)) * QBLK + ul];
-          const int uo = s_uoff[ul];
-          if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
-          __syncwarp();
-#if GPIS_EXP == 2      // experiment: every copy issued twice (same destination): the rise in time is the copies' cost
-          if (lane == 0) asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&gfull[stage])), "r"(2 * QKC * QT * 8) : "memory");
-          __syncwarp();
-          if (lane < QKC)
-            bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
-          else
-            bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
-#endif
-          if (lane < QKC)
-            bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
-          else
-            bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
-        }
+        for (int ul = (b0 == 0 ? npre : 0) + warp - GEMM_CWARPS; ul < bn; ul += QPROD) issue_unit(b0, ul);
       } else {
         // --------------------------------- consumers ---------------------------------
         for (int ul = 0; ul < bn; ++ul) {
           const unsigned q = gcount + (unsigned)(b0 + ul);
           const int gstage = (int)(q % QPIPE);
-          if (cta == 0 && tid == 0) tk0 = gtimer_ns();
           mbar_wait(&gfull[gstage], (q / QPIPE) & 1u);
-          if (cta == 0 && tid == 0) s_clk[PCLK_WAITFULL] += gtimer_ns() - tk0;
           const double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
           const double* Bs = As + QKC * QLD;
           const double* cs = s_cs + ul;
@@ -832,7 +861,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           ++wt;
           wc = 0;
           seg_c0 = 0;
-          if (wt < T) wCt = s_pref[wt + 1] - s_pref[wt];
+          if (wt < T) wCt = s_pref[wt + 1] - s_pref[wt] - QEPI;
         }
       }
     }
@@ -844,8 +873,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       bool ok = true;
       for (int d = 0; d < ndef && ok; ++d) {
         const int t2 = def_t[d];
-        const int g_first = unit_owner((long long)s_pref[t2], U, Gw);
-        const int nseg = unit_owner((long long)s_pref[t2 + 1] - 1, U, Gw) - g_first + 1;
+        const int g_first = unit_owner((long long)s_pref[t2], U, Gw);                      // owner of the tile's first chunk
+        const int nseg = unit_owner((long long)s_pref[t2 + 1] - QEPI - 1, U, Gw) - g_first + 1;      // .. of its last chunk
         const int seg = cta - g_first;
         if (tid == 0) s_flag = spin_ge(&P.tile_cnt[t2], (unsigned)nseg, P, st) ? 1 : 0;
         named_sync(1, PCW);
@@ -853,8 +882,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         __threadfence();
         constexpr int UNITS = QPAIRS / PCW;                              // 8 units of 256 fragment slots
         const int un0 = seg * UNITS / nseg, un1 = (seg + 1) * UNITS / nseg;
-        // the first contributor's partial sits in its slot 1 unless the tile starts its range
-        const int slot_first = ((long long)g_first * U / Gw == (long long)s_pref[t2]) ? 0 : 1;
+        // the first contributor's partial sits in its slot 1 unless the tile is the first of its range
+        // (it starts its range when that range begins at the tile's first chunk or inside the previous tile's epilogue part)
+        const int slot_first = ((long long)g_first * U / Gw >= (long long)s_pref[t2] - QEPI) ? 0 : 1;
         const double2* wsb = reinterpret_cast<const double2*>(P.gws);
         const long long tbase = (long long)t2 * QPAIRS;
         for (int ub = un0; ub < un1; ub += GEPI_SPT) {
@@ -911,6 +941,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         __stcg(&dst->local, b.local);
       }
       PSTAMP(PCLK_EPI);
+      if (tid == 0) d_ns += gtimer_ns() - dt0;
     }
     // ---- every CTA waits for all, then reduces the CTA winners itself: the same winner everywhere
     if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
@@ -993,6 +1024,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     if (stop == 2) { st->err = -5; st->done = 1; }
     if (P.phase_clk)
       for (int i = 0; i < PCLK_N; ++i) P.phase_clk[i] = s_clk[i];
+  }
+  if (tid == 0 && P.phase_clk) {      // per-CTA view of phase D (load balance): [16 + 2 cta] total, [17 + 2 cta] waiting for data
+    P.phase_clk[PCLK_N + 2 * cta] = d_ns;
+    P.phase_clk[PCLK_N + 2 * cta + 1] = dwait_ns;
   }
 }
 

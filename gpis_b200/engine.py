@@ -294,6 +294,15 @@ class GpisEngine:
         self._ck(self.lib.gpis_get_persist_timing(self.h, _ptr(a)))
         return dict(zip(self.PERSIST_SLOTS, a.tolist()))
 
+    def persist_balance(self):
+        """Per-block (time in the update phase, of that waiting for operand data), ms, of the last persistent select()."""
+        n = C.c_int32()
+        self._ck(self.lib.gpis_get_persist_balance(self.h, None, 0, C.byref(n)))
+        a = np.zeros(2 * max(n.value, 1))
+        if n.value:
+            self._ck(self.lib.gpis_get_persist_balance(self.h, _ptr(a), a.size, C.byref(n)))
+        return a.reshape(-1, 2)[:n.value]
+
     def set_profiling(self, on=True):
         self._ck(self.lib.gpis_set_profiling(self.h, int(bool(on))))
 

@@ -305,6 +305,10 @@ gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main
  * [15] = number of (tile, 16-row chunk) units all blocks processed (a count; x 2*64*64*16 = executed MMA flops).
  * 16 doubles. */
 gpis_status gpis_get_persist_timing(gpis_handle h, double* ms16);
+/* Load balance of the persistent kernel's update phase in the last gpis_select: for every block, ms[2 b] = its time in
+ * the phase (MMAs + epilogues), ms[2 b + 1] = of that, waiting for operand data; summed over the steps.  *n_blocks
+ * receives the block count (ms may be NULL to query it); capacity = doubles available at ms. */
+gpis_status gpis_get_persist_balance(gpis_handle h, double* ms, int32_t capacity, int32_t* n_blocks);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
  * stream (plain launches instead of the captured graph). */
 gpis_status gpis_set_profiling(gpis_handle h, int32_t on);

@@ -22,6 +22,14 @@ for rep in range(2):
     eng.select(first_index(N), K)
 t = eng.timing()
 ids, nm = eng.active()
+bal = eng.persist_balance()
+if len(bal):
+    import numpy as np
+    o = np.argsort(bal[:, 0])
+    print("phase-D ms per block: min %.1f (block %d) median %.1f max %.1f (block %d); wait-for-data ms: min %.1f median %.1f max %.1f" % (
+        bal[o[0], 0], o[0], np.median(bal[:, 0]), bal[o[-1], 0], o[-1], bal[:, 1].min(), np.median(bal[:, 1]), bal[:, 1].max()), file=sys.stderr)
+    print("slowest 8 blocks:", [(int(b), round(bal[b, 0], 1), round(bal[b, 1], 1)) for b in o[-8:]], file=sys.stderr)
+    print("fastest 8 blocks:", [(int(b), round(bal[b, 0], 1), round(bal[b, 1], 1)) for b in o[:8]], file=sys.stderr)
 print(json.dumps({"lib": os.path.basename(_lib.LIB_PATH), "grid": g, "K": K, "n": int(len(ids)), "select_ms": t["select_ms"],
                   "phase_ms": {k: round(v, 2) for k, v in eng.persist_timing().items()},
                   "ids_crc32": int(__import__("zlib").crc32(ids.tobytes()))}))
