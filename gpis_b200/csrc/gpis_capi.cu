@@ -90,6 +90,10 @@ struct gpis_engine {
   void* xchg_base = nullptr;       // peer exchange region (cudaMalloc, IPC-exported)
   size_t xchg_bytes = 0;
   std::vector<void*> ipc_opened;
+  // scratch blocks of the prediction / sampling calls, kept across calls (a 25^3 draw needs ~2 GB of them and
+  // cudaMalloc / cudaFree of those dominated its host-side time); released by gpis_destroy
+  struct PoolBlock { void* p; size_t bytes; bool busy; };
+  std::vector<PoolBlock> pool;
 };
 
 namespace {
@@ -501,6 +505,7 @@ gpis_status gpis_destroy(gpis_handle e) {
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->allocs) cudaFree(p);
+  for (auto& b : e->pool) cudaFree(b.p);
   delete e;
   return GPIS_OK;
 }
@@ -822,14 +827,28 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   gpis_status rc = select_begin_impl(e, first_local, stream, persist ? QT : GT);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
-  if (persist) {
-    if (iters > 0) {
-      Dispatch d = get_dispatch(e->D, false);
-      int it_arg = iters;
-      void* args[] = {(void*)&e->P, (void*)&it_arg};
-      CU(launch_cooperative(d.g_persist, (unsigned)e->num_sms, PTHREADS, PERSIST_SMEM, s, args));
+  bool persist_ran = persist;
+  for (double& v : e->persist_ms) v = 0.0;      // of THIS selection (stay zero on the per-step path)
+  if (persist && iters > 0) {
+    Dispatch d = get_dispatch(e->D, false);
+    int it_arg = iters;
+    void* args[] = {(void*)&e->P, (void*)&it_arg};
+    const cudaError_t ce = launch_cooperative(d.g_persist, (unsigned)e->num_sms, PTHREADS, PERSIST_SMEM, s, args);
+    if (ce == cudaSuccess) {
       e->launches += 1;
+    } else if (e->P.world == 1) {
+      // the driver refused the cooperative launch (its blocks cannot all be resident: another context or an SM limit
+      // on the device): the per-step kernels take the selection, on their own state layout, and keep taking it
+      cudaGetLastError();
+      e->persist = false;
+      persist_ran = false;
+      rc = select_begin_impl(e, first_local, stream, GT);
+      if (rc != GPIS_OK) return rc;
+    } else {
+      return fail(e, GPIS_ERR_CUDA, std::string("cooperative launch of the persistent selection kernel: ") + cudaGetErrorString(ce));
     }
+  }
+  if (persist_ran) {
     rc = gpis_select_end(e, stream);
     if (rc != GPIS_OK) return rc;
     CU(cudaEventRecord(e->ev1, s));
@@ -1088,12 +1107,40 @@ namespace {
 // per-call device scratch, released on every return path
 struct Scratch {
   std::vector<void*> p;
-  ~Scratch() { for (void* q : p) cudaFree(q); }
+  gpis_engine* owner = nullptr;         // with an owner the blocks come from (and go back to) the handle's pool
+  cudaStream_t stream = nullptr;
+  Scratch() {}
+  Scratch(gpis_engine* e, cudaStream_t s) : owner(e), stream(s) {}
+  ~Scratch() {
+    if (!owner) { for (void* q : p) cudaFree(q); return; }
+    cudaStreamSynchronize(stream);      // (cudaFree used to synchronise here) the blocks may be handed out again at once
+    for (void* q : p)
+      for (auto& b : owner->pool)
+        if (b.p == q) b.busy = false;
+  }
   template <class T>
   cudaError_t get(T** out, size_t n) {
+    const size_t bytes = (n ? n : 1) * sizeof(T);
+    if (owner) {
+      int best = -1;
+      for (int i = 0; i < (int)owner->pool.size(); ++i) {
+        const auto& b = owner->pool[i];
+        if (!b.busy && b.bytes >= bytes && (best < 0 || b.bytes < owner->pool[best].bytes)) best = i;
+      }
+      if (best >= 0 && owner->pool[best].bytes <= 2 * bytes + (1 << 20)) {      // no 2 GB block for a 1 KB request
+        owner->pool[best].busy = true;
+        p.push_back(owner->pool[best].p);
+        *out = static_cast<T*>(owner->pool[best].p);
+        return cudaSuccess;
+      }
+    }
     void* q = nullptr;
-    cudaError_t r = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
-    if (r == cudaSuccess) { p.push_back(q); *out = static_cast<T*>(q); }
+    cudaError_t r = cudaMalloc(&q, bytes);
+    if (r == cudaSuccess) {
+      p.push_back(q);
+      *out = static_cast<T*>(q);
+      if (owner) owner->pool.push_back({q, bytes, true});
+    }
     return r;
   }
 };
@@ -1154,7 +1201,7 @@ gpis_status gpis_posterior_cov(gpis_handle e, const double* query, int64_t nq, i
   const long long nv = (long long)nq * (use_derivative ? e->D + 1 : 1);
   if (cov && ldc < nv) return fail(e, GPIS_ERR_INVALID, "ldc must be >= the number of values");
   cudaStream_t s = (cudaStream_t)stream;
-  Scratch sc;
+  Scratch sc(e, s);
   FullPosterior fp;
   cudaEventRecord(e->ev0, s);
   gpis_status rc = posterior_full(e, query, nq, use_derivative, s, sc, &fp);
@@ -1181,7 +1228,7 @@ gpis_status gpis_sample_shapes(gpis_handle e, const double* query, int64_t nq, i
   const long long nv = (long long)nq * (use_derivative ? e->D + 1 : 1);
   if (chol && ldt < nv) return fail(e, GPIS_ERR_INVALID, "ldt must be >= the number of values");
   cudaStream_t s = (cudaStream_t)stream;
-  Scratch sc;
+  Scratch sc(e, s);
   FullPosterior fp;
   cudaEventRecord(e->ev0, s);
   gpis_status rc = posterior_full(e, query, nq, use_derivative, s, sc, &fp);
@@ -1518,7 +1565,7 @@ cudaError_t stage_in_f32(Scratch& sc, const float* src, size_t n, cudaStream_t s
     dsrc = tmp;
   }
   if ((ce = sc.get(out, n)) != cudaSuccess) return ce;
-  k_f32_to_f64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dsrc, *out, n);
+  GPIS_LAUNCH_SMEM(k_f32_to_f64, (unsigned)((n + 255) / 256), 256, 0, s, dsrc, *out, n);
   return cudaGetLastError();
 }
 // n doubles on the device -> floats at a host or device pointer
@@ -1528,7 +1575,7 @@ cudaError_t stage_out_f32(Scratch& sc, const double* dsrc, float* dst, size_t n,
   cudaError_t ce = cudaSuccess;
   const bool dev = ptr_on_device(dst);
   if (!dev && (ce = sc.get(&ddst, n)) != cudaSuccess) return ce;
-  k_f64_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dsrc, ddst, n);
+  GPIS_LAUNCH_SMEM(k_f64_to_f32, (unsigned)((n + 255) / 256), 256, 0, s, dsrc, ddst, n);
   if ((ce = cudaGetLastError()) != cudaSuccess) return ce;
   if (!dev) ce = cudaMemcpyAsync(dst, ddst, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
   return ce;

@@ -277,8 +277,13 @@ gpis_status gpis_build_tsdf(const uint8_t* inside, int32_t rows, int32_t cols, c
                             double* tsdf, double* normals, double* noise, int32_t* valid_idx, int32_t* n_valid,
                             int32_t device, void* stream);
 
-/* Level-set state of the candidates after selection: last ambiguity each candidate was
- * scored with, and the high / low masks (straddle.m:121-125; ClassificationBuffers). */
+/* Level-set state of the candidates after selection: the high / low masks (straddle.m:121-125; ClassificationBuffers)
+ * and the straddle score (straddle.m:106-108).  For a candidate that is still unclassified (not active, not high, not
+ * low) `ambiguity` is the score it was last scored with = the score of the current posterior, on both backends.  For
+ * a classified candidate the backends keep different things and say so: the panel backend stops updating it (the
+ * reference only predicts on unclassified points, straddle.m:79-81) and returns the score it had when it was
+ * classified; the lattice backend updates every lattice point every step and returns the score of the CURRENT
+ * posterior with the last step's beta. */
 gpis_status gpis_get_levelset(gpis_handle h, double* ambiguity, uint8_t* high, uint8_t* low,
                               uint8_t* active, void* stream);
 /* Running posterior of the candidates (exact for candidates still unclassified). */

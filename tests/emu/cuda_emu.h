@@ -177,6 +177,9 @@ inline T __shfl_sync(unsigned, T v, int src_lane) {
 }
 template <class T>
 inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return __shfl_sync(m, v, emu::my_lane ^ lane_mask); }
+// lanes below `delta` keep their own value, like the hardware
+template <class T>
+inline T __shfl_up_sync(unsigned m, T v, int delta) { return __shfl_sync(m, v, emu::my_lane >= delta ? emu::my_lane - delta : emu::my_lane); }
 inline unsigned __ballot_sync(unsigned, bool pred) {
   unsigned m = 0;
   emu::exchange(pred ? 1ull : 0ull, 0, &m);

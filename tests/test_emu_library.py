@@ -153,3 +153,53 @@ def test_batch_and_panel_through_the_emulated_library(G):
     assert ei.value.status == G._lib.ERR_INVALID
     with pytest.raises(G._lib.GpisError):
         G.GpisEngine(3, 10, 4, ell=2.0, precision=G._lib.PREC_TF32)          # tcgen05 is not emulated
+
+
+def test_tsdf_builder_and_float_entry_points_through_the_emulated_library(G):
+    """gpis_build_tsdf (auto_tsdf.m:133-262) bit for bit against the oracle on a stored reference shape and a
+    random image, and the fp32 entry points of the reference ABI, on the CPU emulation."""
+    import ctypes as C
+    from oracle import tsdf_oracle as T
+    from test_oracle_tsdf import REF_VP
+    z = np.load(os.path.join(ROOT, "tests", "golden", "tsdf_shapes.npz"))
+    inside = z["tape_inside"]
+    u = np.random.default_rng(2).uniform(size=(3,) + inside.shape)
+    sp, ref = G.auto_tsdf(inside, REF_VP, u=u), T.auto_tsdf(inside, REF_VP, u)
+    assert np.array_equal(sp["fullTsdf"], z["tape_fullTsdf"]) and np.array_equal(sp["fullNormals"], z["tape_fullNormals"])
+    rng = np.random.default_rng(5)
+    img = rng.uniform(size=(13, 9)) < 0.6
+    img[3:9, 2:7] = True
+    u2 = rng.uniform(size=(3, 13, 9))
+    vp = dict(REF_VP, noiseGradMode="BLTR", specularNoise=True, sparsityRate=0.3, edgeWin=1, horizScale=0.7, vertScale=1.3,
+              y_thresh1_low=1.5, y_thresh1_high=6, x_thresh1_low=0, x_thresh1_high=3)
+    for a, b in ((sp, ref), (G.auto_tsdf(img, vp, u=u2), T.auto_tsdf(img, vp, u2))):
+        for k in ("tsdf", "noise", "normals", "points", "fullTsdf", "fullNormals", "fullNoise", "validIndices"):
+            assert np.array_equal(a[k], b[k]), k
+    # float ABI: candidates in as float, active set out as float
+    from gpis_b200 import _lib
+    lib = _lib.load()
+    dims = (6, 5, 3)
+    pts, tsdf = blob(dims, 3)
+    N, K = len(pts), 8
+    t32 = tsdf.astype(np.float32)
+    d32 = np.array(dims, np.int32)
+    org, spc = np.zeros(3), np.ones(3)
+    ref_eng = G.GpisEngine(3, N, K, ell=2.0, noise=0.05)
+    ref_eng.set_grid_candidates(dims, (0, 0, 0), (1, 1, 1), t32.astype(np.float64))
+    ref_eng.select(7, K)
+    eng = G.GpisEngine(3, N, K, ell=2.0, noise=0.05)
+    eng._ck(lib.gpis_set_grid_candidates_f32(eng.h, d32.ctypes.data, org.ctypes.data, spc.ctypes.data, 0, dims[2],
+                                             t32.ctypes.data, None, None, None))
+    eng.select(7, K)
+    ids, nm = eng.active()
+    assert np.array_equal(ids, ref_eng.active()[0])
+    ain, atg = np.full(3 * K, -1, np.float32), np.full(K, -1, np.float32)
+    ns, nmm = C.c_int32(), C.c_int32()
+    eng._ck(lib.gpis_get_active_f32(eng.h, K, ain.ctypes.data, atg.ctypes.data, C.byref(ns), C.byref(nmm), None))
+    assert ns.value == len(ids) and nmm.value == nm
+    assert np.array_equal(ain.reshape(3, K)[:, :nm], pts[ids[:nm]].T.astype(np.float32))
+    assert np.array_equal(atg[:nm], t32[ids[:nm]])
+    pm, pv = np.empty(N, np.float32), np.empty(N, np.float32)
+    eng._ck(lib.gpis_get_candidate_posterior_f32(eng.h, pm.ctypes.data, pv.ctypes.data, None))
+    mu, var = eng.candidate_posterior()
+    assert np.array_equal(pm, mu.astype(np.float32)) and np.array_equal(pv, var.astype(np.float32))

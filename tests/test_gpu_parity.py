@@ -319,3 +319,22 @@ def test_float_entry_points_match_the_double_ones(G):
             mu, var = eng.candidate_posterior()
             assert np.array_equal(pm, mu.astype(np.float32)) and np.array_equal(pv, var.astype(np.float32))
         eng.close()
+
+
+def test_levelset_ambiguity_agrees_across_backends_on_unclassified_candidates(G):
+    """gpis_get_levelset: the straddle score of every still-unclassified candidate is the same on the panel and the
+    lattice backend (and equals the oracle's); classified candidates differ by design (see the header)."""
+    shape, hyp = sphere(18, ell=3.0)
+    tr = {"activeSetSize": 90, "beta": 10.0, "eps": 1e-2, "levelSet": 0.0}
+    ora = O.select_straddle_incremental(shape, tr, 1234, hyp=hyp, prune=False)
+    out = {}
+    for backend in ("panel", "grid"):
+        mdl, pred, _ = G.select_active_set(shape, tr, first_index=1234, hyp=hyp, backend=backend, predict=False)
+        amb, hi, lo, ac = mdl.engine.levelset()
+        out[backend] = (amb, hi | lo | ac)
+        assert np.array_equal(mdl["order"], ora["order"])
+    unc = ~out["panel"][1]
+    assert np.array_equal(out["panel"][1], out["grid"][1]) and unc.sum() > 100
+    # the last pick is selected but not in the model (straddle.m:129-130): scores are those of the last scoring
+    assert np.max(np.abs(out["panel"][0][unc] - out["grid"][0][unc])) < 1e-9
+    assert np.max(np.abs(out["grid"][0][unc] - ora["ambiguity"][unc])) < 1e-9
