@@ -465,8 +465,8 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)disp.update, UPD_THREADS, e->upd_smem));
     if (occ < 1) return fail(e, GPIS_ERR_CUDA, "update kernel does not fit on an SM");
     e->upd_grid = e->num_sms * occ;
-    CU(dalloc(e, &P.partials, (size_t)e->upd_grid));
-    e->partials_cap = (size_t)e->upd_grid;
+    e->partials_cap = (size_t)std::max(e->upd_grid, 2 * e->num_sms);      // persistent kernel: winner + its target / noise per CTA
+    CU(dalloc(e, &P.partials, e->partials_cap));
     e->state_cap = Nn;
     CU(cudaEventCreate(&e->ev0));
     CU(cudaEventCreate(&e->ev1));

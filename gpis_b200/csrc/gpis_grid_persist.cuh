@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   __shared__ double s_gram[PTHREADS / 32][2];
   __shared__ double s_fin[3];                             // dinv, g_new, ok
   __shared__ BlockBest s_bb[GEMM_CWARPS];
+  __shared__ double s_next_aux[2];                        // its target and noise
   __shared__ BlockBest s_next;                            // the winner every CTA reduced at the end of the previous step
   __shared__ int s_win, s_flag;
   __shared__ int s_pref[QT_MAX + 1];                      // exclusive prefix of the tiles' chunk counts
@@ -318,8 +319,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           s_rec[PAY_SCORE] = s_next.score;
           s_rec[PAY_ID] = __longlong_as_double(s_next.id);
           s_rec[PAY_LOCAL] = __longlong_as_double(jl);
-          s_rec[PAY_TSDF] = P.tsdf[jl];
-          s_rec[PAY_NOISE] = P.noise ? P.noise[jl] : P.noise_scalar;
+          s_rec[PAY_TSDF] = s_next_aux[0];
+          s_rec[PAY_NOISE] = s_next_aux[1];
           long long rem = jl;
 #pragma unroll
           for (int d = 0; d < MAXD; ++d) {
@@ -939,6 +940,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         __stcg(&dst->score, b.score);
         __stcg(&dst->id, b.id);
         __stcg(&dst->local, b.local);
+        // the candidate's target and noise travel with it (entries G + cta): whoever wins, the next step needs
+        // no dependent load for them
+        BlockBest* aux = &P.partials[G + cta];
+        __stcg(&aux->score, b.local >= 0 ? P.tsdf[b.local] : 0.0);
+        __stcg(reinterpret_cast<double*>(&aux->id), b.local >= 0 ? (P.noise ? P.noise[b.local] : P.noise_scalar) : 0.0);
       }
       PSTAMP(PCLK_EPI);
       if (tid == 0) d_ns += gtimer_ns() - dt0;
@@ -949,19 +955,22 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     if (warp == 0) {
       BlockBest b;
       b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
+      double bt = 0.0, bn = 0.0;
       for (int i = lane; i < G; i += 32) {
         const BlockBest* pp = &P.partials[i];
         const double ps = __ldcg(&pp->score);
         const long long pid = __ldcg(&pp->id), ploc = __ldcg(&pp->local);
-        if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; }
+        const double pt = __ldcg(&P.partials[G + i].score), pn = __ldcg(reinterpret_cast<const double*>(&P.partials[G + i].id));
+        if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; bt = pt; bn = pn; }
       }
       for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
         const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
         const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
-        if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; }
+        const double ot = __shfl_xor_sync(0xffffffffu, bt, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+        if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; bt = ot; bn = on; }
       }
-      if (lane == 0) s_next = b;
+      if (lane == 0) { s_next = b; s_next_aux[0] = bt; s_next_aux[1] = bn; }
     }
     __syncthreads();
     if (cta == 0) {
@@ -988,8 +997,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           pay[PLL_SCORE] = b.score;
           pay[PLL_ID] = __longlong_as_double(jl >= 0 ? cand_id(P, jl) : -1);
           pay[PLL_LOCAL] = __longlong_as_double(jl);
-          pay[PLL_TSDF] = jl >= 0 ? P.tsdf[jl] : 0.0;
-          pay[PLL_NOISE] = jl >= 0 ? (P.noise ? P.noise[jl] : P.noise_scalar) : 0.0;
+          pay[PLL_TSDF] = s_next_aux[0];
+          pay[PLL_NOISE] = s_next_aux[1];
           long long rem = jl >= 0 ? jl : 0;
 #pragma unroll
           for (int d = 0; d < MAXD; ++d) {
