@@ -386,10 +386,10 @@ def run_ours(args):
             tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
             tach = 3.0 * tach
         if persist_used:
-            # executed flops: (tile, 16-row chunk) units x 2 * 64 * 64 * 16, counted by the kernel itself; the phase
+            # executed flops: (tile, 32-row chunk) units x 2 * 64 * 64 * 32, counted by the kernel itself; the phase
             # time is rank 0's block-0 lap timer summed over the steps (phase D: unit prefix, coefficient
             # precompute, MMAs and the in-register epilogues of whole tiles)
-            exe_flops = float(tot[3]) / args.steps * 2.0 * 64 * 64 * 16
+            exe_flops = float(tot[3]) / args.steps * 2.0 * 64 * 64 * 32
             tach = exe_flops / main_s / 1e12
             ps = {k: v / args.steps for k, v in acc["persist"].items()}
         roof = {"kernel": ("k_grid_persist, update-GEMM phase (per step and 64 x 64 lattice tile a [64 x rows] x [rows x 64] contraction over the "

@@ -644,7 +644,7 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
         e->tt_cap[d] = need;
       }
     }
-    P.rlist_stride = (P.R_cap + 15) & ~15;      // whole 16-row chunks, 32-byte aligned
+    P.rlist_stride = (P.R_cap + QKC - 1) / QKC * QKC;      // whole chunks, 64-byte aligned
     if ((size_t)tiles_q * P.rlist_stride > e->rlist_cap) {
       CU(dalloc(e, &P.rlist, (size_t)tiles_q * P.rlist_stride));
       CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));

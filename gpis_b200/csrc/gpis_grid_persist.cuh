@@ -20,7 +20,7 @@
 //      pipe (DMMA.8x8x4) over 64 x 64 lattice tiles.  A tile only sums the model rows of ITS list: the
 //      rows whose SE factor over the tile's box is >= 2^-70 -- the dropped terms are below 2^-70 |W| each,
 //      far under one ulp of the sum, so the result is the double-precision sum of all rows.  Stream-K over
-//      the (tile, 16-row chunk) units of all lists; a tile that lies inside one CTA's range (most do)
+//      the (tile, 32-row chunk) units of all lists; a tile that lies inside one CTA's range (most do)
 //      goes from the accumulator registers straight into the epilogue (posterior update, straddle score
 //      straddle.m:106-108, classification :122-125, arg-max) while the producer warp already fills the
 //      ring with the next tile's rows; a tile cut by a range boundary goes through a per-CTA workspace and its contributors
@@ -37,23 +37,23 @@ namespace gpis {
 enum { PCLK_RECWAIT = 0, PCLK_WSETUP = 1, PCLK_WPASS = 2, PCLK_BAR1 = 3, PCLK_FINISH = 4, PCLK_BAR2 = 5, PCLK_PREFIX = 6,
        PCLK_GEMM = 7, PCLK_EPI = 8, PCLK_BAR3 = 9, PCLK_WINNER = 10, PCLK_STEPS = 11,
        // inside PCLK_GEMM (booked twice): coefficient precompute, waits for a filled stage, in-register epilogues; the
-       // (tile, 16-row chunk) units of ALL blocks (a count: x 2 * 64 * 64 * 16 = the flops the MMAs executed)
+       // (tile, 32-row chunk) units of ALL blocks (a count: x 2 * 64 * 64 * 32 = the flops the MMAs executed)
        PCLK_PRECOMP = 12, PCLK_WAITFULL = 13, PCLK_EPIREG = 14, PCLK_UNITS = 15, PCLK_N = 16 };
 
 constexpr int QT = 64;                                  // lattice tile edge (jy x jx) of the persistent kernel
-constexpr int QKC = 16;                                 // model rows per pipeline stage
+constexpr int QKC = 32;                                 // model rows per pipeline stage (a "unit" = one tile x 32 rows)
 constexpr int QLD = QT + 4;                             // padded smem row (conflict-free DMMA fragment loads)
-constexpr int QSTAGE_DOUBLES = 2 * QKC * QLD + QKC;     // Ty rows, Tx rows, coefficients
-constexpr int QPIPE = 8;
+constexpr int QSTAGE_DOUBLES = 2 * QKC * QLD;           // Ty rows, Tx rows
+constexpr int QPIPE = 4;
 constexpr int QTILE_ELEMS = QT * QT;
 constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment slots (x-adjacent pairs) per tile
 constexpr int QT_MAX = 2048;                            // most tiles per rank the kernel takes (prefix table in smem)
 // exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2
 constexpr double QCUT = 48.52030263919617;
 // Stream-K splits the COST of a step evenly: a tile costs its chunks plus QEPI unit times for its epilogue (a chunk is
-// 0.52 us of MMAs, an epilogue about 2 us), so blocks with many short tiles are not the last to arrive.
-constexpr int QEPI = 4;
-constexpr int QBLK = 256;                               // units whose coefficients sit in shared memory at a time
+// 1.04 us of MMAs, an epilogue about 2 us), so blocks with many short tiles are not the last to arrive.
+constexpr int QEPI = 2;
+constexpr int QBLK = 128;                               // units whose coefficients sit in shared memory at a time
 
 #ifndef GPIS_EMULATE
 #ifndef GPIS_EXP
@@ -75,6 +75,7 @@ constexpr size_t PERSIST_SMEM =
 static_assert((size_t)QPIPE * QSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
 static_assert(QBLK * QKC <= GS1_RMAX, "the coefficients of a block alias the covariance vector");
+static_assert(QKC == 32, "a producer warp issues one Ty row and one Tx row per lane");
 
 #define PSTAMP(slot)                                                       \
   do {                                                                     \
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       }
     }
     // (the row lists are final since the first barrier: the unit prefix of phase D is formed here, off its critical path)
-    // exclusive prefix of the tiles' COSTS in unit times: their 16-row chunks (at least one: a tile's candidates are
+    // exclusive prefix of the tiles' COSTS in unit times: their 32-row chunks (at least one: a tile's candidates are
     // scored every step even when no model row reaches it) + QEPI for the tile's epilogue
     {
       const int per = (T + PCW - 1) / PCW;             // <= QT_MAX / 256 = 8
@@ -687,8 +688,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         const int t = lo, c = (int)(u - ((long long)s_pref[t] - (long long)QEPI * t));
         const int cnt = __ldcg(P.rcnt + t);
         const uint4* rl4 = reinterpret_cast<const uint4*>(P.rlist + (size_t)t * P.rlist_stride + c * QKC);
-        const uint4 ra = __ldcg(rl4), rb = __ldcg(rl4 + 1);
-        const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        unsigned rw[QKC / 2];
+#pragma unroll
+        for (int k = 0; k < QKC / 8; ++k) {
+          const uint4 r4 = __ldcg(rl4 + k);
+          rw[4 * k] = r4.x; rw[4 * k + 1] = r4.y; rw[4 * k + 2] = r4.z; rw[4 * k + 3] = r4.w;
+        }
         const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
         double tv[QKC];
 #pragma unroll
@@ -714,7 +719,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         for (int k = 0; k < QKC; ++k) s_cs[k * QBLK + ul] *= wv[k];
       }
     };
-    // producers: the 32 row copies of unit ul of the block at b0 (the unit's stage and phase follow from the
+    // producers: the 64 row copies of unit ul of the block at b0 (the unit's stage and phase follow from the
     // running unit count)
     auto issue_unit = [&](int b0, int ul) {
       const unsigned q = gcount + (unsigned)(b0 + ul);
@@ -722,14 +727,12 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
       double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
       double* Bs = As + QKC * QLD;
-      const int rho = (int)s_rho[(lane & (QKC - 1)) * QBLK + ul];
+      const int rho = (int)s_rho[lane * QBLK + ul];
       const int uo = s_uoff[ul];
       if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
       __syncwarp();
-      if (lane < QKC)
-        bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
-      else
-        bulk_g2s(Bs + (lane - QKC) * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+      bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
+      bulk_g2s(Bs + lane * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
     };
     if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
     PSTAMP(PCLK_FINISH);
