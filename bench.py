@@ -203,7 +203,8 @@ def run_ours(args):
     g = args.grid
     grid_backend = args.backend == "grid"
     if grid_backend:       # z-slabs of the lattice
-        z0, z1 = gdist.slab_range(g, rank, world)
+        # z-slabs with about equal work per rank (end slices sum fewer model rows) unless --equal-slabs
+        z0, z1 = gdist.slab_range(g, rank, world) if args.equal_slabs else gdist.slab_range_balanced(g, rank, world, HYP_ELL)
         lo, hi = g * g * z0, g * g * z1
     else:
         lo, hi = gdist.shard_range(N, rank, world)
@@ -649,6 +650,7 @@ def main():
                     help="N>1: per-step record exchange by in-kernel P2P stores over NVLink (default) or an NCCL all-gather")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "tf32"],
                     help="fp64 (default, exact-sequence mode) or tf32: update GEMM on tcgen05 with the 3xTF32 split")
+    ap.add_argument("--equal-slabs", action="store_true", help="N>1: equal z-slabs instead of work-balanced ones")
     ap.add_argument("--loop", default="auto", choices=["auto", "steps"],
                     help="auto: one persistent cooperative kernel per selection when eligible; steps: per-step launches (CUDA graph)")
     ap.add_argument("--backend", default="grid", choices=["grid", "panel"],

@@ -146,3 +146,16 @@ def test_shard_ranges_cover_and_align():
             rs = [gdist.slab_range(nz, r, w) for r in range(w)]
             assert rs[0][0] == 0 and rs[-1][1] == nz and all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
     assert gdist.owner_of(560310, 2097152, 8) == (2, 36022)
+
+
+def test_balanced_slabs_partition_the_lattice():
+    """slab_range_balanced: contiguous, complete, non-empty slabs; end slabs are thicker than middle ones when the
+    reach of a model row (9.85 ell) is a fraction of the axis; equal split when it covers the whole axis."""
+    for nz, world, ell in [(128, 8, 4.0), (128, 4, 4.0), (128, 2, 4.0), (10, 8, 4.0), (64, 3, 1.0), (8, 8, 2.0), (256, 8, 6.0)]:
+        rs = [gdist.slab_range_balanced(nz, r, world, ell) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == nz
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:])) and all(z1 > z0 for z0, z1 in rs)
+    rs = [gdist.slab_range_balanced(128, r, 8, 4.0) for r in range(8)]
+    sizes = [z1 - z0 for z0, z1 in rs]
+    assert sizes[0] > sizes[3] and sizes[-1] > sizes[4] and max(sizes) - min(sizes) <= 8
+    assert [gdist.slab_range_balanced(32, r, 4, 100.0) for r in range(4)] == [gdist.slab_range(32, r, 4) for r in range(4)]
