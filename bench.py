@@ -383,8 +383,12 @@ def run_ours(args):
         tpeak = float(fp64.get("dmma_m8n8k4_tflops", 37.2)) * world
         tach = float(tot[2]) / args.steps / main_s / 1e12
         if args.precision == "tf32":
-            # tcgen05 kind::tf32 runs at half the bf16 rate; three MMAs per algorithmic product (3xTF32)
-            tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
+            # dense tcgen05 kind::tf32 peak measured on this pool's B200 (scripts/tf32_peak.cu, profiles/r02_tf32_peak.json);
+            # three MMAs per algorithmic product (3xTF32): achieved counts the EXECUTED flops, useful = a third of it
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, "profiles", "r02_tf32_peak.json")))["tcgen05_tf32_m128n128k8_tflops"]) * world
+            except Exception:
+                tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
             tach = 3.0 * tach
         if persist_used:
             # executed flops: (tile, 32-row chunk) units x 2 * 64 * 64 * 32, counted by the kernel itself; the phase
@@ -403,7 +407,7 @@ def run_ours(args):
                 "peak_source": ("fp64 DMMA.8x8x4 peak measured on this pool's B200 by scripts/fp64_peak.cu "
                                 "(profiles/r01_fp64_peak.json) x n_gpus; MEASURED_PEAKS.json has no fp64 figure")
                 if args.precision == "fp64" else
-                "MEASURED_PEAKS.json bf16_tflops / 2 (tcgen05 kind::tf32 rate) x n_gpus; achieved counts the 3 executed MMAs per product",
+                "dense tcgen05 kind::tf32 peak measured by scripts/tf32_peak.cu (profiles/r02_tf32_peak.json, 1049 TFLOP/s) x n_gpus; achieved counts the 3 executed MMAs per product (useful flops = a third)",
                 "traffic": ncu_traffic("r01_k_grid_gemm_ncu.csv"),
                 "traffic_note": "DRAM bytes read+written per launch from the committed ncu --set full capture (profiles/, launch at r~300): the operands come from L2, the kernel is not HBM-bound",
                 "algorithmic_flops_per_step": float(tot[2]) / args.steps,
