@@ -62,7 +62,9 @@ struct gpis_engine {
   bool persist = false;            // gpis_select runs the whole greedy loop in one cooperative kernel
   bool self_peer = false;          // world_size 1: the exchange region is this engine's own (flags release the CTAs)
   unsigned long long* d_phase_clk = nullptr;
-  size_t tile_cnt_cap = 0, rlist_cap = 0, tt_cap[MAXD] = {0, 0, 0};
+  size_t tile_cnt_cap = 0, rlist_cap = 0, tt_cap[MAXD] = {0, 0, 0}, upref_cap = 0;
+  int* d_upref = nullptr;
+  bool step_lists = false;         // per-step path sums per-tile row lists (gradient / large fp64 models on a lattice)
   bool persist_grid_ok = false;    // the lattice of the last gpis_set_grid_candidates fits the persistent kernel
   double persist_ms[16] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
   int solve1_ctas = 0;
@@ -176,6 +178,8 @@ struct Dispatch {
   void (*g_solve2)(EngineParams);
   void (*g_wrow)(EngineParams);
   void (*g_gemm)(EngineParams);
+  void (*g_gemm_lists)(EngineParams);
+  void (*g_lists)(EngineParams);
   void (*g_gemm_tf32)(EngineParams);
   void (*g_epi)(EngineParams);
   void (*g_persist)(EngineParams, int);
@@ -184,7 +188,7 @@ struct Dispatch {
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>, k_grid_persist<D>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB, false>, k_grid_gemm<NB, true>, k_grid_lists<NB, D>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>, k_grid_persist<D>};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -229,6 +233,10 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
       }
       GPIS_LAUNCH_SMEM(d.g_wrow, e->solve_ctas, GSOLVE_THREADS, 0, s, e->P);
       e->launches += 2;
+      if (e->P.upref) {      // the new point's rows join the tiles' row lists; unit prefix of the update GEMM
+        GPIS_LAUNCH_SMEM(d.g_lists, 1, 1024, 0, s, e->P);
+        e->launches += 1;
+      }
     }
   } else {
     GPIS_LAUNCH_SMEM(d.append, 1, APP_THREADS, 0, s, e->P, external, finalize_only);
@@ -242,6 +250,7 @@ gpis_status launch_update(gpis_engine* e, cudaStream_t s, cudaEvent_t mid = null
   Dispatch d = get_dispatch(e->D, e->NB > 1);
   if (e->backend == 2) {
     if (e->cfg.precision == GPIS_PREC_TF32) GPIS_LAUNCH_SMEM(d.g_gemm_tf32, e->P.gemm_ctas, TF32_THREADS, TF32_SMEM, s, e->P);
+    else if (e->P.upref) GPIS_LAUNCH_SMEM(d.g_gemm_lists, e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s, e->P);
     else GPIS_LAUNCH_SMEM(d.g_gemm, e->P.gemm_ctas, GEMM_THREADS, GEMM_SMEM, s, e->P);
     if (mid) cudaEventRecord(mid, s);
     GPIS_LAUNCH_SMEM(d.g_epi, GEPI_CTAS_PER_TILE * e->grid_ctas, GEPI_THREADS, 0, s, e->P);
@@ -418,6 +427,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
     CU(cudaFuncSetAttribute((const void*)disp.update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->upd_smem));
     CU(cudaFuncSetAttribute((const void*)disp.predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PRED_SMEM));
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    CU(cudaFuncSetAttribute((const void*)disp.g_gemm_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     CU(cudaFuncSetAttribute((const void*)disp.g_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF32_SMEM));
     P.gemm_kc = cfg->precision == GPIS_PREC_TF32 ? TKC : GKC;
     P.gemm_zgroup = cfg->precision == GPIS_PREC_TF32 ? TZ : 1;
@@ -622,22 +632,34 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   // workspace slots per CTA
   const long long tiles_q = (long long)((P.glen[0] + QT - 1) / QT) * ((P.glen[1] + QT - 1) / QT) * P.glen[2];
   e->persist_grid_ok = e->persist && tiles_q <= QT_MAX && P.R_cap <= 65535;
+  // per-step path of the models the persistent kernel does not take (gradient observations, more than 4096 rows):
+  // row lists per 128 x 128 tile, one workspace slot per tile + one per CTA
+  e->step_lists = !e->onepass && e->cfg.precision == GPIS_PREC_FP64 && tiles <= GLIST_TMAX && P.R_cap <= 65535;
   {
     size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
+    if (e->step_lists) need = sizeof(double) * (size_t)e->NB * ((size_t)tiles + P.gemm_ctas) * GTILE_ELEMS;
     if (e->persist_grid_ok) need = std::max(need, sizeof(double) * (size_t)e->num_sms * 2 * QTILE_ELEMS);
     if (need > e->gws_bytes) {
       CU(dalloc(e, &P.gws, need / sizeof(double)));
       e->gws_bytes = need;
     }
   }
-  if (e->persist_grid_ok) {
+  P.upref = nullptr;
+  if (e->step_lists) {
+    if ((size_t)tiles + 1 > e->upref_cap) {
+      CU(dalloc(e, &e->d_upref, (size_t)tiles + 1));
+      e->upref_cap = (size_t)tiles + 1;
+    }
+    P.upref = e->d_upref;
+  }
+  if (e->persist_grid_ok || e->step_lists) {
     if ((size_t)tiles_q > e->tile_cnt_cap) {
       CU(dalloc(e, &P.tile_cnt, (size_t)tiles_q));
       CU(dalloc(e, &P.rcnt, (size_t)tiles_q));
       e->tile_cnt_cap = (size_t)tiles_q;
     }
     P.ldtt = e->rk_pad;
-    for (int d = 0; d < D; ++d) {
+    for (int d = 0; d < D && e->persist_grid_ok; ++d) {
       const size_t need = (size_t)P.gtlen[d] * (size_t)P.ldtt;
       if (need > e->tt_cap[d]) {
         CU(dalloc(e, &P.TT[d], need));
@@ -647,7 +669,7 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     P.rlist_stride = (P.R_cap + QKC - 1) / QKC * QKC;      // whole chunks, 64-byte aligned
     if ((size_t)tiles_q * P.rlist_stride > e->rlist_cap) {
       CU(dalloc(e, &P.rlist, (size_t)tiles_q * P.rlist_stride));
-      CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));
+      if (e->persist_grid_ok) CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));
       e->rlist_cap = (size_t)tiles_q * P.rlist_stride;
     }
   }

@@ -125,6 +125,7 @@ struct EngineParams {
   double* rtz;             // [tiles][rlist_stride] the rows' z-axis factor at the tile's slice
   int* rcnt;               // [tiles]
   int rlist_stride;
+  int* upref;              // per-step path with row lists: exclusive prefix of the 128 x 128 tiles' chunk counts [tiles + 1], else null
   unsigned long long* phase_clk;   // persistent selection kernel: CTA 0's phase times (globaltimer ns), [8]
   long long spin_cycles;   // SM clocks an in-kernel wait (peer record, grid barrier) may take before it gives up
   // model

@@ -898,11 +898,86 @@ __device__ __forceinline__ int unit_owner(long long u, long long U, int G) {
   return (int)(((u + 1) * G + U - 1) / U) - 1;
 }
 
-template <int NB>
+// exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2: a model row farther than that from every point of a
+// tile cannot change a double-precision sum over the tile (the dropped term is below 2^-70 |W|)
+constexpr double GRID_REACH_CUT = 48.52030263919617;
+constexpr int GLIST_TMAX = 2048;      // most 128 x 128 tiles per rank the list form of the per-step GEMM takes
+
+// Per-step path with ROW LISTS (models the persistent kernel does not take: gradient observations, more than 4096
+// rows): after the factor append, the NB rows of the new point join the list of every 128 x 128 tile they can reach
+// and the exclusive prefix of the tiles' 16-row chunk counts is rebuilt.  One CTA.
+template <int NB, int D>
+__global__ void __launch_bounds__(1024, 1) k_grid_lists(EngineParams P) {
+  const DevState* st = P.st;
+  if (st->done) return;
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int r0 = st->r0;
+  const int nx = P.glen[0], ny = P.glen[1];
+  const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT, txy = tiles_x * tiles_y;
+  const int T = txy * P.glen[2];
+  double p[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) p[d] = st->nx[d];
+  const int per = (T + 1023) / 1024;
+  int loc = 0;
+  for (int k = 0; k < per; ++k) {
+    const int t = tid * per + k;
+    if (t >= T) break;
+    const int tz = t / txy, ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+    double d2 = 0.0;
+    {
+      const double lo = P.gorg[0] + P.gh[0] * (double)(tx * GT), hi = P.gorg[0] + P.gh[0] * (double)(min(tx * GT + GT, nx) - 1);
+      const double a = fmin(lo, hi), b = fmax(lo, hi);
+      const double df = p[0] < a ? a - p[0] : (p[0] > b ? p[0] - b : 0.0);
+      d2 += df * df;
+    }
+    if (D > 1) {
+      const double q = p[D > 1 ? 1 : 0];
+      const double lo = P.gorg[1] + P.gh[1] * (double)(ty * GT), hi = P.gorg[1] + P.gh[1] * (double)(min(ty * GT + GT, ny) - 1);
+      const double a = fmin(lo, hi), b = fmax(lo, hi);
+      const double df = q < a ? a - q : (q > b ? q - b : 0.0);
+      d2 += df * df;
+    }
+    if (D > 2) {
+      const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - p[D > 2 ? 2 : 0];
+      d2 += df * df;
+    }
+    int n = P.rcnt[t];
+    if (0.5 * d2 * P.inv_ell2 <= GRID_REACH_CUT) {
+      for (int a = 0; a < NB; ++a) P.rlist[(size_t)t * P.rlist_stride + n + a] = (unsigned short)(r0 + a);
+      n += NB;
+      P.rcnt[t] = n;
+    }
+    const int c = (n + GKC - 1) / GKC;
+    loc += c > 0 ? c : 1;
+  }
+  // exclusive prefix over the tiles (thread tid owns tiles tid*per .. tid*per + per - 1)
+  s_part[tid] = loc;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - loc;
+  for (int k = 0; k < per; ++k) {
+    const int t = tid * per + k;
+    if (t >= T) break;
+    P.upref[t] = run;
+    const int c = (P.rcnt[t] + GKC - 1) / GKC;
+    run += c > 0 ? c : 1;
+  }
+  if (tid == 1023) P.upref[T] = s_part[1023];
+}
+
+template <int NB, bool LISTS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
   GPIS_DYN_SMEM_F64A(g_smem);
   const DevState* st = P.st;
   if (st->done) return;
+  __shared__ int s_upref[LISTS ? GLIST_TMAX + 1 : 1];
   unsigned long long* full = reinterpret_cast<unsigned long long*>(g_smem + (size_t)GPIPE * GSTAGE_DOUBLES);
   unsigned long long* empty = full + GPIPE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -916,11 +991,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
   const int T = tiles_x * tiles_y * P.glen[2];
   const int C = (r0 + NB + GKC - 1) / GKC;           // chunks per tile (all passes share the count)
-  const long long U = (long long)T * C;
+  if (LISTS) {       // per-tile chunk counts: their exclusive prefix (k_grid_lists) into shared memory
+    for (int i = tid; i <= T; i += GEMM_THREADS) s_upref[i] = P.upref[i];
+    __syncthreads();
+  }
+  const long long U = LISTS ? (long long)s_upref[T] : (long long)T * C;
   // fewer units than CTAs: only the first U CTAs work, so every working CTA's range is non-empty
   const int G = (int)min((long long)gridDim.x, U), g = blockIdx.x;
   if (g >= G) return;
   const long long u0 = (long long)g * U / G, u1 = (long long)(g + 1) * U / G;
+  int tile_first = 0;
+  if (LISTS) {       // last tile whose first unit is <= u0
+    int lo = 0, hi = T - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((long long)s_upref[mid] <= u0) lo = mid; else hi = mid - 1; }
+    tile_first = lo;
+  }
   int stage = 0;
   unsigned phase = 0;
 
@@ -929,17 +1014,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
     for (int a = 0; a < NB; ++a) {
       const double* wrow = P.W + (long long)(r0 + a) * P.ldW;
       const int klen = r0 + a + 1;
+      int ltile = tile_first;
       for (long long u = u0; u < u1; ++u) {
-        const int tile = (int)(u / C), c = (int)(u % C);
+        int tile, c;
+        if (LISTS) {
+          while ((long long)s_upref[ltile + 1] <= u) ++ltile;
+          tile = ltile;
+          c = (int)(u - s_upref[ltile]);
+        } else {
+          tile = (int)(u / C);
+          c = (int)(u % C);
+        }
         const int tz = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
         mbar_wait(&empty[stage], phase ^ 1);
         double* As = g_smem + (size_t)stage * GSTAGE_DOUBLES;
         double* Bs = As + GKC * GLD;
         double* cs = Bs + GKC * GLD;
         const long long rho0 = (long long)c * GKC;
+        long long rho = rho0 + (lane & (GKC - 1));      // LISTS: the chunk's row of the tile's list (row 0 past its end)
+        bool live = true;
+        if (LISTS) {
+          const int k = (int)rho;
+          live = k < P.rcnt[tile];
+          rho = live ? (long long)P.rlist[(size_t)tile * P.rlist_stride + k] : 0;
+        }
         if (lane < GKC) {
-          const long long rho = rho0 + lane;
-          double cv = rho < klen ? wrow[rho] : 0.0;
+          double cv = (live && rho < klen) ? wrow[rho] : 0.0;
           cv *= P.T[2][rho * P.ldt[2] + P.gz0 + tz];
           cs[lane] = cv;
         }
@@ -947,9 +1047,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
         if (lane == 0) mbar_arrive_expect_tx(&full[stage], 2 * GKC * GT * (unsigned)sizeof(double));
         __syncwarp();
         if (lane < GKC)
-          bulk_g2s(As + lane * GLD, P.T[1] + (rho0 + lane) * P.ldt[1] + ty * GT, GT * sizeof(double), &full[stage]);
+          bulk_g2s(As + lane * GLD, P.T[1] + rho * P.ldt[1] + ty * GT, GT * sizeof(double), &full[stage]);
         else
-          bulk_g2s(Bs + (lane - GKC) * GLD, P.T[0] + (rho0 + lane - GKC) * P.ldt[0] + tx * GT, GT * sizeof(double), &full[stage]);
+          bulk_g2s(Bs + (lane - GKC) * GLD, P.T[0] + rho * P.ldt[0] + tx * GT, GT * sizeof(double), &full[stage]);
         if (++stage == GPIPE) { stage = 0; phase ^= 1; }
       }
     }
@@ -960,9 +1060,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
   const int wm = warp >> 1, wn = warp & 1;
   for (int a = 0; a < NB; ++a) {
     long long u = u0;
+    int ltile = tile_first;
     while (u < u1) {
-      const int tile = (int)(u / C);
-      const long long uend = min(u1, (long long)(tile + 1) * C);
+      if (LISTS) while ((long long)s_upref[ltile + 1] <= u) ++ltile;
+      const int tile = LISTS ? ltile : (int)(u / C);
+      const long long uend = min(u1, LISTS ? (long long)s_upref[tile + 1] : (long long)(tile + 1) * C);
       double acc[4][8][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -992,8 +1094,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_grid_gemm(EngineParams P) {
         if (++stage == GPIPE) { stage = 0; phase ^= 1; }
       }
       // partial accumulators of this (tile, segment) -> workspace, fragment-native layout
-      const int seg = g - unit_owner((long long)tile * C, U, G);
-      double2* ws = reinterpret_cast<double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax + seg) * GTILE_ELEMS);
+      const int seg = g - unit_owner(LISTS ? (long long)s_upref[tile] : (long long)tile * C, U, G);
+      // LISTS: the first segment of a tile in the tile's slot, a later one (always the first tile of its CTA's range)
+      // in the CTA's slot -- no bound on the segments per tile is needed
+      double2* ws = reinterpret_cast<double2*>(
+          LISTS ? P.gws + (seg == 0 ? ((long long)a * T + tile) : ((long long)NB * T + (long long)a * gridDim.x + g)) * GTILE_ELEMS
+                : P.gws + (((long long)a * T + tile) * P.gws_segmax + seg) * GTILE_ELEMS);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1023,7 +1129,7 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   const int tiles_x = (nx + GT - 1) / GT, tiles_y = (ny + GT - 1) / GT;
   const int T = tiles_x * tiles_y * P.glen[2];
   const double NEG_INF = -__longlong_as_double(0x7ff0000000000000LL);
-  __shared__ int s_nseg;
+  __shared__ int s_nseg, s_gfirst;
   __shared__ double s_sb, s_gn[NB];
   if (tid == 0) {                       // CTA-uniform: split-K segment count of this tile, sqrt(beta_t)
     const int r0 = st->r0;
@@ -1033,8 +1139,15 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
     const int gtile = (tile / txy / zg) * txy + tile % txy;
     const long long U = (long long)txy * ((P.glen[2] + zg - 1) / zg) * C;
     const int G = (int)min((long long)P.gemm_ctas, U);
-    const int g_first = unit_owner((long long)gtile * C, U, G);
+    int g_first = unit_owner((long long)gtile * C, U, G);
     s_nseg = unit_owner((long long)(gtile + 1) * C - 1, U, G) - g_first + 1;
+    if (P.upref) {      // row lists: chunk counts differ per tile
+      const long long Ul = P.upref[T];
+      const int Gl = (int)min((long long)P.gemm_ctas, Ul);
+      g_first = unit_owner((long long)P.upref[tile], Ul, Gl);
+      s_nseg = unit_owner((long long)P.upref[tile + 1] - 1, Ul, Gl) - g_first + 1;
+    }
+    s_gfirst = g_first;
     double beta = P.beta;
     if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(st->iter + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
     else if (P.beta_mode == 2) { const double k1 = (double)(st->iter + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
@@ -1051,14 +1164,19 @@ __global__ void __launch_bounds__(GEPI_THREADS) k_grid_epilogue(EngineParams P) 
   for (int k = 0; k < GEPI_SPT; ++k) dv[k][0] = dv[k][1] = dm[k][0] = dm[k][1] = 0.0;
 #pragma unroll
   for (int a = 0; a < NB; ++a) {
-    const double2* ws = reinterpret_cast<const double2*>(P.gws + (((long long)a * T + tile) * P.gws_segmax) * GTILE_ELEMS) + q0;
+    const bool lists = P.upref != nullptr;
+    const double2* ws = reinterpret_cast<const double2*>(
+        P.gws + (lists ? ((long long)a * T + tile) : (((long long)a * T + tile) * P.gws_segmax)) * GTILE_ELEMS) + q0;
+    // row lists: segments after the first sit in the slots of the CTAs that computed them
+    const double2* wsx = reinterpret_cast<const double2*>(
+        P.gws + ((long long)NB * T + (long long)a * P.gemm_ctas + s_gfirst) * GTILE_ELEMS) + q0;
     double2 v[GEPI_SPT];
 #pragma unroll
     for (int k = 0; k < GEPI_SPT; ++k) v[k] = __ldcg(ws + k * GEPI_THREADS);
     for (int sgi = 1; sgi < nseg; ++sgi) {
       double2 pz[GEPI_SPT];
 #pragma unroll
-      for (int k = 0; k < GEPI_SPT; ++k) pz[k] = __ldcg(ws + (long long)sgi * (GTILE_ELEMS / 2) + k * GEPI_THREADS);
+      for (int k = 0; k < GEPI_SPT; ++k) pz[k] = __ldcg((lists ? wsx : ws) + (long long)sgi * (GTILE_ELEMS / 2) + k * GEPI_THREADS);
 #pragma unroll
       for (int k = 0; k < GEPI_SPT; ++k) { v[k].x += pz[k].x; v[k].y += pz[k].y; }
     }

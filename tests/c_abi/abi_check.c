@@ -18,13 +18,18 @@ typedef gpis_status (*gpis_select_t)(gpis_handle, int64_t, int32_t, void*);
 typedef gpis_status (*gpis_get_active_t)(gpis_handle, int64_t*, int32_t*, int32_t*, void*);
 typedef gpis_status (*gpis_get_candidate_posterior_t)(gpis_handle, double*, double*, void*);
 typedef const char* (*gpis_version_t)(void);
+typedef gpis_status (*gpis_set_grid_candidates_f32_t)(gpis_handle, const int32_t*, const double*, const double*, int32_t, int32_t,
+                                                      const float*, const float*, const float*, void*);
+typedef gpis_status (*gpis_get_active_f32_t)(gpis_handle, int32_t, float*, float*, int32_t*, int32_t*, void*);
+typedef gpis_status (*gpis_build_tsdf_t)(const uint8_t*, int32_t, int32_t, const gpis_tsdf_params*, const double*, double*, double*,
+                                         double*, int32_t*, int32_t*, int32_t, void*);
 
 int main(int argc, char** argv) {
   if (argc < 2) { printf("usage: abi_check <lib> [gpu]\n"); return 2; }
   void* lib = dlopen(argv[1], RTLD_NOW);
   if (!lib) { printf("dlopen failed: %s\n", dlerror()); return 2; }
   SYM(gpis_create) SYM(gpis_destroy) SYM(gpis_set_grid_candidates) SYM(gpis_select) SYM(gpis_get_active)
-  SYM(gpis_get_candidate_posterior) SYM(gpis_version)
+  SYM(gpis_get_candidate_posterior) SYM(gpis_version) SYM(gpis_set_grid_candidates_f32) SYM(gpis_get_active_f32) SYM(gpis_build_tsdf)
   printf("sizeof(gpis_config)=%zu version=%s\n", sizeof(gpis_config), p_gpis_version());
   enum { G = 10, N = G * G * G, K = 30 };
   gpis_config cfg;
@@ -61,6 +66,32 @@ int main(int argc, char** argv) {
   double vmin = 1e9, vmax = -1e9;
   for (int i = 0; i < N; ++i) { if (var[i] < vmin) vmin = var[i]; if (var[i] > vmax) vmax = var[i]; }
   printf("selected=%d in_model=%d first=%lld var=[%.4f, %.4f]\n", ns, nm, (long long)ids[0], vmin, vmax);
+  /* the reference's own fp32 signatures (gpu_active_set_selector.hpp:41-46): float TSDF in, float active set out */
+  static float tsdf32[N], ain[3 * K], atg[K];
+  for (int i = 0; i < N; ++i) tsdf32[i] = (float)tsdf[i];
+  if (p_gpis_set_grid_candidates_f32(h, dims, org, sp, 0, G, tsdf32, NULL, NULL, NULL) != GPIS_OK) return 1;
+  if (p_gpis_select(h, 123, K, NULL) != GPIS_OK) return 1;
+  int32_t ns32 = 0, nm32 = 0;
+  if (p_gpis_get_active_f32(h, K, ain, atg, &ns32, &nm32, NULL) != GPIS_OK) return 1;
+  int f32_ok = ns32 == K && nm32 == K - 1 && ain[0] == 3.0f && ain[K] == 2.0f && ain[2 * K] == 1.0f && atg[0] == tsdf32[123];
+  printf("f32: selected=%d in_model=%d first point=(%g, %g, %g) target=%g ok=%d\n", ns32, nm32, ain[0], ain[K], ain[2 * K], atg[0], f32_ok);
   p_gpis_destroy(h);
-  return (ns == K && nm == K - 1 && ids[0] == 123 && vmin > -1e-9 && vmax <= 1.0 + 1e-12) ? 0 : 1;
+  /* auto_tsdf.m:133-262 on a 12 x 9 image (rows x columns, column-major) holding a filled rectangle */
+  enum { R = 12, C = 9 };
+  static uint8_t inside[R * C];
+  static double t2[R * C], nrm2[2 * R * C], nz2[R * C];
+  static int32_t vidx[R * C];
+  for (int j = 0; j < C; ++j) for (int i = 0; i < R; ++i) inside[i + j * R] = (i >= 3 && i < 9 && j >= 2 && j < 7);
+  gpis_tsdf_params tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.struct_size = (int32_t)sizeof(tp);
+  tp.noise_scale = 0.05; tp.occlusion_scale = 1000.0; tp.interior_rate = 0.4; tp.horiz_scale = 1.0; tp.vert_scale = 1.0;
+  for (int k = 0; k < 3; ++k) { tp.occ_y_low[k] = R; tp.occ_x_low[k] = C; }      /* no occlusion window */
+  int32_t nvalid = 0;
+  st = p_gpis_build_tsdf(inside, R, C, &tp, NULL, t2, nrm2, nz2, vidx, &nvalid, -1, NULL);
+  /* centre of the rectangle is two pixels from the border: -1; its border pixels: 0; the image corner: +1 */
+  int tsdf_ok = st == GPIS_OK && t2[5 + 4 * R] == -1.0 && t2[3 + 2 * R] == 0.0 && t2[0] == 1.0 && t2[2 + 2 * R] == 0.5 &&
+                nrm2[2 + 4 * R] == 0.0 && nvalid > 0 && nvalid <= R * C && nz2[0] == 0.05;
+  printf("tsdf: status=%d valid=%d centre=%g border=%g corner=%g ok=%d\n", st, nvalid, t2[5 + 4 * R], t2[3 + 2 * R], t2[0], tsdf_ok);
+  return (ns == K && nm == K - 1 && ids[0] == 123 && vmin > -1e-9 && vmax <= 1.0 + 1e-12 && f32_ok && tsdf_ok) ? 0 : 1;
 }

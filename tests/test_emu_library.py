@@ -96,6 +96,26 @@ def test_grid_backend_gradients_2d_through_the_emulated_library(G):
     assert np.max(np.abs(pred["normals"] - fn[test])) < 1e-10
 
 
+def test_grid_backend_gradients_3d_row_lists_prune_through_the_emulated_library(G):
+    """3-D lattice with normal observations and a length scale much shorter than the z extent: the per-step path's
+    ROW LISTS (k_grid_lists + the list form of k_grid_gemm) leave out the model rows farther than 9.85 ell from a
+    slice -- the posterior still equals the oracle's dense sums."""
+    dims = (5, 4, 26)
+    pts, tsdf, nrm = blob(dims, 4, with_normals=True)
+    hyp = {"cov": np.array([np.log(0.7), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.02)}
+    tr = dict(TRAIN, activeSetSize=9)
+    shape = {"points": pts, "tsdf": tsdf, "normals": nrm, "noise": None}
+    ora = O.select_straddle_incremental(shape, tr, 11, hyp=hyp, prune=False)
+    mdl, pred, test = G.select_active_set(shape, tr, first_index=11, hyp=hyp, backend="grid")
+    assert np.array_equal(mdl["order"], ora["order"]) and mdl["n_in_model"] == ora["n_in_model"]
+    zs = pts[mdl["order"][:mdl["n_in_model"]], 2]
+    assert zs.max() - zs.min() > 2 * 9.85 * 0.7           # some rows are out of reach of some slices
+    mu, var = mdl.engine.candidate_posterior()
+    fm, fv, fn = O.predict_points(ora["gp"], pts, want_normals=True)
+    assert np.max(np.abs(mu - fm)) < 1e-10 and np.max(np.abs(var - fv)) < 1e-10
+    assert np.array_equal(pred["high"], ora["high"]) and np.array_equal(pred["low"], ora["low"])
+
+
 def test_dense_fit_predict_and_sampling_through_the_emulated_library(G):
     """create_gpis (the append kernel fed by gpis_fit), gp_mean / gp_cov / predict kernels, the full posterior
     covariance and the draws, on a third of the reference's stored loofa model against its stored predGrid
