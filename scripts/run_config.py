@@ -36,7 +36,7 @@ if a.shape == "sphere":
 else:
     tsdf, nrm = box_tsdf(g)[1], None
 N = g ** 3
-z0, z1 = gdist.slab_range(g, rank, world)
+z0, z1 = gdist.slab_range_balanced(g, rank, world, a.ell)
 lo, hi = g * g * z0, g * g * z1
 eng = GpisEngine(3, hi - lo, a.active, ell=a.ell, noise=0.05, level=0.0, eps=1e-2, beta=10.0,
                  use_gradients=a.gradients, rank=rank, world_size=world, total_candidates=N, id_base=lo, device=lr)
