@@ -221,6 +221,10 @@ gpis_status launch_append(gpis_engine* e, cudaStream_t s, int external, int fina
           GPIS_LAUNCH_SMEM(k_grid_wrow1, e->num_sms, GSOLVE_THREADS, 0, s, e->P, e->solve1_ctas);
           e->launches += 2;
         }
+        if (e->P.upref) {      // the new point's row joins the tiles' row lists; unit prefix of the update GEMM
+          GPIS_LAUNCH_SMEM(d.g_lists, 1, 1024, 0, s, e->P);
+          e->launches += 1;
+        }
         CU(cudaGetLastError());
         return GPIS_OK;
       }
@@ -632,9 +636,9 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   // workspace slots per CTA
   const long long tiles_q = (long long)((P.glen[0] + QT - 1) / QT) * ((P.glen[1] + QT - 1) / QT) * P.glen[2];
   e->persist_grid_ok = e->persist && tiles_q <= QT_MAX && P.R_cap <= 65535;
-  // per-step path of the models the persistent kernel does not take (gradient observations, more than 4096 rows):
-  // row lists per 128 x 128 tile, one workspace slot per tile + one per CTA
-  e->step_lists = !e->onepass && e->cfg.precision == GPIS_PREC_FP64 && tiles <= GLIST_TMAX && P.R_cap <= 65535;
+  // per-step fp64 path (the models the persistent kernel does not take -- gradient observations, more than 4096 rows --
+  // and loop_mode = GPIS_LOOP_STEPS): row lists per 128 x 128 tile, one workspace slot per tile + one per CTA
+  e->step_lists = e->cfg.precision == GPIS_PREC_FP64 && tiles <= GLIST_TMAX && P.R_cap <= 65535;
   {
     size_t need = sizeof(double) * (size_t)e->NB * tiles * P.gws_segmax * GTILE_ELEMS;
     if (e->step_lists) need = sizeof(double) * (size_t)e->NB * ((size_t)tiles + P.gemm_ctas) * GTILE_ELEMS;
