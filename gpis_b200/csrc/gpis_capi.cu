@@ -26,7 +26,7 @@ template <int NB>
 void k_grid_gemm_tf32(EngineParams) {}
 constexpr size_t PERSIST_SMEM = 0;      // in-kernel grid barriers are not emulated either: the per-step path runs
 constexpr int PTHREADS = 32, PLL_WORLD_MAX = 16;
-template <int D>
+template <int D, bool CUBE>
 void k_grid_persist(EngineParams, int) {}
 }  // namespace gpis
 #endif
@@ -62,8 +62,9 @@ struct gpis_engine {
   bool persist = false;            // gpis_select runs the whole greedy loop in one cooperative kernel
   bool self_peer = false;          // world_size 1: the exchange region is this engine's own (flags release the CTAs)
   unsigned long long* d_phase_clk = nullptr;
-  size_t tile_cnt_cap = 0, rlist_cap = 0, tt_cap[MAXD] = {0, 0, 0}, upref_cap = 0;
+  size_t tile_cnt_cap = 0, rlist_cap = 0, tt_cap[MAXD] = {0, 0, 0}, upref_cap = 0, rtz_cap = 0;
   int* d_upref = nullptr;
+  bool persist_cube = false;       // persistent kernel on 16 x 16 x 16 tiles (3-D lattices)
   bool step_lists = false;         // per-step path sums per-tile row lists (gradient / large fp64 models on a lattice)
   bool persist_grid_ok = false;    // the lattice of the last gpis_set_grid_candidates fits the persistent kernel
   double persist_ms[16] = {0};     // CTA 0's lap times of the last persistent selection (PCLK_* slots), ms
@@ -183,12 +184,19 @@ struct Dispatch {
   void (*g_gemm_tf32)(EngineParams);
   void (*g_epi)(EngineParams);
   void (*g_persist)(EngineParams, int);
+  void (*g_persist_cube)(EngineParams, int);
 };
+
+template <int D, bool CUBE>
+auto persist_kernel() -> void (*)(EngineParams, int) {
+  if constexpr (!CUBE || D == 3) return k_grid_persist<D, CUBE>;
+  else return nullptr;
+}
 
 template <int NB, int D>
 Dispatch make_dispatch() {
   return Dispatch{k_append<NB, D>, k_update<NB, D>, k_predict_f64<NB, D>,
-                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB, false>, k_grid_gemm<NB, true>, k_grid_lists<NB, D>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>, k_grid_persist<D>};
+                  k_grid_point<NB, D>, k_grid_solve<NB, D, false>, k_grid_solve<NB, D, true>, k_grid_solve1<D>, k_grid_solve2<D>, k_grid_wrow<NB>, k_grid_gemm<NB, false>, k_grid_gemm<NB, true>, k_grid_lists<NB, D>, k_grid_gemm_tf32<NB>, k_grid_epilogue<NB>, persist_kernel<D, false>(), persist_kernel<D, true>()};
 }
 
 Dispatch get_dispatch(int D, bool grad) {
@@ -459,11 +467,15 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
                               (int)(sizeof(double) * GS1_RMAX)));
 #ifndef GPIS_EMULATE
       CU(cudaFuncSetAttribute((const void*)disp.g_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSIST_SMEM));
+      if (disp.g_persist_cube)
+        CU(cudaFuncSetAttribute((const void*)disp.g_persist_cube, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PERSIST_SMEM));
       // kernels with in-kernel grid barriers need every CTA resident: one per SM, or not at all
       int occ2 = 0, occp = 0;
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, (const void*)disp.g_solve2, GSOLVE_THREADS, GS2_SMEM));
       CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, (const void*)disp.g_persist, PTHREADS, PERSIST_SMEM));
       if (!coop || occ2 < 1) e->solve_ring = false;
+      if (disp.g_persist_cube && occp >= 1)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occp, (const void*)disp.g_persist_cube, PTHREADS, PERSIST_SMEM));
       if (!coop || occp < 1) e->persist = false;
 #endif
       e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
@@ -614,6 +626,9 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   }
   // per-candidate state in tile/fragment order (padded to whole tiles)
   e->grid_slots = (size_t)tiles * GTILE_ELEMS;
+  if (D == 3)      // the persistent kernel's 16 x 16 x 16 cube layout pads the z axis too
+    e->grid_slots = std::max(e->grid_slots, (size_t)((P.glen[0] + QC - 1) / QC) * ((P.glen[1] + QC - 1) / QC) *
+                                                ((P.glen[2] + QC - 1) / QC) * QTILE_ELEMS);
   if (e->grid_slots > e->state_cap) {
     CU(dalloc(e, &P.mu, e->grid_slots));
     CU(dalloc(e, &P.var, e->grid_slots));
@@ -634,7 +649,12 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
   }
   // persistent selection kernel: 64 x 64 lattice tiles, a row list and a split-K counter per tile, two
   // workspace slots per CTA
-  const long long tiles_q = (long long)((P.glen[0] + QT - 1) / QT) * ((P.glen[1] + QT - 1) / QT) * P.glen[2];
+  // (3-D lattices: 16 x 16 x 16 cubes, unless the slab is so thin that padding its z axis to whole cubes wastes more
+  // than the shorter row lists save)
+  e->persist_cube = D == 3 && 3 * (((long long)P.glen[2] + QC - 1) / QC * QC) <= 4 * (long long)P.glen[2];
+  const long long tiles_q = e->persist_cube
+      ? (long long)((P.glen[0] + QC - 1) / QC) * ((P.glen[1] + QC - 1) / QC) * ((P.glen[2] + QC - 1) / QC)
+      : (long long)((P.glen[0] + QT - 1) / QT) * ((P.glen[1] + QT - 1) / QT) * P.glen[2];
   e->persist_grid_ok = e->persist && tiles_q <= QT_MAX && P.R_cap <= 65535;
   // per-step fp64 path (the models the persistent kernel does not take -- gradient observations, more than 4096 rows --
   // and loop_mode = GPIS_LOOP_STEPS): row lists per 128 x 128 tile, one workspace slot per tile + one per CTA
@@ -657,10 +677,12 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
     P.upref = e->d_upref;
   }
   if (e->persist_grid_ok || e->step_lists) {
-    if ((size_t)tiles_q > e->tile_cnt_cap) {
-      CU(dalloc(e, &P.tile_cnt, (size_t)tiles_q));
-      CU(dalloc(e, &P.rcnt, (size_t)tiles_q));
-      e->tile_cnt_cap = (size_t)tiles_q;
+    // (the per-step row-list path keeps its lists of 128 x 128 tiles in the same arrays)
+    const size_t list_tiles = (size_t)std::max<long long>(e->persist_grid_ok ? tiles_q : 0, e->step_lists ? tiles : 0);
+    if (list_tiles > e->tile_cnt_cap) {
+      CU(dalloc(e, &P.tile_cnt, list_tiles));
+      CU(dalloc(e, &P.rcnt, list_tiles));
+      e->tile_cnt_cap = list_tiles;
     }
     P.ldtt = e->rk_pad;
     for (int d = 0; d < D && e->persist_grid_ok; ++d) {
@@ -671,10 +693,13 @@ gpis_status gpis_set_grid_candidates(gpis_handle e, const int32_t* dims, const d
       }
     }
     P.rlist_stride = (P.R_cap + QKC - 1) / QKC * QKC;      // whole chunks, 64-byte aligned
-    if ((size_t)tiles_q * P.rlist_stride > e->rlist_cap) {
-      CU(dalloc(e, &P.rlist, (size_t)tiles_q * P.rlist_stride));
-      if (e->persist_grid_ok) CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));
-      e->rlist_cap = (size_t)tiles_q * P.rlist_stride;
+    if (list_tiles * P.rlist_stride > e->rlist_cap) {
+      CU(dalloc(e, &P.rlist, list_tiles * P.rlist_stride));
+      e->rlist_cap = list_tiles * P.rlist_stride;
+    }
+    if (e->persist_grid_ok && !e->persist_cube && (size_t)tiles_q * P.rlist_stride > e->rtz_cap) {
+      CU(dalloc(e, &P.rtz, (size_t)tiles_q * P.rlist_stride));
+      e->rtz_cap = (size_t)tiles_q * P.rlist_stride;
     }
   }
   P.tile_e = GT;
@@ -850,7 +875,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
   // one persistent cooperative kernel for the whole greedy loop (lattice candidates, function values, fp64)
   const bool persist = e->persist && e->backend == 2 && e->persist_grid_ok && !e->profiling && e->P.peer_mode && e->P.tile_cnt &&
                        e->P.world <= PLL_WORLD_MAX;
-  gpis_status rc = select_begin_impl(e, first_local, stream, persist ? QT : GT);
+  gpis_status rc = select_begin_impl(e, first_local, stream, persist ? (e->persist_cube ? QC : QT) : GT);
   if (rc != GPIS_OK) return rc;
   const int iters = K - 1;
   bool persist_ran = persist;
@@ -859,7 +884,7 @@ gpis_status gpis_select(gpis_handle e, int64_t first_local, int32_t K, void* str
     Dispatch d = get_dispatch(e->D, false);
     int it_arg = iters;
     void* args[] = {(void*)&e->P, (void*)&it_arg};
-    const cudaError_t ce = launch_cooperative(d.g_persist, (unsigned)e->num_sms, PTHREADS, PERSIST_SMEM, s, args);
+    const cudaError_t ce = launch_cooperative(e->persist_cube ? d.g_persist_cube : d.g_persist, (unsigned)e->num_sms, PTHREADS, PERSIST_SMEM, s, args);
     if (ce == cudaSuccess) {
       e->launches += 1;
     } else if (e->P.world == 1) {

@@ -33,7 +33,7 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 #endif
 // Internal layout of the per-candidate state (mu, var, ambiguity, flags) in the grid backend:
 // tile-major, and inside a TE x TE tile (TE = P.tile_e: 128 for the per-step kernels, 64 for the persistent
-// selection kernel) the order of the update GEMM's accumulator fragments -- 8 warps as 4 (jy) x 2 (jx), each
+// selection kernel on 1-D / 2-D lattices; 16 = its 16 x 16 x 16 cubes on 3-D lattices, below) the order of the update GEMM's accumulator fragments -- 8 warps as 4 (jy) x 2 (jx), each
 // warp tile (TE/4) x (TE/2) in 8 x 8 DMMA blocks -- so that the epilogue streams it with fully coalesced
 // 16-byte accesses.
 __host__ __device__ inline int grid_tile_edge(const EngineParams& P) { return P.tile_e > 0 ? P.tile_e : GT; }
@@ -47,8 +47,31 @@ __host__ __device__ inline long long grid_slot_te(const EngineParams& P, int jx,
   const int frag = ((gwarp * NI + (my % WY) / 8) * NJ + (mx % WX) / 8) * 32 + (my % 8) * 4 + (mx % 8) / 2;
   return tile * (TE * TE) + frag * 2 + (mx & 1);
 }
+// tile_e == 16: the persistent kernel's 16 x 16 x 16 cubes of a 3-D lattice.  Warp w of the update GEMM holds the
+// z-slices 2w, 2w + 1 of a cube as 4 x 2 DMMA blocks: fragment ((w * 4 + i) * 2 + j) * 32 + lane with
+// i = (jz & 1) * 2 + (jy >> 3), j = jx >> 3 (gpis_grid_persist.cuh: persist_pair_index<true>)
+constexpr int GCUBE = 16;
+__host__ __device__ inline long long grid_slot_cube(const EngineParams& P, int jx, int jy, int jz) {
+  const int tiles_x = (P.glen[0] + GCUBE - 1) / GCUBE, tiles_y = (P.glen[1] + GCUBE - 1) / GCUBE;
+  const long long tile = ((long long)(jz / GCUBE) * tiles_y + jy / GCUBE) * tiles_x + jx / GCUBE;
+  const int mz = jz % GCUBE, my = jy % GCUBE, mx = jx % GCUBE;
+  const int frag = (((mz >> 1) * 4 + (mz & 1) * 2 + (my >> 3)) * 2 + (mx >> 3)) * 32 + (my & 7) * 4 + (mx & 7) / 2;
+  return tile * (GCUBE * GCUBE * GCUBE) + frag * 2 + (mx & 1);
+}
+__host__ __device__ inline bool grid_unslot_cube(const EngineParams& P, long long slot, int& jx, int& jy, int& jz) {
+  const int tiles_x = (P.glen[0] + GCUBE - 1) / GCUBE, tiles_y = (P.glen[1] + GCUBE - 1) / GCUBE;
+  const long long tile = slot / (GCUBE * GCUBE * GCUBE);
+  const int w = (int)(slot % (GCUBE * GCUBE * GCUBE));
+  const int e = w & 1, frag = w >> 1;
+  const int lane = frag & 31, j = (frag >> 5) & 1, i = (frag >> 6) & 3, gwarp = frag >> 8;
+  jz = (int)(tile / (tiles_x * tiles_y)) * GCUBE + 2 * gwarp + (i >> 1);
+  jy = (int)((tile / tiles_x) % tiles_y) * GCUBE + (i & 1) * 8 + (lane >> 2);
+  jx = (int)(tile % tiles_x) * GCUBE + j * 8 + (lane & 3) * 2 + e;
+  return jx < P.glen[0] && jy < P.glen[1] && jz < P.glen[2];
+}
 __host__ __device__ inline long long grid_slot(const EngineParams& P, int jx, int jy, int tz) {
-  return grid_tile_edge(P) == 64 ? grid_slot_te<64>(P, jx, jy, tz) : grid_slot_te<GT>(P, jx, jy, tz);
+  const int te = grid_tile_edge(P);
+  return te == GCUBE ? grid_slot_cube(P, jx, jy, tz) : te == 64 ? grid_slot_te<64>(P, jx, jy, tz) : grid_slot_te<GT>(P, jx, jy, tz);
 }
 __host__ __device__ inline long long grid_slot_of_local(const EngineParams& P, long long jl) {
   const int nx = P.glen[0], ny = P.glen[1];
@@ -72,11 +95,15 @@ __host__ __device__ inline bool grid_unslot_te(const EngineParams& P, long long 
   return jx < P.glen[0] && jy < P.glen[1];
 }
 __host__ __device__ inline bool grid_unslot(const EngineParams& P, long long slot, int& jx, int& jy, int& tz) {
-  return grid_tile_edge(P) == 64 ? grid_unslot_te<64>(P, slot, jx, jy, tz) : grid_unslot_te<GT>(P, slot, jx, jy, tz);
+  const int te = grid_tile_edge(P);
+  return te == GCUBE ? grid_unslot_cube(P, slot, jx, jy, tz)
+                     : te == 64 ? grid_unslot_te<64>(P, slot, jx, jy, tz) : grid_unslot_te<GT>(P, slot, jx, jy, tz);
 }
 // slots of the whole (tile-padded) lattice in the layout of this selection
 __host__ __device__ inline long long grid_slot_count(const EngineParams& P) {
   const int TE = grid_tile_edge(P);
+  if (TE == GCUBE)
+    return (long long)((P.glen[0] + TE - 1) / TE) * ((P.glen[1] + TE - 1) / TE) * ((P.glen[2] + TE - 1) / TE) * TE * TE * TE;
   return (long long)((P.glen[0] + TE - 1) / TE) * ((P.glen[1] + TE - 1) / TE) * P.glen[2] * TE * TE;
 }
 

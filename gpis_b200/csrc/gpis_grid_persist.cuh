@@ -45,7 +45,16 @@ constexpr int QKC = 32;                                 // model rows per pipeli
 constexpr int QLD = QT + 4;                             // padded smem row (conflict-free DMMA fragment loads)
 constexpr int QSTAGE_DOUBLES = 2 * QKC * QLD;           // Ty rows, Tx rows
 constexpr int QPIPE = 4;
+// 3-D lattices: 16 x 16 x 16 tiles (same 4096 points, same accumulator fragments).  A model row reaches far fewer
+// cubes than 64 x 64 x 1 slabs (config 3: 15.0 % of the dense (tile, row) pairs instead of 27.6 %), the contraction is
+// [(jz, jy) = 256 x rows] x [rows x (jx) = 16] with A = (W[r,rho] Tz[rho][jz]) Ty[rho][jy] formed in registers.
+constexpr int QC = 16;                                  // cube edge
+constexpr int QLDC = QC + 4;                            // padded smem row of a cube stage (conflict-free fragment loads)
+constexpr int QSTAGE_CUBE = 3 * QKC * QLDC;             // Ty rows, Tx rows, Tz rows (18 doubles copied: even-aligned start)
+constexpr int QPIPE_CUBE = 8;
+constexpr int QPIPE_MAX = 8;
 constexpr int QTILE_ELEMS = QT * QT;
+static_assert(QC * QC * QC == QT * QT, "both tile shapes hold the same number of lattice points");
 constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment slots (x-adjacent pairs) per tile
 constexpr int QT_MAX = 2048;                            // most tiles per rank the kernel takes (prefix table in smem)
 // exp(-d^2 / (2 ell^2)) < 2^-70  <=>  d^2 / (2 ell^2) > 70 ln 2
@@ -71,8 +80,9 @@ constexpr int PCW = GEMM_CWARPS * 32;                   // 256 compute threads (
 constexpr int QPROD = 4;
 constexpr int PTHREADS = (GEMM_CWARPS + QPROD) * 32;
 constexpr size_t PERSIST_SMEM =
-    sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * QPIPE);
+    sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * QPIPE_MAX);
 static_assert((size_t)QPIPE * QSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
+static_assert((size_t)QPIPE_CUBE * QSTAGE_CUBE <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
 static_assert(QBLK * QKC <= GS1_RMAX, "the coefficients of a block alias the covariance vector");
 static_assert(QKC == 32, "a producer warp issues one Ty row and one Tx row per lane");
@@ -182,22 +192,34 @@ __device__ __forceinline__ void persist_pair(const EngineParams& P, long long sl
 }
 
 // lattice index of the first point of fragment slot q (0 .. QPAIRS-1) of the tile at (tx, ty, tz)
+template <bool CUBE>
 __device__ __forceinline__ long long persist_pair_index(int q, int tx, int ty, int tz, int nx, int ny) {
+  if (CUBE) {      // warp w holds z-slices 2w, 2w + 1 of the cube: fragment f = i * 2 + j, i = (jz & 1) * 2 + (jy >> 3), j = jx >> 3
+    const int l = q & 31, j = (q >> 5) & 1, i = (q >> 6) & 3, w = q >> 8;
+    const int jz = tz * QC + 2 * w + (i >> 1);
+    const int jy = ty * QC + (i & 1) * 8 + (l >> 2);
+    const int jx = tx * QC + j * 8 + (l & 3) * 2;
+    return (long long)jx + (long long)nx * (jy + (long long)ny * jz);
+  }
   const int l = q & 31, j = (q >> 5) & 3, i = (q >> 7) & 1, w = q >> 8;
   const int jy = ty * QT + (w >> 1) * 16 + i * 8 + (l >> 2);
   const int jx = tx * QT + (w & 1) * 32 + j * 8 + (l & 3) * 2;
   return (long long)jx + (long long)nx * (jy + (long long)ny * tz);
 }
 
-template <int D>
+template <int D, bool CUBE>
 __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, int iters) {
+  static_assert(!CUBE || D == 3, "cube tiles are for 3-D lattices");
+  constexpr int NPIPE = CUBE ? QPIPE_CUBE : QPIPE;
+  constexpr int TE = CUBE ? QC : QT;                      // tile edge along x and y
+  constexpr int STAGE = CUBE ? QSTAGE_CUBE : QSTAGE_DOUBLES;
   GPIS_DYN_SMEM_F64A(p_smem);
   double* s_kv = p_smem;                                  // [GS1_RMAX] covariance of the winner with the model rows
   double* ring = p_smem + GS1_RMAX;                       // phase B: rows of W; phase D: GEMM stages
   unsigned long long* rfull = reinterpret_cast<unsigned long long*>(ring + PRING_DOUBLES);
   unsigned long long* rempty = rfull + PRING_SLOTS_MAX;
   unsigned long long* gfull = rempty + PRING_SLOTS_MAX;
-  unsigned long long* gempty = gfull + QPIPE;
+  unsigned long long* gempty = gfull + QPIPE_MAX;
   __shared__ double s_red[2][PB][GEMM_CWARPS];
   __shared__ double s_rec[PAY_HDR];
   __shared__ double s_gram[PTHREADS / 32][2];
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   if (*(volatile int*)&st->r != 0 || *(volatile int*)&st->m != 0 || *(volatile int*)&st->iter != 0) return;
   for (int i = tid; i < GS1_RMAX; i += PTHREADS) s_kv[i] = 0.0;
   if (tid == 0) {
-    for (int i = 0; i < QPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
+    for (int i = 0; i < NPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
     for (int i = 0; i < PRING_SLOTS_MAX; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS); }
     mbar_init_fence();
     s_next.score = NEG_INF; s_next.id = 0x7fffffffffffffffLL; s_next.local = -1;
@@ -231,8 +253,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   __syncthreads();
 
   const int nx = P.glen[0], ny = P.glen[1];
-  const int tiles_x = (nx + QT - 1) / QT, tiles_y = (ny + QT - 1) / QT, txy = tiles_x * tiles_y;
-  const int T = txy * P.glen[2];
+  const int tiles_x = (nx + TE - 1) / TE, tiles_y = (ny + TE - 1) / TE, txy = tiles_x * tiles_y;
+  const int T = txy * (CUBE ? (P.glen[2] + QC - 1) / QC : P.glen[2]);
+  const int zodd = CUBE ? (P.gz0 & 1) : 0;                // the Tz rows are copied from the even index below the cube's first slice
   if (tid < PCLK_N) s_clk[tid] = 0;
   if (tid == 0) s_tk[0] = gtimer_ns();
   unsigned long long d_ns = 0, dwait_ns = 0, dt0 = 0;      // thread 0 of every CTA: its time in phase D / waiting for a filled stage
@@ -380,32 +403,43 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const int tz = t / txy, ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
           double d2 = 0.0;
           {
-            const double lo = P.gorg[0] + P.gh[0] * (double)(tx * QT), hi = P.gorg[0] + P.gh[0] * (double)(min(tx * QT + QT, nx) - 1);
+            const double lo = P.gorg[0] + P.gh[0] * (double)(tx * TE), hi = P.gorg[0] + P.gh[0] * (double)(min(tx * TE + TE, nx) - 1);
             const double a = fmin(lo, hi), b = fmax(lo, hi);
             const double df = nxp[0] < a ? a - nxp[0] : (nxp[0] > b ? nxp[0] - b : 0.0);
             d2 += df * df;
           }
           if (D > 1) {
             const double p1 = nxp[D > 1 ? 1 : 0];
-            const double lo = P.gorg[1] + P.gh[1] * (double)(ty * QT), hi = P.gorg[1] + P.gh[1] * (double)(min(ty * QT + QT, ny) - 1);
+            const double lo = P.gorg[1] + P.gh[1] * (double)(ty * TE), hi = P.gorg[1] + P.gh[1] * (double)(min(ty * TE + TE, ny) - 1);
             const double a = fmin(lo, hi), b = fmax(lo, hi);
             const double df = p1 < a ? a - p1 : (p1 > b ? p1 - b : 0.0);
             d2 += df * df;
           }
           if (D > 2) {
-            const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - nxp[D > 2 ? 2 : 0];
-            d2 += df * df;
+            const double p2 = nxp[D > 2 ? 2 : 0];
+            if (CUBE) {
+              const double lo = P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz * QC),
+                           hi = P.gorg[2] + P.gh[2] * (double)(P.gz0 + min(tz * QC + QC, P.glen[2]) - 1);
+              const double a = fmin(lo, hi), b = fmax(lo, hi);
+              const double df = p2 < a ? a - p2 : (p2 > b ? p2 - b : 0.0);
+              d2 += df * df;
+            } else {
+              const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - p2;
+              d2 += df * df;
+            }
           }
           if (0.5 * d2 * P.inv_ell2 <= QCUT) {
             const int n = __ldcg(P.rcnt + t);
             P.rlist[(size_t)t * P.rlist_stride + n] = (unsigned short)r0;
-            // the row's z-axis factor at this tile's slice (what the axis-2 table holds for it)
-            double tzf = 1.0;
-            if (D > 2) {
-              const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - nxp[D > 2 ? 2 : 0];
-              tzf = exp(-0.5 * df * df * P.inv_ell2);
+            if (!CUBE) {
+              // the row's z-axis factor at this tile's slice (what the axis-2 table holds for it)
+              double tzf = 1.0;
+              if (D > 2) {
+                const double df = (P.gorg[2] + P.gh[2] * (double)(P.gz0 + tz)) - nxp[D > 2 ? 2 : 0];
+                tzf = exp(-0.5 * df * df * P.inv_ell2);
+              }
+              P.rtz[(size_t)t * P.rlist_stride + n] = tzf;
             }
-            P.rtz[(size_t)t * P.rlist_stride + n] = tzf;
             __stcg(P.rcnt + t, n + 1);
           }
           P.tile_cnt[t] = 0u;
@@ -694,10 +728,15 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const uint4 r4 = __ldcg(rl4 + k);
           rw[4 * k] = r4.x; rw[4 * k + 1] = r4.y; rw[4 * k + 2] = r4.z; rw[4 * k + 3] = r4.w;
         }
-        const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
         double tv[QKC];
+        if (CUBE) {      // the z factors come from the axis-2 table with the stage
 #pragma unroll
-        for (int k = 0; k < QKC; k += 2) { const double2 z2 = __ldcg(tz2 + (k >> 1)); tv[k] = z2.x; tv[k + 1] = z2.y; }
+          for (int k = 0; k < QKC; ++k) tv[k] = 1.0;
+        } else {
+          const double2* tz2 = reinterpret_cast<const double2*>(P.rtz + (size_t)t * P.rlist_stride + c * QKC);
+#pragma unroll
+          for (int k = 0; k < QKC; k += 2) { const double2 z2 = __ldcg(tz2 + (k >> 1)); tv[k] = z2.x; tv[k + 1] = z2.y; }
+        }
 #pragma unroll
         for (int k = 0; k < QKC; ++k) {
           const bool live = c * QKC + k < cnt;
@@ -705,7 +744,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           s_rho[k * QBLK + ul] = (unsigned short)(live ? rr : 0);      // [k][unit]: conflict-free stores
           s_cs[k * QBLK + ul] = live ? tv[k] : 0.0;
         }
-        s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
+        if (CUBE) s_uoff[ul] = (t % tiles_x) | ((t / tiles_x) % tiles_y) << 10 | (t / txy) << 20;      // tile indices
+        else s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
       }
     };
     auto stage_part_b = [&](int bn) {
@@ -723,16 +763,27 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     // running unit count)
     auto issue_unit = [&](int b0, int ul) {
       const unsigned q = gcount + (unsigned)(b0 + ul);
-      const int stage = (int)(q % QPIPE);
-      mbar_wait(&gempty[stage], ((q / QPIPE) & 1u) ^ 1u);
-      double* As = ring + (size_t)stage * QSTAGE_DOUBLES;
-      double* Bs = As + QKC * QLD;
+      const int stage = (int)(q % NPIPE);
+      mbar_wait(&gempty[stage], ((q / NPIPE) & 1u) ^ 1u);
+      double* As = ring + (size_t)stage * STAGE;
       const int rho = (int)s_rho[lane * QBLK + ul];
       const int uo = s_uoff[ul];
-      if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
-      __syncwarp();
-      bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
-      bulk_g2s(Bs + lane * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+      if (CUBE) {
+        double* Bs = As + QKC * QLDC;
+        double* Zs = Bs + QKC * QLDC;
+        if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], QKC * (2 * QC + QC + 2) * (unsigned)sizeof(double));
+        __syncwarp();
+        bulk_g2s(As + lane * QLDC, P.T[1] + (long long)rho * P.ldt[1] + ((uo >> 10) & 1023) * QC, QC * sizeof(double), &gfull[stage]);
+        bulk_g2s(Bs + lane * QLDC, P.T[0] + (long long)rho * P.ldt[0] + (uo & 1023) * QC, QC * sizeof(double), &gfull[stage]);
+        bulk_g2s(Zs + lane * QLDC, P.T[D > 2 ? 2 : 0] + (long long)rho * P.ldt[D > 2 ? 2 : 0] + ((P.gz0 + (uo >> 20) * QC) & ~1),
+                 (QC + 2) * sizeof(double), &gfull[stage]);
+      } else {
+        double* Bs = As + QKC * QLD;
+        if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
+        __syncwarp();
+        bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
+        bulk_g2s(Bs + lane * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
+      }
     };
     if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
     PSTAMP(PCLK_FINISH);
@@ -741,7 +792,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     // Block 0's part A, then the first QPIPE units' copies go out while part B multiplies the coefficients in.
     // (Measured: doing part A and these copies BEFORE the barrier gains nothing -- the wait-for-data time of the MMA
     // warps is the cost of polling a completed barrier once per unit, not a pipeline-fill stall.)
-    const int bn0 = min(QBLK, n_units), npre = min(QPIPE, bn0);
+    const int bn0 = min(QBLK, n_units), npre = min(NPIPE, bn0);
     stage_part_a(0, bn0);
     __syncthreads();
     if (warp >= GEMM_CWARPS)
@@ -764,11 +815,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0] - QEPI;
     int seg_c0 = c0;                                      // first chunk of the running segment
     int def_t[2], ndef = 0;
-    double acc[2][4][2];
+    // accumulator fragments f = 0..7: 64 x 64 tiles f = i * 4 + j (2 x 4 blocks of the warp's 16 x 32), cubes
+    // f = i * 2 + j (4 x 2 blocks of the warp's [2 slices x 16 jy] x 16 jx); fragment slot q = (warp * 8 + f) * 32 + lane
+    double acc[8][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int f = 0; f < 8; ++f) acc[f][0] = acc[f][1] = 0.0;
     for (int b0 = 0; b0 < n_units; b0 += QBLK) {
       const int bn = min(QBLK, n_units - b0);
       unsigned long long tk0 = 0;
@@ -788,31 +839,57 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         // --------------------------------- consumers ---------------------------------
         for (int ul = 0; ul < bn; ++ul) {
           const unsigned q = gcount + (unsigned)(b0 + ul);
-          const int gstage = (int)(q % QPIPE);
-          mbar_wait(&gfull[gstage], (q / QPIPE) & 1u);
-          const double* As = ring + (size_t)gstage * QSTAGE_DOUBLES;
-          const double* Bs = As + QKC * QLD;
+          const int gstage = (int)(q % NPIPE);
+          mbar_wait(&gfull[gstage], (q / NPIPE) & 1u);
+          const double* As = ring + (size_t)gstage * STAGE;
           const double* cs = s_cs + ul;
 #if GPIS_EXP == 1      // experiment: the MMA loop runs twice (second time with zero coefficients): the rise is its cost
           for (int rep = 0; rep < 2; ++rep)
 #endif
+          if (CUBE) {
+            const double* Bs = As + QKC * QLDC;
+            const double* Zs = Bs + QKC * QLDC + zodd + 2 * warp;
 #pragma unroll
-          for (int k4 = 0; k4 < QKC / 4; ++k4) {
-            const int kb = k4 * 4 + (lane & 3);
+            for (int k4 = 0; k4 < QKC / 4; ++k4) {
+              const int kb = k4 * 4 + (lane & 3);
 #if GPIS_EXP == 1
-            const double cv = rep ? 0.0 : cs[kb * QBLK];
+              const double cv = rep ? 0.0 : cs[kb * QBLK];
 #else
-            const double cv = cs[kb * QBLK];
+              const double cv = cs[kb * QBLK];
 #endif
-            double af[2], bf[4];
+              // A[(jz, jy)][rho] = (W[r,rho] Tz[rho][jz]) Ty[rho][jy]: the same product, in the same order, as the
+              // 64 x 64 form's (tz w) ty
+              const double z0 = Zs[kb * QLDC] * cv, z1 = Zs[kb * QLDC + 1] * cv;
+              const double y0 = As[kb * QLDC + (lane >> 2)], y1 = As[kb * QLDC + 8 + (lane >> 2)];
+              const double af[4] = {y0 * z0, y1 * z0, y0 * z1, y1 * z1};
+              double bf[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) af[i] = As[kb * QLD + wm * 16 + i * 8 + (lane >> 2)] * cv;
+              for (int j = 0; j < 2; ++j) bf[j] = Bs[kb * QLDC + j * 8 + (lane >> 2)];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[kb * QLD + wn * 32 + j * 8 + (lane >> 2)];
+              for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) dmma8x8x4(acc[i * 2 + j][0], acc[i * 2 + j][1], af[i], bf[j]);
+            }
+          } else {
+            const double* Bs = As + QKC * QLD;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            for (int k4 = 0; k4 < QKC / 4; ++k4) {
+              const int kb = k4 * 4 + (lane & 3);
+#if GPIS_EXP == 1
+              const double cv = rep ? 0.0 : cs[kb * QBLK];
+#else
+              const double cv = cs[kb * QBLK];
+#endif
+              double af[2], bf[4];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) af[i] = As[kb * QLD + wm * 16 + i * 8 + (lane >> 2)] * cv;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bf[j] = Bs[kb * QLD + wn * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma8x8x4(acc[i * 4 + j][0], acc[i * 4 + j][1], af[i], bf[j]);
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&gempty[gstage]);
@@ -823,35 +900,28 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const long long tbase = (long long)wt * QPAIRS;
           if (cta == 0 && tid == 0) tk0 = gtimer_ns();
           if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
-            double2 pmu[2][4], pvar[2][4];
-            uchar2 pfl[2][4];
+            double2 pmu[8], pvar[8];
+            uchar2 pfl[8];
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const long long s2 = tbase + ((warp * 2 + i) * 4 + j) * 32 + lane;
-                pmu[i][j] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
-                pvar[i][j] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
-                pfl[i][j] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
-              }
+            for (int f = 0; f < 8; ++f) {
+              const long long s2 = tbase + (warp * 8 + f) * 32 + lane;
+              pmu[f] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+              pvar[f] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+              pfl[f] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
+            }
             const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int q = ((warp * 2 + i) * 4 + j) * 32 + lane;
-                persist_pair(P, tbase + q, persist_pair_index(q, etx, ety, etz, nx, ny), make_double2(acc[i][j][0], acc[i][j][1]),
-                             pmu[i][j], pvar[i][j], pfl[i][j], sb, gn1, best);
-              }
+            for (int f = 0; f < 8; ++f) {
+              const int q = (warp * 8 + f) * 32 + lane;
+              persist_pair(P, tbase + q, persist_pair_index<CUBE>(q, etx, ety, etz, nx, ny), make_double2(acc[f][0], acc[f][1]),
+                           pmu[f], pvar[f], pfl[f], sb, gn1, best);
+            }
           } else {
             // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
             // first tile, 1: its last), then arrive on the tile
             double2* ws = reinterpret_cast<double2*>(P.gws) + ((size_t)cta * 2 + (wt == tile0 ? 0 : 1)) * QPAIRS;
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                __stcg(&ws[((warp * 2 + i) * 4 + j) * 32 + lane], make_double2(acc[i][j][0], acc[i][j][1]));
+            for (int f = 0; f < 8; ++f) __stcg(&ws[(warp * 8 + f) * 32 + lane], make_double2(acc[f][0], acc[f][1]));
             __threadfence();
             named_sync(1, PCW);
             if (tid == 0) atomicAdd(&P.tile_cnt[wt], 1u);
@@ -859,9 +929,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           }
           if (cta == 0 && tid == 0) s_clk[PCLK_EPIREG] += gtimer_ns() - tk0;
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+          for (int f = 0; f < 8; ++f) acc[f][0] = acc[f][1] = 0.0;
           ++wt;
           wc = 0;
           seg_c0 = 0;
@@ -920,7 +988,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           for (int k = 0; k < GEPI_SPT; ++k) {
             if (ub + k >= un1) continue;
             const int q = (ub + k) * PCW + tid;
-            persist_pair(P, tbase + q, persist_pair_index(q, t2 % tiles_x, (t2 / tiles_x) % tiles_y, t2 / txy, nx, ny), v[k], mu[k],
+            persist_pair(P, tbase + q, persist_pair_index<CUBE>(q, t2 % tiles_x, (t2 / tiles_x) % tiles_y, t2 / txy, nx, ny), v[k], mu[k],
                          var[k], fl[k], sb, gn1, best);
           }
         }
