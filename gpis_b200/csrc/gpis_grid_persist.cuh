@@ -36,7 +36,7 @@ namespace gpis {
 // lap timer of CTA 0 (globaltimer ns): each stamp books the time since the previous stamp
 enum { PCLK_RECWAIT = 0, PCLK_WSETUP = 1, PCLK_WPASS = 2, PCLK_BAR1 = 3, PCLK_FINISH = 4, PCLK_BAR2 = 5, PCLK_PREFIX = 6,
        PCLK_GEMM = 7, PCLK_EPI = 8, PCLK_BAR3 = 9, PCLK_WINNER = 10, PCLK_STEPS = 11,
-       // inside PCLK_GEMM (booked twice): coefficient precompute, waits for a filled stage, in-register epilogues; the
+       // inside PCLK_GEMM (booked twice): coefficient precompute, partial tiles to the workspace, in-register epilogues; the
        // (tile, 32-row chunk) units of ALL blocks (a count: x 2 * 64 * 64 * 32 = the flops the MMAs executed)
        PCLK_PRECOMP = 12, PCLK_WAITFULL = 13, PCLK_EPIREG = 14, PCLK_UNITS = 15, PCLK_N = 16 };
 
@@ -51,8 +51,11 @@ constexpr int QPIPE = 4;
 constexpr int QC = 16;                                  // cube edge
 constexpr int QLDC = QC + 4;                            // padded smem row of a cube stage (conflict-free fragment loads)
 constexpr int QSTAGE_CUBE = 3 * QKC * QLDC;             // Ty rows, Tx rows, Tz rows (18 doubles copied: even-aligned start)
-constexpr int QPIPE_CUBE = 8;
-constexpr int QPIPE_MAX = 8;
+#ifndef GPIS_QPIPE_CUBE
+#define GPIS_QPIPE_CUBE 8
+#endif
+constexpr int QPIPE_CUBE = GPIS_QPIPE_CUBE;
+constexpr int QPIPE_MAX = 10;
 constexpr int QTILE_ELEMS = QT * QT;
 static_assert(QC * QC * QC == QT * QT, "both tile shapes hold the same number of lattice points");
 constexpr int QPAIRS = QTILE_ELEMS / 2;                 // accumulator fragment slots (x-adjacent pairs) per tile
@@ -61,7 +64,10 @@ constexpr int QT_MAX = 2048;                            // most tiles per rank t
 constexpr double QCUT = 48.52030263919617;
 // Stream-K splits the COST of a step evenly: a tile costs its chunks plus QEPI unit times for its epilogue (a chunk is
 // 1.04 us of MMAs, an epilogue about 2 us), so blocks with many short tiles are not the last to arrive.
-constexpr int QEPI = 2;
+#ifndef GPIS_QEPI
+#define GPIS_QEPI 2
+#endif
+constexpr int QEPI = GPIS_QEPI;
 constexpr int QBLK = 128;                               // units whose coefficients sit in shared memory at a time
 
 #ifndef GPIS_EMULATE
@@ -161,34 +167,60 @@ struct PBest {
   long long id, j;
 };
 
-// posterior update + straddle rule for one accumulator fragment slot (two x-adjacent lattice points)
-// jl: lattice index (x fastest) of the slot's first point; its x-neighbour is the second
-__device__ __forceinline__ void persist_pair(const EngineParams& P, long long slot2, long long jl0, double2 v, double2 mu, double2 var,
-                                             uchar2 fl, double sb, double gn1, PBest& b) {
-  mu.x += v.x * gn1; mu.y += v.y * gn1;
-  var.x -= v.x * v.x; var.y -= v.y * v.y;
-  __stcg(reinterpret_cast<double2*>(P.mu) + slot2, mu);
-  __stcg(reinterpret_cast<double2*>(P.var) + slot2, var);
-  unsigned char f[2] = {fl.x, fl.y};
-  if ((f[0] & (F_ACTIVE | F_HIGH | F_LOW)) && (f[1] & (F_ACTIVE | F_HIGH | F_LOW))) return;
-  const double mus[2] = {mu.x, mu.y}, vars[2] = {var.x, var.y};
+// best candidate of the tile a thread is working on: its score and 2 * fragment slot + element inside the tile (-1: none).
+// A thread meets its cells of a tile in ascending lattice order, so a strict comparison keeps the lowest index on a tie.
+struct PTileBest {
+  double s;
+  int q;
+};
+
+// straddle rule for one cell (straddle.m:106-108, 122-125), without branches: returns the cell's flags after the
+// classification and offers its score to the tile's best when the cell is still unclassified
+__device__ __forceinline__ unsigned persist_cell(double mu, double ve, unsigned f0, bool live, int qe, double sb, double level, double eps,
+                                                 PTileBest& b) {
+  const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
+  const double hi = __dadd_rn(mu, w), lo = __dadd_rn(mu, -w);
+  const double sc = fmin(__dadd_rn(hi, -level), __dadd_rn(level, -lo));
+  const bool un = live && (f0 & (unsigned)(F_ACTIVE | F_HIGH | F_LOW)) == 0u;
+  unsigned add = 0u;
+  if (__dadd_rn(lo, eps) > level) add |= (unsigned)F_HIGH;   // :122-125
+  if (__dadd_rn(hi, -eps) < level) add |= (unsigned)F_LOW;
+  const bool take = un && sc > b.s;                    // (false for NaN)
+  b.s = take ? sc : b.s;
+  b.q = take ? qe : b.q;
+  return un ? (f0 | add) : f0;
+}
+
+// Posterior update + straddle rule for NP accumulator fragment slots (two x-adjacent lattice points each) of one tile,
+// branch-free per cell so that the NP independent dependency chains interleave (the branchy per-cell form was bound by
+// fixed-latency waits and instruction fetch: ncu, profiles/r02_k_grid_persist_cube_ncu.csv).
+// q[k]: the fragment slot inside the tile; live[k]: the slot exists (the last batch of a shared tile may be short).
+// nz: predictive-variance mode only, the cells' noise (else null).
+__device__ __forceinline__ void persist_pairs(const int NP, const EngineParams& P, long long tbase, const int* q, const bool* live, const double2* v,
+                                              double2* mu, double2* var, const uchar2* fl, const double2* nz, double sb, double gn1,
+                                              PTileBest& b) {
+  const unsigned CLS = F_ACTIVE | F_HIGH | F_LOW;
+  bool open = false;
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    if (f[e] & (F_ACTIVE | F_HIGH | F_LOW)) continue;
-    const long long jl = jl0 + e;
-    double ve = vars[e];
-    if (P.variance_mode == 1) ve = __dadd_rn(ve, P.noise ? P.noise[jl] : P.noise_scalar);
-    const double w = __dmul_rn(sb, ve);                  // variance, not sigma: straddle.m:106-107
-    const double hi = __dadd_rn(mus[e], w), lo = __dadd_rn(mus[e], -w);
-    const double sc = fmin(__dadd_rn(hi, -P.level), __dadd_rn(P.level, -lo));
-    if (__dadd_rn(lo, P.eps) > P.level) f[e] |= F_HIGH;   // :122-125
-    if (__dadd_rn(hi, -P.eps) < P.level) f[e] |= F_LOW;
-    if (sc >= b.s) {          // (false for NaN) the id only matters on a tie
-      const long long id = cand_id(P, jl);
-      if (better(sc, id, b.s, b.id)) { b.s = sc; b.id = id; b.j = jl; }
+  for (int k = 0; k < NP; ++k) {
+    mu[k].x += v[k].x * gn1; mu[k].y += v[k].y * gn1;
+    var[k].x -= v[k].x * v[k].x; var[k].y -= v[k].y * v[k].y;
+    if (live[k]) {
+      __stcg(reinterpret_cast<double2*>(P.mu) + tbase + q[k], mu[k]);
+      __stcg(reinterpret_cast<double2*>(P.var) + tbase + q[k], var[k]);
     }
+    open = open || (live[k] && (!(fl[k].x & CLS) || !(fl[k].y & CLS)));
   }
-  if (f[0] != fl.x || f[1] != fl.y) __stcg(reinterpret_cast<uchar2*>(P.flags) + slot2, make_uchar2(f[0], f[1]));
+  if (!__any_sync(0xffffffffu, open)) return;      // every cell of the warp's slots is classified: nothing to score
+  const double level = P.level, eps = P.eps;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const unsigned f0 = fl[k].x, f1 = fl[k].y;
+    const unsigned g0 = persist_cell(mu[k].x, nz ? __dadd_rn(var[k].x, nz[k].x) : var[k].x, f0, live[k], 2 * q[k], sb, level, eps, b);
+    const unsigned g1 = persist_cell(mu[k].y, nz ? __dadd_rn(var[k].y, nz[k].y) : var[k].y, f1, live[k], 2 * q[k] + 1, sb, level, eps, b);
+    if (g0 != f0 || g1 != f1)
+      __stcg(reinterpret_cast<uchar2*>(P.flags) + tbase + q[k], make_uchar2((unsigned char)g0, (unsigned char)g1));
+  }
 }
 
 // lattice index of the first point of fragment slot q (0 .. QPAIRS-1) of the tile at (tx, ty, tz)
@@ -205,6 +237,25 @@ __device__ __forceinline__ long long persist_pair_index(int q, int tx, int ty, i
   const int jy = ty * QT + (w >> 1) * 16 + i * 8 + (l >> 2);
   const int jx = tx * QT + (w & 1) * 32 + j * 8 + (l & 3) * 2;
   return (long long)jx + (long long)nx * (jy + (long long)ny * tz);
+}
+
+// predictive-variance mode: the noise of the two cells of fragment slot q (padding cells are classified: not read)
+template <bool CUBE>
+__device__ __forceinline__ double2 persist_cell_noise(const EngineParams& P, int q, int tx, int ty, int tz, int nx, int ny, uchar2 f) {
+  if (!P.noise) return make_double2(P.noise_scalar, P.noise_scalar);
+  const long long jl = persist_pair_index<CUBE>(q, tx, ty, tz, nx, ny);
+  const unsigned cls = F_ACTIVE | F_HIGH | F_LOW;
+  return make_double2((f.x & cls) ? 0.0 : P.noise[jl], (f.y & cls) ? 0.0 : P.noise[jl + 1]);
+}
+
+// the tile's best candidate joins the CTA's running best of the step (lowest id on a tie)
+template <bool CUBE>
+__device__ __forceinline__ void persist_merge_best(const EngineParams& P, const PTileBest& tb, int tx, int ty, int tz, int nx, int ny,
+                                                   PBest& best) {
+  if (tb.q < 0) return;
+  const long long jl = persist_pair_index<CUBE>(tb.q >> 1, tx, ty, tz, nx, ny) + (tb.q & 1);
+  const long long id = cand_id(P, jl);
+  if (better(tb.s, id, best.s, best.id)) { best.s = tb.s; best.id = id; best.j = jl; }
 }
 
 template <int D, bool CUBE>
@@ -810,6 +861,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       return sqrt(beta);
     }();
     const double gn1 = s_fin[1];
+    // predictive-variance mode (max_subset_buffers.cu:113-115): the cells' noise joins the variance before scoring
+    const bool pred_var = P.variance_mode == 1;
     const int wm = warp >> 1, wn = warp & 1;
     // walking state of the consumers: tile, chunk inside it, its chunk count
     int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0] - QEPI;
@@ -900,21 +953,48 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const long long tbase = (long long)wt * QPAIRS;
           if (cta == 0 && tid == 0) tk0 = gtimer_ns();
           if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
-            double2 pmu[8], pvar[8];
-            uchar2 pfl[8];
+#if GPIS_EXP == 2 || GPIS_EXP == 3      // experiments: the whole epilogue (2) or its state loads (3) a second time, values unchanged
+            for (int rep = 0; rep < 2; ++rep) {
+#else
+            {
+              constexpr int rep = 0;
+#endif
+              double2 pmu[8], pvar[8];
+              uchar2 pfl[8];
 #pragma unroll
-            for (int f = 0; f < 8; ++f) {
-              const long long s2 = tbase + (warp * 8 + f) * 32 + lane;
-              pmu[f] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
-              pvar[f] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
-              pfl[f] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
-            }
-            const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
+              for (int f = 0; f < 8; ++f) {
+                const long long s2 = tbase + (warp * 8 + f) * 32 + lane;
+                pmu[f] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+                pvar[f] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+                pfl[f] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
+              }
+#if GPIS_EXP == 3
+              if (rep == 0) {
 #pragma unroll
-            for (int f = 0; f < 8; ++f) {
-              const int q = (warp * 8 + f) * 32 + lane;
-              persist_pair(P, tbase + q, persist_pair_index<CUBE>(q, etx, ety, etz, nx, ny), make_double2(acc[f][0], acc[f][1]),
-                           pmu[f], pvar[f], pfl[f], sb, gn1, best);
+                for (int f = 0; f < 8; ++f) asm volatile("" ::"d"(pmu[f].x), "d"(pmu[f].y), "d"(pvar[f].x), "d"(pvar[f].y), "r"((int)pfl[f].x));
+                continue;
+              }
+#endif
+              const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
+              int pq[8];
+              bool plive[8];
+              double2 pv[8], pnz[8];
+#pragma unroll
+              for (int f = 0; f < 8; ++f) {
+                pq[f] = (warp * 8 + f) * 32 + lane;
+                plive[f] = true;
+                const bool zero = (GPIS_EXP == 2) && rep == 1;
+                pv[f] = zero ? make_double2(0.0, 0.0) : make_double2(acc[f][0], acc[f][1]);
+              }
+              if (pred_var) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) pnz[f] = persist_cell_noise<CUBE>(P, pq[f], etx, ety, etz, nx, ny, pfl[f]);
+              }
+              PTileBest tb;
+              tb.s = NEG_INF; tb.q = -1;
+              const double2* pnzp = pnz;
+              persist_pairs(8, P, tbase, pq, plive, pv, pmu, pvar, pfl, pred_var ? pnzp : nullptr, sb, gn1, tb);
+              persist_merge_best<CUBE>(P, tb, etx, ety, etz, nx, ny, best);
             }
           } else {
             // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
@@ -927,7 +1007,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
             if (tid == 0) atomicAdd(&P.tile_cnt[wt], 1u);
             def_t[ndef++] = wt;
           }
-          if (cta == 0 && tid == 0) s_clk[PCLK_EPIREG] += gtimer_ns() - tk0;
+          if (cta == 0 && tid == 0) s_clk[whole ? PCLK_EPIREG : PCLK_WAITFULL] += gtimer_ns() - tk0;
 #pragma unroll
           for (int f = 0; f < 8; ++f) acc[f][0] = acc[f][1] = 0.0;
           ++wt;
@@ -959,6 +1039,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         const int slot_first = ((long long)g_first * U / Gw >= (long long)s_pref[t2] - QEPI) ? 0 : 1;
         const double2* wsb = reinterpret_cast<const double2*>(P.gws);
         const long long tbase = (long long)t2 * QPAIRS;
+        const int e2x = t2 % tiles_x, e2y = (t2 / tiles_x) % tiles_y, e2z = t2 / txy;
+        PTileBest tb;
+        tb.s = NEG_INF; tb.q = -1;
         for (int ub = un0; ub < un1; ub += GEPI_SPT) {
           double2 v[GEPI_SPT], mu[GEPI_SPT], var[GEPI_SPT];
           uchar2 fl[GEPI_SPT];
@@ -984,14 +1067,22 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
             var[k] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
             fl[k] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
           }
+          int pq[GEPI_SPT];
+          bool plive[GEPI_SPT];
+          double2 pnz[GEPI_SPT];
 #pragma unroll
           for (int k = 0; k < GEPI_SPT; ++k) {
-            if (ub + k >= un1) continue;
-            const int q = (ub + k) * PCW + tid;
-            persist_pair(P, tbase + q, persist_pair_index<CUBE>(q, t2 % tiles_x, (t2 / tiles_x) % tiles_y, t2 / txy, nx, ny), v[k], mu[k],
-                         var[k], fl[k], sb, gn1, best);
+            plive[k] = ub + k < un1;
+            pq[k] = (plive[k] ? ub + k : un1 - 1) * PCW + tid;
           }
+          if (pred_var) {
+#pragma unroll
+            for (int k = 0; k < GEPI_SPT; ++k) pnz[k] = persist_cell_noise<CUBE>(P, pq[k], e2x, e2y, e2z, nx, ny, fl[k]);
+          }
+          const double2* pnzp = pnz;
+          persist_pairs(GEPI_SPT, P, tbase, pq, plive, v, mu, var, fl, pred_var ? pnzp : nullptr, sb, gn1, tb);
         }
+        persist_merge_best<CUBE>(P, tb, e2x, e2y, e2z, nx, ny, best);
       }
       if (!ok && tid == 0) persist_fail(st);
       // CTA winner

@@ -286,7 +286,7 @@ class GpisEngine:
                 "append_ms": p.value, "main_ms": q.value, "epilogue_ms": r.value}
 
     PERSIST_SLOTS = ("record_wait", "w_setup", "w_pass", "barrier1", "new_row", "barrier2", "prefix", "gemm", "epilogue",
-                     "barrier3", "winner", "steps", "gemm_precompute", "gemm_wait_full", "gemm_epilogue_regs", "units")
+                     "barrier3", "winner", "steps", "gemm_precompute", "gemm_partial_tiles", "gemm_epilogue_regs", "units")
 
     def persist_timing(self):
         """Lap times (ms, block 0's clock) of the persistent selection kernel in the last select()."""

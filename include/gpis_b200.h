@@ -306,7 +306,7 @@ gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main
  * rows, [2] W pass of the factor append, [3] grid barrier, [4] new row of W, [5] grid barrier, [6] unit prefix,
  * [7] update GEMM with the in-register epilogues of whole tiles, [8] epilogues of tiles shared between blocks,
  * [9] grid barrier, [10] winner reduction (+ record publication when sharded), [11] = number of steps (a count);
- * inside [7]: [12] coefficient precompute, [13] waits for a filled pipeline stage, [14] in-register epilogues,
+ * inside [7]: [12] coefficient precompute, [13] partial tiles to the workspace (store, fence, arrival), [14] in-register epilogues,
  * [15] = number of (tile, 32-row chunk) units all blocks processed (a count; x 2*64*64*32 = executed MMA flops).
  * 16 doubles. */
 gpis_status gpis_get_persist_timing(gpis_handle h, double* ms16);
