@@ -52,7 +52,7 @@ constexpr int QC = 16;                                  // cube edge
 constexpr int QLDC = QC + 4;                            // padded smem row of a cube stage (conflict-free fragment loads)
 constexpr int QSTAGE_CUBE = 3 * QKC * QLDC;             // Ty rows, Tx rows, Tz rows (18 doubles copied: even-aligned start)
 #ifndef GPIS_QPIPE_CUBE
-#define GPIS_QPIPE_CUBE 8
+#define GPIS_QPIPE_CUBE 6
 #endif
 constexpr int QPIPE_CUBE = GPIS_QPIPE_CUBE;
 constexpr int QPIPE_MAX = 10;
@@ -64,6 +64,9 @@ constexpr int QT_MAX = 2048;                            // most tiles per rank t
 constexpr double QCUT = 48.52030263919617;
 // Stream-K splits the COST of a step evenly: a tile costs its chunks plus QEPI unit times for its epilogue (a chunk is
 // 1.04 us of MMAs, an epilogue about 2 us), so blocks with many short tiles are not the last to arrive.
+#ifndef GPIS_PROD_EPI
+#define GPIS_PROD_EPI 1      // cubes: the producer warps run the epilogues of whole tiles (0: the MMA warps, from registers)
+#endif
 #ifndef GPIS_QEPI
 #define GPIS_QEPI 2
 #endif
@@ -88,7 +91,8 @@ constexpr int PTHREADS = (GEMM_CWARPS + QPROD) * 32;
 constexpr size_t PERSIST_SMEM =
     sizeof(double) * ((size_t)GS1_RMAX + PRING_DOUBLES) + 8 * (2 * PRING_SLOTS_MAX + 2 * QPIPE_MAX);
 static_assert((size_t)QPIPE * QSTAGE_DOUBLES <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
-static_assert((size_t)QPIPE_CUBE * QSTAGE_CUBE <= (size_t)PRING_DOUBLES, "GEMM stages alias the ring");
+static_assert((size_t)QPIPE_CUBE * QSTAGE_CUBE + 2 * (size_t)QTILE_ELEMS <= (size_t)PRING_DOUBLES,
+              "GEMM stages and the two accumulator staging tiles alias the ring");
 static_assert(GS1_CPT * PCW == GS1_RMAX, "column ownership of the W pass");
 static_assert(QBLK * QKC <= GS1_RMAX, "the coefficients of a block alias the covariance vector");
 static_assert(QKC == 32, "a producer warp issues one Ty row and one Tx row per lane");
@@ -109,6 +113,16 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 __device__ __forceinline__ void mbar_inval(unsigned long long* bar) {
   asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -275,7 +289,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   __shared__ double s_rec[PAY_HDR];
   __shared__ double s_gram[PTHREADS / 32][2];
   __shared__ double s_fin[3];                             // dinv, g_new, ok
-  __shared__ BlockBest s_bb[GEMM_CWARPS];
+  __shared__ BlockBest s_bb[PTHREADS / 32];
+  __shared__ unsigned long long s_sbar[4];                // cubes: accumulator staging tiles, full[2] / free[2]
+  __shared__ int s_stile[2];                              // the tiles they hold
   __shared__ double s_next_aux[2];                        // its target and noise
   __shared__ BlockBest s_next;                            // the winner every CTA reduced at the end of the previous step
   __shared__ int s_win, s_flag;
@@ -296,7 +312,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   if (*(volatile int*)&st->r != 0 || *(volatile int*)&st->m != 0 || *(volatile int*)&st->iter != 0) return;
   for (int i = tid; i < GS1_RMAX; i += PTHREADS) s_kv[i] = 0.0;
   if (tid == 0) {
-    for (int i = 0; i < NPIPE; ++i) { mbar_init(&gfull[i], 1); mbar_init(&gempty[i], GEMM_CWARPS); }
+    for (int i = 0; i < NPIPE; ++i) { mbar_init(&gfull[i], CUBE ? 32 : 1); mbar_init(&gempty[i], GEMM_CWARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_sbar[i], GEMM_CWARPS); mbar_init(&s_sbar[2 + i], QPROD); }
     for (int i = 0; i < PRING_SLOTS_MAX; ++i) { mbar_init(&rfull[i], 1); mbar_init(&rempty[i], GEMM_CWARPS); }
     mbar_init_fence();
     s_next.score = NEG_INF; s_next.id = 0x7fffffffffffffffLL; s_next.local = -1;
@@ -311,6 +328,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   if (tid == 0) s_tk[0] = gtimer_ns();
   unsigned long long d_ns = 0, dwait_ns = 0, dt0 = 0;      // thread 0 of every CTA: its time in phase D / waiting for a filled stage
   int stop = 0;          // 1: nothing unclassified / capacity (done), 2: not positive definite
+  unsigned nst = 0;      // cubes: whole tiles staged (consumers) / taken from the staging tiles (producers) so far
   unsigned gcount = 0;   // units this CTA has put through the GEMM ring so far (the barriers' phases run on across steps)
   int w_nslots = -1;     // W ring: slots of the current geometry and rows streamed through it so far
   unsigned wseq = 0;
@@ -756,6 +774,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       if (tile0 >= T) tile0 = T - 1;
     }
     const long long q_first = ((long long)s_pref[tile0] - (long long)QEPI * tile0) + c0;      // first chunk, in chunk space
+    PBest best;
+    best.s = NEG_INF; best.id = 0x7fffffffffffffffLL; best.j = -1;
+    const double sb = [&]() {
+      double beta = P.beta;
+      if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
+      else if (P.beta_mode == 2) { const double k1 = (double)(gen + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
+      return sqrt(beta);
+    }();
+    const double gn1 = s_fin[1];
+    // predictive-variance mode (max_subset_buffers.cu:113-115): the cells' noise joins the variance before scoring
+    const bool pred_var = P.variance_mode == 1;
     double* s_cs = s_kv;                                  // [QKC][QBLK], aliases the winner's covariance vector (phase B only)
     // The units of this CTA go through the ring in blocks of QBLK.  Before a block starts every thread takes one
     // unit and leaves, in shared memory, its 16 model-row indices, its tile's offsets into the axis-table rows and
@@ -820,14 +849,27 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       const int rho = (int)s_rho[lane * QBLK + ul];
       const int uo = s_uoff[ul];
       if (CUBE) {
+        // 16-byte asynchronous copies (LDGSTS), eight lanes per 128-byte row segment: 25 instructions per lane and
+        // unit, completion counted by the stage's mbarrier (cp.async.mbarrier.arrive.noinc, 32 arrivals).  A bulk
+        // copy per row segment (96 per unit) costs a serial elect-one loop of ~40 cycles each: 2 us per unit and warp,
+        // which left the producer warps no time for the epilogues they run now.
         double* Bs = As + QKC * QLDC;
         double* Zs = Bs + QKC * QLDC;
-        if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], QKC * (2 * QC + QC + 2) * (unsigned)sizeof(double));
-        __syncwarp();
-        bulk_g2s(As + lane * QLDC, P.T[1] + (long long)rho * P.ldt[1] + ((uo >> 10) & 1023) * QC, QC * sizeof(double), &gfull[stage]);
-        bulk_g2s(Bs + lane * QLDC, P.T[0] + (long long)rho * P.ldt[0] + (uo & 1023) * QC, QC * sizeof(double), &gfull[stage]);
-        bulk_g2s(Zs + lane * QLDC, P.T[D > 2 ? 2 : 0] + (long long)rho * P.ldt[D > 2 ? 2 : 0] + ((P.gz0 + (uo >> 20) * QC) & ~1),
-                 (QC + 2) * sizeof(double), &gfull[stage]);
+        const int rsel = lane >> 3, pc = (lane & 7) * 2;
+        const double* sy = P.T[1] + ((uo >> 10) & 1023) * QC + pc;
+        const double* sx = P.T[0] + (uo & 1023) * QC + pc;
+        const double* sz = P.T[D > 2 ? 2 : 0] + ((P.gz0 + (uo >> 20) * QC) & ~1);
+        const long long l1 = P.ldt[1], l0 = P.ldt[0], l2 = P.ldt[D > 2 ? 2 : 0];
+#pragma unroll
+        for (int i = 0; i < QKC / 4; ++i) {
+          const int row = i * 4 + rsel;
+          const long long rr = (long long)s_rho[row * QBLK + ul];
+          g_cp_async16(As + row * QLDC + pc, sy + rr * l1);
+          g_cp_async16(Bs + row * QLDC + pc, sx + rr * l0);
+          g_cp_async16(Zs + row * QLDC + pc, sz + rr * l2 + pc);
+        }
+        g_cp_async16(Zs + lane * QLDC + QC, sz + (long long)rho * l2 + QC);      // the z rows' ninth piece (even-aligned start)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&gfull[stage])) : "memory");
       } else {
         double* Bs = As + QKC * QLD;
         if (lane == 0) mbar_arrive_expect_tx(&gfull[stage], 2 * QKC * QT * (unsigned)sizeof(double));
@@ -835,6 +877,70 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         bulk_g2s(As + lane * QLD, P.T[1] + (long long)rho * P.ldt[1] + (uo & 0xffff), QT * sizeof(double), &gfull[stage]);
         bulk_g2s(Bs + lane * QLD, P.T[0] + (long long)rho * P.ldt[0] + (uo >> 16), QT * sizeof(double), &gfull[stage]);
       }
+    };
+    // Cubes: a tile that lies inside this CTA's range leaves the MMA warps as a 32 KB staging tile in shared memory
+    // (two of them, full / free mbarriers) and the four PRODUCER warps -- idle nine tenths of the time -- run its
+    // epilogue (posterior update, straddle score, classification, arg-max) a quarter each, while the MMA warps are
+    // already on the next tile.  whole_upto(u): such tiles among the first u units of this CTA.
+    auto whole_upto = [&](int uend) {
+      int n = 0, t = tile0, c = c0, pos = 0;
+      while (pos < uend && t < T) {
+        const int Ct = s_pref[t + 1] - s_pref[t] - QEPI, take = min(Ct - c, uend - pos);
+        pos += take;
+        if (c == 0 && take == Ct) ++n;
+        ++t; c = 0;
+      }
+      return n;
+    };
+    double2* stg = reinterpret_cast<double2*>(ring + (size_t)NPIPE * STAGE);      // [2][QPAIRS]
+    int ptaken = 0, pb = 0;      // producers: staged tiles of THIS step finished, batches of the tile at hand done
+    PTileBest ptb;
+    ptb.s = NEG_INF; ptb.q = -1;
+    // one batch (GEPI_SPT fragment slots per lane: a quarter of this warp's quarter) of the staged tile at hand
+    auto service_batch = [&]() {
+      const int slot = (int)(nst & 1u);
+      const int t = *(volatile int*)&s_stile[slot];
+      const double2* sv = stg + (size_t)slot * QPAIRS;
+      const long long tbase = (long long)t * QPAIRS;
+      const int etz = t / txy, ety = (t / tiles_x) % tiles_y, etx = t % tiles_x;
+      int pq[GEPI_SPT];
+      bool plive[GEPI_SPT];
+      double2 pv[GEPI_SPT], pmu[GEPI_SPT], pvar[GEPI_SPT], pnz[GEPI_SPT];
+      uchar2 pfl[GEPI_SPT];
+#pragma unroll
+      for (int k = 0; k < GEPI_SPT; ++k) {
+        pq[k] = ((warp - GEMM_CWARPS) * 16 + pb * GEPI_SPT + k) * 32 + lane;
+        plive[k] = true;
+        pmu[k] = __ldcg(reinterpret_cast<const double2*>(P.mu) + tbase + pq[k]);
+        pvar[k] = __ldcg(reinterpret_cast<const double2*>(P.var) + tbase + pq[k]);
+        pfl[k] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + tbase + pq[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < GEPI_SPT; ++k) pv[k] = sv[pq[k]];
+      if (pred_var) {
+#pragma unroll
+        for (int k = 0; k < GEPI_SPT; ++k) pnz[k] = persist_cell_noise<CUBE>(P, pq[k], etx, ety, etz, nx, ny, pfl[k]);
+      }
+      const double2* pnzp = pnz;
+      persist_pairs(GEPI_SPT, P, tbase, pq, plive, pv, pmu, pvar, pfl, pred_var ? pnzp : nullptr, sb, gn1, ptb);
+      if (++pb == 16 / GEPI_SPT) {
+        persist_merge_best<CUBE>(P, ptb, etx, ety, etz, nx, ny, best);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_sbar[2 + slot]);
+        ++nst;
+        ++ptaken;
+        pb = 0;
+        ptb.s = NEG_INF; ptb.q = -1;
+      }
+    };
+    // producers, main loop: like issue_unit, but while the stage is still in use they take staged tiles
+    auto issue_unit_serving = [&](int b0, int ul, int n_whole) {
+      const unsigned q = gcount + (unsigned)(b0 + ul);
+      const int stage = (int)(q % NPIPE);
+      while (!mbar_test(&gempty[stage], ((q / NPIPE) & 1u) ^ 1u)) {      // copies first, a batch of epilogue while the ring is full
+        if (pb > 0 || (ptaken < n_whole && mbar_test(&s_sbar[nst & 1u], (nst >> 1) & 1u))) service_batch();
+      }
+      issue_unit(b0, ul);
     };
     if (s_fin[2] == 0.0) { stop = 2; break; }          // every CTA computes the same pivot: uniform exit
     PSTAMP(PCLK_FINISH);
@@ -852,17 +958,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     // ------------------------------------------------------------------ D: update GEMM + epilogue
     PSTAMP(PCLK_PREFIX);
     if (tid == 0) dt0 = gtimer_ns();
-    PBest best;
-    best.s = NEG_INF; best.id = 0x7fffffffffffffffLL; best.j = -1;
-    const double sb = [&]() {
-      double beta = P.beta;
-      if (P.beta_mode == 1) beta = 2.0 * log((double)P.N_total * (double)(gen + 1) * 9.869604401089358 / (6.0 * P.beta_delta));
-      else if (P.beta_mode == 2) { const double k1 = (double)(gen + 1); beta = 2.0 * log((double)P.N_total * 9.869604401089358 * k1 * k1 / (6.0 * P.beta_delta)); }
-      return sqrt(beta);
-    }();
-    const double gn1 = s_fin[1];
-    // predictive-variance mode (max_subset_buffers.cu:113-115): the cells' noise joins the variance before scoring
-    const bool pred_var = P.variance_mode == 1;
     const int wm = warp >> 1, wn = warp & 1;
     // walking state of the consumers: tile, chunk inside it, its chunk count
     int wt = tile0, wc = c0, wCt = s_pref[tile0 + 1] - s_pref[tile0] - QEPI;
@@ -887,7 +982,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       if (cta == 0 && tid == 0) { s_clk[PCLK_PRECOMP] += gtimer_ns() - tk0; if (b0 == 0) s_clk[PCLK_UNITS] += (unsigned long long)(U - (long long)QEPI * T); }
       if (warp >= GEMM_CWARPS) {
         // ------------------------------- producers: every QPROD-th unit each -------------------------------
-        for (int ul = (b0 == 0 ? npre : 0) + warp - GEMM_CWARPS; ul < bn; ul += QPROD) issue_unit(b0, ul);
+        if (CUBE && GPIS_PROD_EPI) {
+          const int n_whole = whole_upto(b0 + bn);       // staged by the end of this block of units
+          for (int ul = (b0 == 0 ? npre : 0) + warp - GEMM_CWARPS; ul < bn; ul += QPROD) issue_unit_serving(b0, ul, n_whole);
+          while (ptaken < n_whole) {                     // every copy of the block is out: the MMA warps cannot be waiting for us
+            if (pb == 0) mbar_wait(&s_sbar[nst & 1u], (nst >> 1) & 1u);
+            service_batch();
+          }
+        } else {
+          for (int ul = (b0 == 0 ? npre : 0) + warp - GEMM_CWARPS; ul < bn; ul += QPROD) issue_unit(b0, ul);
+        }
       } else {
         // --------------------------------- consumers ---------------------------------
         for (int ul = 0; ul < bn; ++ul) {
@@ -952,50 +1056,45 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const bool whole = (seg_c0 == 0) && (wc == wCt);
           const long long tbase = (long long)wt * QPAIRS;
           if (cta == 0 && tid == 0) tk0 = gtimer_ns();
-          if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
-#if GPIS_EXP == 2 || GPIS_EXP == 3      // experiments: the whole epilogue (2) or its state loads (3) a second time, values unchanged
-            for (int rep = 0; rep < 2; ++rep) {
-#else
-            {
-              constexpr int rep = 0;
-#endif
-              double2 pmu[8], pvar[8];
-              uchar2 pfl[8];
+          if (whole && CUBE && GPIS_PROD_EPI) {      // to a staging tile in shared memory: the producer warps run its epilogue
+            const int slot = (int)(nst & 1u);
+            mbar_wait(&s_sbar[2 + slot], ((nst >> 1) & 1u) ^ 1u);
+            double2* sv = stg + (size_t)slot * QPAIRS;
 #pragma unroll
-              for (int f = 0; f < 8; ++f) {
-                const long long s2 = tbase + (warp * 8 + f) * 32 + lane;
-                pmu[f] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
-                pvar[f] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
-                pfl[f] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
-              }
-#if GPIS_EXP == 3
-              if (rep == 0) {
+            for (int f = 0; f < 8; ++f) sv[(warp * 8 + f) * 32 + lane] = make_double2(acc[f][0], acc[f][1]);
+            if (tid == 0) s_stile[slot] = wt;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_sbar[slot]);
+            ++nst;
+          } else if (whole) {       // straight from the accumulator registers: all of the tile's state loads in flight first
+            double2 pmu[8], pvar[8];
+            uchar2 pfl[8];
 #pragma unroll
-                for (int f = 0; f < 8; ++f) asm volatile("" ::"d"(pmu[f].x), "d"(pmu[f].y), "d"(pvar[f].x), "d"(pvar[f].y), "r"((int)pfl[f].x));
-                continue;
-              }
-#endif
-              const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
-              int pq[8];
-              bool plive[8];
-              double2 pv[8], pnz[8];
-#pragma unroll
-              for (int f = 0; f < 8; ++f) {
-                pq[f] = (warp * 8 + f) * 32 + lane;
-                plive[f] = true;
-                const bool zero = (GPIS_EXP == 2) && rep == 1;
-                pv[f] = zero ? make_double2(0.0, 0.0) : make_double2(acc[f][0], acc[f][1]);
-              }
-              if (pred_var) {
-#pragma unroll
-                for (int f = 0; f < 8; ++f) pnz[f] = persist_cell_noise<CUBE>(P, pq[f], etx, ety, etz, nx, ny, pfl[f]);
-              }
-              PTileBest tb;
-              tb.s = NEG_INF; tb.q = -1;
-              const double2* pnzp = pnz;
-              persist_pairs(8, P, tbase, pq, plive, pv, pmu, pvar, pfl, pred_var ? pnzp : nullptr, sb, gn1, tb);
-              persist_merge_best<CUBE>(P, tb, etx, ety, etz, nx, ny, best);
+            for (int f = 0; f < 8; ++f) {
+              const long long s2 = tbase + (warp * 8 + f) * 32 + lane;
+              pmu[f] = __ldcg(reinterpret_cast<const double2*>(P.mu) + s2);
+              pvar[f] = __ldcg(reinterpret_cast<const double2*>(P.var) + s2);
+              pfl[f] = __ldcg(reinterpret_cast<const uchar2*>(P.flags) + s2);
             }
+            const int etz = wt / txy, ety = (wt / tiles_x) % tiles_y, etx = wt % tiles_x;
+            int pq[8];
+            bool plive[8];
+            double2 pv[8], pnz[8];
+#pragma unroll
+            for (int f = 0; f < 8; ++f) {
+              pq[f] = (warp * 8 + f) * 32 + lane;
+              plive[f] = true;
+              pv[f] = make_double2(acc[f][0], acc[f][1]);
+            }
+            if (pred_var) {
+#pragma unroll
+              for (int f = 0; f < 8; ++f) pnz[f] = persist_cell_noise<CUBE>(P, pq[f], etx, ety, etz, nx, ny, pfl[f]);
+            }
+            PTileBest tb;
+            tb.s = NEG_INF; tb.q = -1;
+            const double2* pnzp = pnz;
+            persist_pairs(8, P, tbase, pq, plive, pv, pmu, pvar, pfl, pred_var ? pnzp : nullptr, sb, gn1, tb);
+            persist_merge_best<CUBE>(P, tb, etx, ety, etz, nx, ny, best);
           } else {
             // a tile cut by this CTA's range: partial accumulators -> the CTA's workspace slot (0: the range's
             // first tile, 1: its last), then arrive on the tile
@@ -1085,7 +1184,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         persist_merge_best<CUBE>(P, tb, e2x, e2y, e2z, nx, ny, best);
       }
       if (!ok && tid == 0) persist_fail(st);
-      // CTA winner
+    }
+    // CTA winner (cubes: the producer warps hold the best of the tiles they finished)
+    {
       for (int o = 16; o > 0; o >>= 1) {
         const double os = __shfl_xor_sync(0xffffffffu, best.s, o);
         const long long oid = __shfl_xor_sync(0xffffffffu, best.id, o);
@@ -1093,10 +1194,10 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         if (oj >= 0 && better(os, oid, best.s, best.id)) { best.s = os; best.id = oid; best.j = oj; }
       }
       if (lane == 0) { s_bb[warp].score = best.s; s_bb[warp].id = best.id; s_bb[warp].local = best.j; }
-      named_sync(1, PCW);
+      __syncthreads();
       if (tid == 0) {
         BlockBest b = s_bb[0];
-        for (int w = 1; w < GEMM_CWARPS; ++w)
+        for (int w = 1; w < PTHREADS / 32; ++w)
           if (s_bb[w].local >= 0 && (b.local < 0 || better(s_bb[w].score, s_bb[w].id, b.score, b.id))) b = s_bb[w];
         BlockBest* dst = &P.partials[cta];
         __stcg(&dst->score, b.score);
