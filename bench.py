@@ -204,7 +204,7 @@ def run_ours(args):
     grid_backend = args.backend == "grid"
     if grid_backend:       # z-slabs of the lattice
         # z-slabs with about equal work per rank (end slices sum fewer model rows) unless --equal-slabs
-        z0, z1 = gdist.slab_range(g, rank, world) if args.equal_slabs else gdist.slab_range_balanced(g, rank, world, HYP_ELL)
+        z0, z1 = gdist.slab_range(g, rank, world) if args.equal_slabs else gdist.slab_range_balanced(g, rank, world, HYP_ELL, align=16)
         lo, hi = g * g * z0, g * g * z1
     else:
         lo, hi = gdist.shard_range(N, rank, world)
@@ -391,14 +391,15 @@ def run_ours(args):
                 tpeak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 * world
             tach = 3.0 * tach
         if persist_used:
-            # executed flops: (tile, 32-row chunk) units x 2 * 64 * 64 * 32, counted by the kernel itself; the phase
-            # time is rank 0's block-0 lap timer summed over the steps (phase D: unit prefix, coefficient
-            # precompute, MMAs and the in-register epilogues of whole tiles)
+            # executed flops: (tile, 32-row chunk) units x 2 * 4096 * 32 (a tile is 4096 lattice points: a 16^3 cube of a
+            # 3-D lattice, 64 x 64 of a 2-D one), counted by the kernel itself; the phase time is rank 0's block-0 lap
+            # timer summed over the steps (phase D: unit prefix, coefficient precompute, MMAs, staging of finished tiles)
             exe_flops = float(tot[3]) / args.steps * 2.0 * 64 * 64 * 32
             tach = exe_flops / main_s / 1e12
             ps = {k: v / args.steps for k, v in acc["persist"].items()}
-        roof = {"kernel": ("k_grid_persist, update-GEMM phase (per step and 64 x 64 lattice tile a [64 x rows] x [rows x 64] contraction over the "
-                           "model rows within reach of the tile, fp64 tensor pipe DMMA.8x8x4; stream-K over one resident CTA per SM)")
+        roof = {"kernel": ("k_grid_persist, update-GEMM phase (per step and 16 x 16 x 16 lattice cube a [(jz, jy) = 256 x rows] x [rows x (jx) = 16] "
+                           "contraction over the model rows within reach of the cube, fp64 tensor pipe DMMA.8x8x4; stream-K over one resident "
+                           "CTA per SM; the epilogues of finished cubes run on the producer warps meanwhile)")
                 if persist_used else
                 "k_grid_gemm (per-step [ny x r] x [r x nx] contraction per z-slice on the fp64 tensor "
                           "pipe, DMMA.8x8x4; stream-K over 148 persistent CTAs)",

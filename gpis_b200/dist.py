@@ -34,13 +34,15 @@ def slab_range(nz, rank, world):
     return z0, z0 + per + (1 if rank < extra else 0)
 
 
-def slab_range_balanced(nz, rank, world, ell, spacing=1.0, fixed=0.35):
+def slab_range_balanced(nz, rank, world, ell, spacing=1.0, fixed=0.35, align=1):
     """z-slabs of a lattice with about equal WORK per rank for the persistent selection kernel: a slice only
     sums the model rows within 9.85 ell of it (gpis_grid_persist.cuh), so with rows spread over the volume the
     slices near the two ends of the z axis cost about half of a middle slice.  Weight of slice z = the part of
     [z - c, z + c] inside the lattice (c = 9.85 ell / spacing slices) + `fixed` x 2c for the per-slice work
     that does not depend on the rows (epilogue, state traffic); slabs are contiguous and cut where the running
-    weight crosses k / world of the total.  Every rank gets at least one slice.  Returns [z0, z1)."""
+    weight crosses k / world of the total.  Every rank gets at least one slice.  `align` = 16 moves the cuts to
+    multiples of 16 slices when every rank can have 16: the persistent kernel works on 16 x 16 x 16 cubes of a 3-D
+    slab, and a slab of 19 slices would pay for 32.  Returns [z0, z1)."""
     c = 9.85 * float(ell) / float(spacing)
     z = np.arange(nz, dtype=np.float64)
     w = np.minimum(z + c, nz - 1) - np.maximum(z - c, 0.0) + fixed * 2.0 * c
@@ -51,6 +53,12 @@ def slab_range_balanced(nz, rank, world, ell, spacing=1.0, fixed=0.35):
         zc = min(max(zc, cuts[-1] + 1), nz - (world - k))
         cuts.append(zc)
     cuts.append(nz)
+    if align > 1 and nz >= align * world:
+        al = [0]
+        for k in range(1, world):
+            zc = int(round(cuts[k] / align)) * align
+            al.append(min(max(zc, al[-1] + align), nz - align * (world - k)))
+        cuts = al + [nz]
     return cuts[rank], cuts[rank + 1]
 
 
