@@ -1101,9 +1101,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
             double2* ws = reinterpret_cast<double2*>(P.gws) + ((size_t)cta * 2 + (wt == tile0 ? 0 : 1)) * QPAIRS;
 #pragma unroll
             for (int f = 0; f < 8; ++f) __stcg(&ws[(warp * 8 + f) * 32 + lane], make_double2(acc[f][0], acc[f][1]));
-            __threadfence();
-            named_sync(1, PCW);
-            if (tid == 0) atomicAdd(&P.tile_cnt[wt], 1u);
+            named_sync(1, PCW);      // the MMA warps' stores happen before thread 0's fence (cumulative) and its arrival
+            if (tid == 0) { __threadfence(); atomicAdd(&P.tile_cnt[wt], 1u); }
             def_t[ndef++] = wt;
           }
           if (cta == 0 && tid == 0) s_clk[whole ? PCLK_EPIREG : PCLK_WAITFULL] += gtimer_ns() - tk0;
