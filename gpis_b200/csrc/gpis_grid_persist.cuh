@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   const int zodd = CUBE ? (P.gz0 & 1) : 0;                // the Tz rows are copied from the even index below the cube's first slice
   if (tid < PCLK_N) s_clk[tid] = 0;
   if (tid == 0) s_tk[0] = gtimer_ns();
-  unsigned long long d_ns = 0, dwait_ns = 0, dt0 = 0;      // thread 0 of every CTA: its time in phase D / waiting for a filled stage
+  unsigned long long d_ns = 0, dwait_ns = 0, dt0 = 0;      // thread 0 of every CTA: its time in phase D / (experiments 5, 6) waiting for its producer warps, for shared tiles
   int stop = 0;          // 1: nothing unclassified / capacity (done), 2: not positive definite
   unsigned nst = 0;      // cubes: whole tiles staged (consumers) / taken from the staging tiles (producers) so far
   unsigned gcount = 0;   // units this CTA has put through the GEMM ring so far (the barriers' phases run on across steps)
@@ -1126,7 +1126,11 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         const int g_first = unit_owner((long long)s_pref[t2], U, Gw);                      // owner of the tile's first chunk
         const int nseg = unit_owner((long long)s_pref[t2 + 1] - QEPI - 1, U, Gw) - g_first + 1;      // .. of its last chunk
         const int seg = cta - g_first;
-        if (tid == 0) s_flag = spin_ge(&P.tile_cnt[t2], (unsigned)nseg, P, st) ? 1 : 0;
+        if (tid == 0) {
+          const unsigned long long tw0 = gtimer_ns();
+          s_flag = spin_ge(&P.tile_cnt[t2], (unsigned)nseg, P, st) ? 1 : 0;
+          if (GPIS_EXP == 6) dwait_ns += gtimer_ns() - tw0;      // per-CTA view: waiting for a shared tile's other contributors
+        }
         named_sync(1, PCW);
         if (!s_flag) { ok = false; break; }
         __threadfence();
@@ -1193,7 +1197,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         if (oj >= 0 && better(os, oid, best.s, best.id)) { best.s = os; best.id = oid; best.j = oj; }
       }
       if (lane == 0) { s_bb[warp].score = best.s; s_bb[warp].id = best.id; s_bb[warp].local = best.j; }
+      const unsigned long long tp0 = (GPIS_EXP == 5 && tid == 0) ? gtimer_ns() : 0ull;
       __syncthreads();
+      if (GPIS_EXP == 5 && tid == 0) dwait_ns += gtimer_ns() - tp0;      // per-CTA view: waiting for the producer warps' last epilogues
       if (tid == 0) {
         BlockBest b = s_bb[0];
         for (int w = 1; w < PTHREADS / 32; ++w)
