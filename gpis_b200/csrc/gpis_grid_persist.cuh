@@ -586,8 +586,17 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
       for (int c = 0; c < GS1_CPT; ++c) acc[c] = 0.0;
       int par = 0;
       for (int i0 = 0; i0 < my_rows; i0 += PB) {
+#if GPIS_EXP == 7      // experiment: where a W-pass batch spends its time: [12] waits + loads, [13] dots + shuffles, [14] barrier
+        unsigned long long t7 = (cta == 0 && tid == 0) ? gtimer_ns() : 0ull;
+#define GPIS_LAP7(slot) do { if (cta == 0 && tid == 0) { const unsigned long long n7 = gtimer_ns(); s_clk[slot] += n7 - t7; t7 = n7; } } while (0)
+#else
+#define GPIS_LAP7(slot) do { } while (0)
+#endif
         double w[PB][GS1_CPT];
         double p[PB];
+        // column slots of this batch's longest row (its last), in groups of four: the slots beyond hold nothing of
+        // any row of the batch and are skipped (uniform branches) -- on average two thirds of them
+        const int cgmax = min(GS1_CPT / 4, ((cta + min(i0 + PB - 1, my_rows - 1) * G) / (4 * PCW)) + 1);
 #pragma unroll
         for (int b = 0; b < PB; ++b) {
           p[b] = 0.0;
@@ -598,15 +607,24 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
             mbar_wait(&rfull[slot], (q / (unsigned)nslots) & 1u);
             const double* buf = ring + (size_t)slot * stride;
 #pragma unroll
-            for (int c = 0; c < GS1_CPT; ++c) {
-              const int col = tid + PCW * c;
-              w[b][c] = col <= row ? buf[col] : 0.0;
+            for (int cg = 0; cg < GS1_CPT / 4; ++cg) {
+              if (cg < cgmax) {
+#pragma unroll
+                for (int c = cg * 4; c < cg * 4 + 4; ++c) {
+                  const int col = tid + PCW * c;
+                  w[b][c] = col <= row ? buf[col] : 0.0;
+                }
+              } else {
+#pragma unroll
+                for (int c = cg * 4; c < cg * 4 + 4; ++c) w[b][c] = 0.0;
+              }
             }
           } else {
 #pragma unroll
             for (int c = 0; c < GS1_CPT; ++c) w[b][c] = 0.0;
           }
         }
+        GPIS_LAP7(PCLK_PRECOMP);
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
@@ -614,16 +632,26 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
             if (i0 + b < my_rows) mbar_arrive(&rempty[(int)((wseq + (unsigned)(i0 + b)) % (unsigned)nslots)]);
         }
 #pragma unroll
-        for (int b = 0; b < PB; ++b) {
+        for (int cg = 0; cg < GS1_CPT / 4; ++cg) {
+          if (cg < cgmax) {
 #pragma unroll
-          for (int c = 0; c < GS1_CPT; ++c) p[b] += w[b][c] * s_kv[tid + PCW * c];
-          for (int o = 16; o > 0; o >>= 1) p[b] += __shfl_xor_sync(0xffffffffu, p[b], o);
+            for (int c = cg * 4; c < cg * 4 + 4; ++c) {
+              const double kv = s_kv[tid + PCW * c];
+#pragma unroll
+              for (int b = 0; b < PB; ++b) p[b] += w[b][c] * kv;
+            }
+          }
         }
+#pragma unroll
+        for (int b = 0; b < PB; ++b)
+          for (int o = 16; o > 0; o >>= 1) p[b] += __shfl_xor_sync(0xffffffffu, p[b], o);
         if (lane == 0) {
 #pragma unroll
           for (int b = 0; b < PB; ++b) s_red[par][b][warp] = p[b];
         }
+        GPIS_LAP7(PCLK_WAITFULL);
         named_sync(1, PCW);
+        GPIS_LAP7(PCLK_EPIREG);
         double ell[PB];
 #pragma unroll
         for (int b = 0; b < PB; ++b) {
@@ -637,9 +665,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           if (tid == b && i0 + b < my_rows) P.L[(long long)r0 * P.R_cap + cta + (i0 + b) * G] = ell[b];
         par ^= 1;
 #pragma unroll
-        for (int b = 0; b < PB; ++b)
+        for (int cg = 0; cg < GS1_CPT / 4; ++cg) {
+          if (cg < cgmax) {
 #pragma unroll
-          for (int c = 0; c < GS1_CPT; ++c) acc[c] += ell[b] * w[b][c];
+            for (int b = 0; b < PB; ++b)
+#pragma unroll
+              for (int c = cg * 4; c < cg * 4 + 4; ++c) acc[c] += ell[b] * w[b][c];
+          }
+        }
       }
       if (my_rows > 0) {
         double* yp = P.ypart + (long long)cta * GS1_RMAX + tid;
