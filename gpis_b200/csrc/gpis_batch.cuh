@@ -64,7 +64,9 @@ __device__ __forceinline__ void b_dmma(double& c0, double& c1, double a, double 
 // independent partial sums in the two triangular passes of the append).  Both forms are kept: the plain
 // one is the reference the tuned one is tested against (same picks; sums grouped differently).
 #define GPIS_BATCH_KERNEL_NAME k_batch_select
+#define GPIS_BATCH_BT 256
 #include "gpis_batch_kernel.inc"
+#undef GPIS_BATCH_BT
 #undef GPIS_BATCH_KERNEL_NAME
 
 // The update on the fp64 tensor pipe (opt-in, GPIS_BATCH_KERNEL=dmma; verified on the CPU emulation only so
@@ -74,15 +76,18 @@ __device__ __forceinline__ void b_dmma(double& c0, double& c1, double a, double 
 // loads are conflict-free without padding (there is no shared memory left to pad with).
 #define GPIS_BATCH_KERNEL_NAME k_batch_select_dmma
 #define GPIS_BATCH_DMMA 1
+#define GPIS_BATCH_BT 512      // 16 warps: more slices in flight, the tensor pipe overlaps other warps' epilogues
 #include "gpis_batch_kernel.inc"
+#undef GPIS_BATCH_BT
 #undef GPIS_BATCH_DMMA
 #undef GPIS_BATCH_KERNEL_NAME
+constexpr int BT_DMMA = 512;
 
 inline void launch_batch_select(const BatchParams& P, int n_blocks, int variant, cudaStream_t s) {
   auto k0 = k_batch_select<false>;
   auto k1 = k_batch_select<true>;
   auto k2 = k_batch_select_dmma<true>;
-  if (variant == 2) GPIS_LAUNCH_SMEM(k2, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
+  if (variant == 2) GPIS_LAUNCH_SMEM(k2, dim3((unsigned)n_blocks), dim3(BT_DMMA), BATCH_SMEM, s, P);
   else if (variant == 1) GPIS_LAUNCH_SMEM(k1, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
   else GPIS_LAUNCH_SMEM(k0, dim3((unsigned)n_blocks), dim3(BT), BATCH_SMEM, s, P);
 }
