@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const bool live = c * QKC + k < cnt;
           const int rr = (int)((rw[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
           s_rho[k * QBLK + ul] = (unsigned short)(live ? rr : 0);      // [k][unit]: conflict-free stores
-          s_cs[k * QBLK + ul] = live ? tv[k] : 0.0;
+          s_cs[k * QBLK + (ul ^ ((k & 3) << 2))] = live ? tv[k] : 0.0;      // (swizzled: see the MMA loop)
         }
         if (CUBE) s_uoff[ul] = (t % tiles_x) | ((t / tiles_x) % tiles_y) << 10 | (t / txy) << 20;      // tile indices
         else s_uoff[ul] = (((t / tiles_x) % tiles_y) * QT) | ((t % tiles_x) * QT) << 16;
@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
 #pragma unroll
         for (int k = 0; k < QKC; ++k) wv[k] = wrow[s_rho[k * QBLK + ul]];
 #pragma unroll
-        for (int k = 0; k < QKC; ++k) s_cs[k * QBLK + ul] *= wv[k];
+        for (int k = 0; k < QKC; ++k) s_cs[k * QBLK + (ul ^ ((k & 3) << 2))] *= wv[k];
       }
     };
     // producers: the 64 row copies of unit ul of the block at b0 (the unit's stage and phase follow from the
@@ -1032,7 +1032,9 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           const int gstage = (int)(q % NPIPE);
           mbar_wait(&gfull[gstage], (q / NPIPE) & 1u);
           const double* As = ring + (size_t)gstage * STAGE;
-          const double* cs = s_cs + ul;
+          // a k-step reads the coefficients of four consecutive rows of the unit: their column is XOR-swizzled by the
+          // row (rows are QBLK doubles = a whole number of bank cycles apart) so that the four land in different banks
+          const double* cs = s_cs + (ul ^ ((lane & 3) << 2));
 #if GPIS_EXP == 1      // experiment: the MMA loop runs twice (second time with zero coefficients): the rise is its cost
           for (int rep = 0; rep < 2; ++rep)
 #endif
