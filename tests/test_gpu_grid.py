@@ -192,6 +192,33 @@ def test_real_sdf_fixture_through_the_grid_backend(G):
     assert np.max(np.abs(gp3.var_pred_[:, 0] - (O.gp_var_diag(ref, q, Kx, False) + 0.05))) < 1e-8
 
 
+def test_gpis2d_host_class_matches_the_oracle_dense_fit(G):
+    """Gpis2D (src/grasp_selection/gpis.py:125-160 shape of the 2-D class): dense fit on scattered 2-D points, the grid of
+    its `dims` predicted at construction, predict_locations with the full covariance, surface_points, and the dimension
+    check -- against the oracle's create_gpis / gp_mean / gp_cov."""
+    from gpis_b200.sdf_io import Gpis2D
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0.0, 9.0, size=(120, 2))
+    y = np.hypot(X[:, 0] - 4.5, X[:, 1] - 4.0) - 3.0 + 0.01 * rng.standard_normal(120)
+    ell, noise = 2.0, 0.02
+    gp2 = Gpis2D(X, y, (10, 9), meas_variance=noise, kernel_hyps=(1.0, ell))
+    hyp = {"cov": np.array([np.log(ell), 0.0]), "mean": np.zeros(3), "lik": 0.5 * np.log(noise)}
+    ref = O.create_gpis(X, y, None, None, hyp)
+    q = gp2.grid_pts_
+    assert q.shape == (90, 2) and gp2.mean_sdf().shape == (10, 9) and gp2.variance().shape == (10, 9)
+    m_ref, _, Kx = O.gp_mean(ref, q, False)
+    assert np.max(np.abs(gp2.mean_pred_[:, 0] - m_ref)) < 1e-8
+    assert np.max(np.abs(gp2.var_pred_[:, 0] - (O.gp_var_diag(ref, q, Kx, False) + noise))) < 1e-8
+    m, c = gp2.predict_locations(q[:20], full_cov=True)
+    cov_ref = O.gp_cov(ref, q[:20], None, False)
+    assert np.max(np.abs(m[:, 0] - m_ref[:20])) < 1e-8
+    assert np.max(np.abs(c - (cov_ref + noise * np.eye(20)))) < 1e-8
+    sp = gp2.surface_points(0.3)
+    assert np.array_equal(sp, q[np.abs(m_ref) < 0.3]) and len(sp) > 0
+    with pytest.raises(ValueError):
+        Gpis2D(X, y, (10, 9, 2))
+
+
 def test_batch_of_independent_objects_matches_solo_runs(G):
     """Config 5 in miniature: a batch of independent small objects over a pool of engines/streams."""
     from gpis_b200.batch import select_batch, superellipsoid_tsdf
