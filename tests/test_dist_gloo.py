@@ -159,3 +159,11 @@ def test_balanced_slabs_partition_the_lattice():
     sizes = [z1 - z0 for z0, z1 in rs]
     assert sizes[0] > sizes[3] and sizes[-1] > sizes[4] and max(sizes) - min(sizes) <= 8
     assert [gdist.slab_range_balanced(32, r, 4, 100.0) for r in range(4)] == [gdist.slab_range(32, r, 4) for r in range(4)]
+    # cube-aligned cuts (the persistent kernel's 16 x 16 x 16 tiles): multiples of 16 when every rank can have 16 slices
+    for nz, world in ((128, 2), (128, 4), (128, 8), (100, 4), (96, 3)):
+        rs = [gdist.slab_range_balanced(nz, r, world, 4.0, align=16) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == nz and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert all(z1 - z0 >= 16 for z0, z1 in rs) and all(z0 % 16 == 0 for z0, _ in rs)
+    assert [gdist.slab_range_balanced(128, r, 8, 4.0, align=16) for r in range(8)] == [gdist.slab_range(128, r, 8) for r in range(8)]
+    # too few slices for that: the unaligned cuts stay
+    assert [gdist.slab_range_balanced(40, r, 4, 4.0, align=16) for r in range(4)] == [gdist.slab_range_balanced(40, r, 4, 4.0) for r in range(4)]
