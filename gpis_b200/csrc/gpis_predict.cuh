@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(PRED_THREADS, 2) k_predict_f64(PredictParams P
       if (more) { issue_A(c + 1, buf ^ 1); gen_B(c + 1, bnext); }
       const double* Ab = As + buf * PKC * PLDA + warp * 32 + (lane >> 2);
       const double* Bb = Bs + buf * PKC * PLDB + (lane >> 2);
+      // W = L^-1 is lower triangular: a chunk of columns k only reaches rows >= k, so in the super-block on the
+      // diagonal a warp skips the chunks beyond its last row (their tiles of Wt are zero) and leaves the pipe to the
+      // other warps / the SM's other CTA
+      if (c * PKC <= sb * PSB + warp * 32 + 31)
 #pragma unroll
       for (int k4 = 0; k4 < PKC / 4; ++k4) {
         const int kb = k4 * 4 + (lane & 3);
