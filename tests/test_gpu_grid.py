@@ -192,6 +192,33 @@ def test_real_sdf_fixture_through_the_grid_backend(G):
     assert np.max(np.abs(gp3.var_pred_[:, 0] - (O.gp_var_diag(ref, q, Kx, False) + 0.05))) < 1e-8
 
 
+def test_cube_tiles_with_per_point_noise_and_predictive_variance(G):
+    """The persistent kernel's 16 x 16 x 16 cubes on a lattice that ends in partial cubes (24 x 20 x 24), per-point
+    noise and the predictive-variance score (max_subset_buffers.cu:113-115: the cell's own noise joins the variance
+    before scoring) -- picks, model size and level-set masks against the oracle loop; the per-step kernels agree."""
+    from gpis_b200.synth import grid_points
+    dims = (24, 20, 24)
+    pts = grid_points(dims)
+    c = np.array([11.3, 9.6, 12.2])
+    tsdf = np.clip(np.linalg.norm((pts - c) * np.array([1.0, 1.2, 0.9]), axis=1) - 7.5, -3.0, 3.0)
+    rng = np.random.default_rng(11)
+    noise = 0.02 + 0.06 * rng.uniform(size=pts.shape[0])
+    hyp = {"cov": np.array([np.log(3.0), 0.0]), "mean": np.zeros(4), "lik": 0.5 * np.log(0.05)}
+    shape = {"points": pts, "tsdf": tsdf, "normals": None, "noise": noise}
+    tr = {"activeSetSize": 130, "beta": 10.0, "eps": 2e-2, "levelSet": 0.0, "predictiveVariance": True}
+    ora = O.select_straddle_incremental(shape, tr, 777, hyp=hyp, prune=False)
+    mdl, pred, _ = G.select_active_set(shape, tr, first_index=777, hyp=hyp, backend="grid", predict=False)
+    assert mdl.engine.stats()["kernel_launches"] < 40          # the persistent kernel ran (one launch per selection)
+    assert np.array_equal(mdl["order"], ora["order"]), first_divergence(mdl["order"], ora["order"])
+    assert mdl["n_in_model"] == ora["n_in_model"]
+    assert np.array_equal(pred["high"], ora["high"]) and np.array_equal(pred["low"], ora["low"])
+    eng = G.GpisEngine(3, pts.shape[0], 130, ell=3.0, noise=0.05, level=0.0, eps=2e-2, beta=10.0,
+                       variance_mode=G._lib.VAR_PREDICTIVE, loop_mode=G._lib.LOOP_STEPS)
+    eng.set_grid_candidates(dims, (0, 0, 0), (1, 1, 1), tsdf, noise=noise)
+    eng.select(777, 130)
+    assert np.array_equal(eng.active()[0], ora["order"])
+
+
 def test_gpis2d_host_class_matches_the_oracle_dense_fit(G):
     """Gpis2D (src/grasp_selection/gpis.py:125-160 shape of the 2-D class): dense fit on scattered 2-D points, the grid of
     its `dims` predicted at construction, predict_locations with the full covariance, surface_points, and the dimension
