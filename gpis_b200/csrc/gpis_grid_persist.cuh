@@ -688,6 +688,22 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
 
     // ------------------------------------------------------------------ C: d, g_new, new row of W
     {
+      // The sum of the CTAs' partial Y's for this thread's column does not depend on d: its loads go out together with
+      // those of |l|^2 and l.g (one L2 round trip instead of two), only the scaling by 1/d waits for the block sums.
+      const int nparts = min(G, r0);
+      const int gw = (cta * PTHREADS + tid) >> 5;      // (G * 12 warps x 4 columns >= 4096 rows: one pass)
+      const int sub = lane >> 2, cq = lane & 3;
+      const int c = gw * 4 + cq;
+      double a[24];
+      {
+        const double* yp = P.ypart + c;
+        // the CTAs' partials in a fixed order (bit-identical on every rank), 24 loads in flight
+#pragma unroll
+        for (int q = 0; q < 24; ++q) {
+          const int part = sub + 8 * q;
+          a[q] = (c < r0 && part < nparts) ? __ldcg(yp + (long long)part * GS1_RMAX) : 0.0;
+        }
+      }
       const double* X = P.L + (long long)r0 * P.R_cap;
       double p0 = 0.0, p1 = 0.0;
       for (int s0 = 0; s0 < r0; s0 += 8 * PTHREADS) {      // 16 loads in flight per thread
@@ -724,32 +740,16 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
           P.W[(long long)r0 * P.ldW + r0] = dinv;
         }
       }
+      double y = 0.0;
+#pragma unroll
+      for (int q = 0; q < 24; ++q) y += a[q];
+      if (c < r0)
+        for (int part = sub + 8 * 24; part < nparts; part += 8) y += __ldcg(P.ypart + c + (long long)part * GS1_RMAX);
+      y += __shfl_xor_sync(0xffffffffu, y, 4);
+      y += __shfl_xor_sync(0xffffffffu, y, 8);
+      y += __shfl_xor_sync(0xffffffffu, y, 16);
       __syncthreads();
-      const double dinv = s_fin[0];
-      const int nparts = min(G, r0);
-      const int gw = (cta * PTHREADS + tid) >> 5, nw = (G * PTHREADS) >> 5;
-      const int sub = lane >> 2, cq = lane & 3;
-      for (int c0 = gw * 4; c0 < r0; c0 += nw * 4) {
-        const int c = c0 + cq;
-        double y = 0.0;
-        if (c < r0) {
-          const double* yp = P.ypart + c;
-          // the CTAs' partials in a fixed order (bit-identical on every rank), 24 loads in flight
-          double a[24];
-#pragma unroll
-          for (int q = 0; q < 24; ++q) {
-            const int part = sub + 8 * q;
-            a[q] = part < nparts ? __ldcg(yp + (long long)part * GS1_RMAX) : 0.0;
-          }
-#pragma unroll
-          for (int q = 0; q < 24; ++q) y += a[q];
-          for (int part = sub + 8 * 24; part < nparts; part += 8) y += __ldcg(yp + (long long)part * GS1_RMAX);
-        }
-        y += __shfl_xor_sync(0xffffffffu, y, 4);
-        y += __shfl_xor_sync(0xffffffffu, y, 8);
-        y += __shfl_xor_sync(0xffffffffu, y, 16);
-        if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * dinv;
-      }
+      if (sub == 0 && c < r0) P.W[(long long)r0 * P.ldW + c] = -y * s_fin[0];
     }
     // (the row lists are final since the first barrier: the unit prefix of phase D is formed here, off its critical path)
     // exclusive prefix of the tiles' COSTS in unit times: their 32-row chunks (at least one: a tile's candidates are
