@@ -1162,7 +1162,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
         const int nseg = unit_owner((long long)s_pref[t2 + 1] - QEPI - 1, U, Gw) - g_first + 1;      // .. of its last chunk
         const int seg = cta - g_first;
         if (tid == 0) {
-          const unsigned long long tw0 = gtimer_ns();
+          const unsigned long long tw0 = (GPIS_EXP == 6) ? gtimer_ns() : 0ull;
           s_flag = spin_ge(&P.tile_cnt[t2], (unsigned)nseg, P, st) ? 1 : 0;
           if (GPIS_EXP == 6) dwait_ns += gtimer_ns() - tw0;      // per-CTA view: waiting for a shared tile's other contributors
         }
