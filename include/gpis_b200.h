@@ -304,14 +304,17 @@ gpis_status gpis_get_phase_timing(gpis_handle h, double* append_ms, double* main
 /* The persistent selection kernel's own lap timer (block 0, %globaltimer), summed over the steps of the
  * last gpis_select, ms: [0] winner / wait for the exchange records, [1] covariance of the winner with the model
  * rows, [2] W pass of the factor append, [3] grid barrier, [4] new row of W, [5] grid barrier, [6] unit prefix,
- * [7] update GEMM with the in-register epilogues of whole tiles, [8] epilogues of tiles shared between blocks,
+ * [7] update GEMM (3-D lattices: finished cubes are handed to the producer warps, whose epilogues run meanwhile;
+ *     1-D / 2-D lattices: with the in-register epilogues of whole tiles), [8] epilogues of tiles shared between blocks
+ *     + the wait for the producer warps' last epilogues,
  * [9] grid barrier, [10] winner reduction (+ record publication when sharded), [11] = number of steps (a count);
- * inside [7]: [12] coefficient precompute, [13] partial tiles to the workspace (store, fence, arrival), [14] in-register epilogues,
- * [15] = number of (tile, 32-row chunk) units all blocks processed (a count; x 2*64*64*32 = executed MMA flops).
+ * inside [7]: [12] coefficient precompute, [13] partial tiles to the workspace (store, fence, arrival), [14] whole tiles:
+ *     staging for the producer warps (3-D) or in-register epilogues, [15] = number of (tile, 32-row chunk) units all
+ *     blocks processed (a count; x 2*4096*32 = executed MMA flops: a tile is 4096 lattice points).
  * 16 doubles. */
 gpis_status gpis_get_persist_timing(gpis_handle h, double* ms16);
 /* Load balance of the persistent kernel's update phase in the last gpis_select: for every block, ms[2 b] = its time in
- * the phase (MMAs + epilogues), ms[2 b + 1] = of that, waiting for operand data; summed over the steps.  *n_blocks
+ * the phase (MMAs + epilogues), ms[2 b + 1] = reserved (0; experiment builds book a wait there); summed over the steps.  *n_blocks
  * receives the block count (ms may be NULL to query it); capacity = doubles available at ms. */
 gpis_status gpis_get_persist_balance(gpis_handle h, double* ms, int32_t capacity, int32_t* n_blocks);
 /* on != 0: gpis_select brackets every update-kernel launch with CUDA events on the launching
