@@ -36,7 +36,8 @@ if a.shape == "sphere":
 else:
     tsdf, nrm = box_tsdf(g)[1], None
 N = g ** 3
-z0, z1 = gdist.slab_range_balanced(g, rank, world, a.ell)
+# function-only models up to 4096 rows run the persistent kernel on 16 x 16 x 16 cubes: cube-aligned slab cuts
+z0, z1 = gdist.slab_range_balanced(g, rank, world, a.ell, align=1 if (a.gradients or a.active > 4096) else 16)
 lo, hi = g * g * z0, g * g * z1
 eng = GpisEngine(3, hi - lo, a.active, ell=a.ell, noise=0.05, level=0.0, eps=1e-2, beta=10.0,
                  use_gradients=a.gradients, rank=rank, world_size=world, total_candidates=N, id_base=lo, device=lr)
