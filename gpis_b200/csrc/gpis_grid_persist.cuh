@@ -73,6 +73,22 @@ constexpr double QCUT = 48.52030263919617;
 constexpr int QEPI = GPIS_QEPI;
 constexpr int QBLK = 128;                               // units whose coefficients sit in shared memory at a time
 
+// lattice index of the first point of fragment slot q (0 .. QPAIRS-1) of the tile at (tx, ty, tz)
+template <bool CUBE>
+__host__ __device__ inline long long persist_pair_index(int q, int tx, int ty, int tz, int nx, int ny) {
+  if (CUBE) {      // warp w holds z-slices 2w, 2w + 1 of the cube: fragment f = i * 2 + j, i = (jz & 1) * 2 + (jy >> 3), j = jx >> 3
+    const int l = q & 31, j = (q >> 5) & 1, i = (q >> 6) & 3, w = q >> 8;
+    const int jz = tz * QC + 2 * w + (i >> 1);
+    const int jy = ty * QC + (i & 1) * 8 + (l >> 2);
+    const int jx = tx * QC + j * 8 + (l & 3) * 2;
+    return (long long)jx + (long long)nx * (jy + (long long)ny * jz);
+  }
+  const int l = q & 31, j = (q >> 5) & 3, i = (q >> 7) & 1, w = q >> 8;
+  const int jy = ty * QT + (w >> 1) * 16 + i * 8 + (l >> 2);
+  const int jx = tx * QT + (w & 1) * 32 + j * 8 + (l & 3) * 2;
+  return (long long)jx + (long long)nx * (jy + (long long)ny * tz);
+}
+
 #ifndef GPIS_EMULATE
 #ifndef GPIS_EXP
 #define GPIS_EXP 0
@@ -235,22 +251,6 @@ __device__ __forceinline__ void persist_pairs(const int NP, const EngineParams& 
     if (g0 != f0 || g1 != f1)
       __stcg(reinterpret_cast<uchar2*>(P.flags) + tbase + q[k], make_uchar2((unsigned char)g0, (unsigned char)g1));
   }
-}
-
-// lattice index of the first point of fragment slot q (0 .. QPAIRS-1) of the tile at (tx, ty, tz)
-template <bool CUBE>
-__device__ __forceinline__ long long persist_pair_index(int q, int tx, int ty, int tz, int nx, int ny) {
-  if (CUBE) {      // warp w holds z-slices 2w, 2w + 1 of the cube: fragment f = i * 2 + j, i = (jz & 1) * 2 + (jy >> 3), j = jx >> 3
-    const int l = q & 31, j = (q >> 5) & 1, i = (q >> 6) & 3, w = q >> 8;
-    const int jz = tz * QC + 2 * w + (i >> 1);
-    const int jy = ty * QC + (i & 1) * 8 + (l >> 2);
-    const int jx = tx * QC + j * 8 + (l & 3) * 2;
-    return (long long)jx + (long long)nx * (jy + (long long)ny * jz);
-  }
-  const int l = q & 31, j = (q >> 5) & 3, i = (q >> 7) & 1, w = q >> 8;
-  const int jy = ty * QT + (w >> 1) * 16 + i * 8 + (l >> 2);
-  const int jx = tx * QT + (w & 1) * 32 + j * 8 + (l & 3) * 2;
-  return (long long)jx + (long long)nx * (jy + (long long)ny * tz);
 }
 
 // predictive-variance mode: the noise of the two cells of fragment slot q (padding cells are classified: not read)
