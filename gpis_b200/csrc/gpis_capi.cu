@@ -479,6 +479,7 @@ gpis_status gpis_create(gpis_handle* out, const gpis_config* cfg_in) {
       if (!coop || occp < 1) e->persist = false;
       // phase C of the persistent kernel sums the partial Y's with ONE column per thread group: every model row needs one
       if ((long long)e->num_sms * (PTHREADS / 32) * 4 < (long long)P.R_cap) e->persist = false;
+      if (e->num_sms > 32 * (PTHREADS / 32)) e->persist = false;      // its winner reduction: one record per lane of the CTA's warps
 #endif
       e->solve1_ctas = e->solve_ring ? e->num_sms - 1 : e->num_sms * 2;
       CU(dalloc(e, &P.ypart, (size_t)std::max(e->solve1_ctas, e->num_sms) * GS1_RMAX));

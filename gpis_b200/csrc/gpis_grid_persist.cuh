@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
   __shared__ double s_gram[PTHREADS / 32][2];
   __shared__ double s_fin[3];                             // dinv, g_new, ok
   __shared__ BlockBest s_bb[PTHREADS / 32];
+  __shared__ double s_wred[PTHREADS / 32][2];             // winner reduction: the warps' candidates' target and noise
   __shared__ unsigned long long s_sbar[4];                // cubes: accumulator staging tiles, full[2] / free[2]
   __shared__ int s_stile[2];                              // the tiles they hold
   __shared__ double s_next_aux[2];                        // its target and noise
@@ -1255,25 +1256,41 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_grid_persist(EngineParams P, in
     // ---- every CTA waits for all, then reduces the CTA winners itself: the same winner everywhere
     if (!grid_barrier(P, st, passed, &s_flag)) { if (tid == 0) persist_fail(st); return; }
     PSTAMP(PCLK_BAR3);
-    if (warp == 0) {
-      BlockBest b;
-      b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
-      double bt = 0.0, bn = 0.0;
-      for (int i = lane; i < G; i += 32) {
-        const BlockBest* pp = &P.partials[i];
-        const double ps = __ldcg(&pp->score);
-        const long long pid = __ldcg(&pp->id), ploc = __ldcg(&pp->local);
-        const double pt = __ldcg(&P.partials[G + i].score), pn = __ldcg(reinterpret_cast<const double*>(&P.partials[G + i].id));
-        if (ploc >= 0 && better(ps, pid, b.score, b.id)) { b.score = ps; b.id = pid; b.local = ploc; bt = pt; bn = pn; }
+    // one record per lane over the first ceil(G / 32) warps (ONE L2 round trip, not one per 32 records), a shuffle tree
+    // per warp, then the warps' bests in order: the same winner in every CTA
+    {
+      const int nwr = (G + 31) >> 5;
+      if (warp < nwr) {
+        BlockBest b;
+        b.score = NEG_INF; b.id = 0x7fffffffffffffffLL; b.local = -1;
+        double bt = 0.0, bn = 0.0;
+        const int i = warp * 32 + lane;
+        if (i < G) {
+          const BlockBest* pp = &P.partials[i];
+          const double ps = __ldcg(&pp->score);
+          const long long pid = __ldcg(&pp->id), ploc = __ldcg(&pp->local);
+          const double pt = __ldcg(&P.partials[G + i].score), pn = __ldcg(reinterpret_cast<const double*>(&P.partials[G + i].id));
+          if (ploc >= 0) { b.score = ps; b.id = pid; b.local = ploc; bt = pt; bn = pn; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
+          const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
+          const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
+          const double ot = __shfl_xor_sync(0xffffffffu, bt, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+          if (ol >= 0 && (b.local < 0 || better(os, oid, b.score, b.id))) { b.score = os; b.id = oid; b.local = ol; bt = ot; bn = on; }
+        }
+        if (lane == 0) { s_bb[warp] = b; s_wred[warp][0] = bt; s_wred[warp][1] = bn; }
       }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, b.score, o);
-        const long long oid = __shfl_xor_sync(0xffffffffu, b.id, o);
-        const long long ol = __shfl_xor_sync(0xffffffffu, b.local, o);
-        const double ot = __shfl_xor_sync(0xffffffffu, bt, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
-        if (ol >= 0 && better(os, oid, b.score, b.id)) { b.score = os; b.id = oid; b.local = ol; bt = ot; bn = on; }
+      __syncthreads();
+      if (tid == 0) {
+        BlockBest b = s_bb[0];
+        double bt = s_wred[0][0], bn = s_wred[0][1];
+        for (int w = 1; w < nwr; ++w)
+          if (s_bb[w].local >= 0 && (b.local < 0 || better(s_bb[w].score, s_bb[w].id, b.score, b.id))) {
+            b = s_bb[w]; bt = s_wred[w][0]; bn = s_wred[w][1];
+          }
+        s_next = b; s_next_aux[0] = bt; s_next_aux[1] = bn;
       }
-      if (lane == 0) { s_next = b; s_next_aux[0] = bt; s_next_aux[1] = bn; }
     }
     __syncthreads();
     if (cta == 0) {
