@@ -432,7 +432,11 @@ def run_ours(args):
                 "dense_equivalent_tflops": float(tot[2]) / args.steps / main_s / 1e12,
                 "whole_job_executed_tflops": exe_flops / s_dev / 1e12, "whole_job_frac": exe_flops / s_dev / 1e12 / tpeak,
                 "launches_per_step": 1, "timer": "in-kernel lap timer of block 0 (%globaltimer), rank 0",
-                "traffic": None, "traffic_note": "operands (axis-table rows, 12 MB) and the posterior state come from L2; see profiles/ for the ncu capture"})
+                "traffic": ncu_traffic("r02_k_grid_persist_full_ncu.csv") if (world == 1 and g == 128 and K == 4000) else None,
+                "traffic_note": ("DRAM bytes read + written by the ONE launch of the whole job (ncu --set full of the same kernel on "
+                                 "config 3, profiles/r02_k_grid_persist_full_ncu.csv: 78.9 GB + 46.4 GB, 4 % of the DRAM peak, L2 hit "
+                                 "86 %): the posterior state (34 B per lattice point and step = 285 GB per job) and W mostly stay in L2; "
+                                 "the kernel is bound by the fp64 pipe and its serial chain, not by HBM")})
     else:
         roof = None
     out = {
